@@ -1,0 +1,562 @@
+"""BM25 index served from the GPU, behind the reference's ``BM25Index`` /
+``PersistentBM25Index`` interface (reference radiant/storage/bm25_index.py).
+
+Host side (this file, Python like the reference): tokenizer :50-58, the document /
+df / idf bookkeeping of ``_rebuild_index`` :100-137, ``add_document`` :139-180 (with its
+stale-idf behaviour: an incremental add only refreshes the idf of the new document's
+own terms), ``remove_document`` :182-216, JSON round trip :275-327 and the persistent,
+thread-safe wrapper :330-709.
+
+Device side (``Bm25DeviceIndex``): a tile-sharded inverted CSR with one float64 impact
+per posting; ``search`` of :218-270 becomes ``rr_bm25_topk``.  The device index is a
+derived cache: it is rebuilt lazily from the host bookkeeping after any mutation
+(idf/avgdl are COPIED from the host tables, never recomputed on device - SURVEY.md R7).
+"""
+
+from __future__ import annotations
+
+import gzip
+import json
+import logging
+import os
+import threading
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Sequence, Set, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .base import StoredDoc
+from .index import _stream, to_device
+
+logger = logging.getLogger(__name__)
+
+_INDEX_EXTENSIONS = (".json.gz", ".pickle", ".json", ".pkl")
+
+
+def _normalize_index_path(path: Path) -> Path:
+    """Strip a known index extension so paths with and without one name the same files."""
+    name = path.name
+    for ext in _INDEX_EXTENSIONS:  # longest first
+        if name.endswith(ext):
+            return path.parent / name[: -len(ext)]
+    return path
+
+
+def _tokenize(text: str) -> List[str]:
+    """lower-case, every non-alphanumeric character becomes a separator, tokens of
+    length <= 1 are dropped (Unicode-aware ``str.isalnum``)."""
+    out: List[str] = []
+    cur: List[str] = []
+    for ch in text.lower():
+        if ch.isalnum():
+            cur.append(ch)
+        elif cur:
+            if len(cur) > 1:
+                out.append("".join(cur))
+            cur = []
+    if len(cur) > 1:
+        out.append("".join(cur))
+    return out
+
+
+class Bm25DeviceIndex:
+    """Tile-sharded inverted CSR + per-posting float64 impacts in HBM (one shard).
+
+    tile t owns rows [t*tile_docs, (t+1)*tile_docs); postings are sorted by
+    (tile, term, row):
+        tile_term_ptr int64 [n_tiles, n_terms+1]
+        post_row      int32 [P]   (read as uint32 by the kernel)
+        post_impact   f64   [P]   idf_t * (tf*(k1+1)) / (tf + k1*((1-b) + (b*len)/avgdl))
+    """
+
+    def __init__(self, device: torch.device, n_docs: int, n_terms: int, tile_docs: int,
+                 tile_term_ptr: torch.Tensor, post_row: torch.Tensor, post_impact: torch.Tensor,
+                 row_base: int = 0) -> None:
+        self.device = device
+        self.n_docs = n_docs
+        self.n_terms = n_terms
+        self.tile_docs = tile_docs
+        self.n_tiles = int(tile_term_ptr.shape[0]) if n_docs else 0
+        self.tile_term_ptr = tile_term_ptr
+        self.post_row = post_row
+        self.post_impact = post_impact
+        self.row_base = row_base
+
+    @property
+    def n_postings(self) -> int:
+        return int(self.post_row.numel())
+
+    @classmethod
+    def build(
+        cls,
+        doc_ptr,
+        doc_terms,
+        n_terms: int,
+        idf,
+        avgdl: float,
+        k1: float,
+        b: float,
+        device=0,
+        tile_docs: int = 8192,
+        row_base: int = 0,
+        doc_len=None,
+    ) -> "Bm25DeviceIndex":
+        """doc_ptr int64 [N+1] / doc_terms int32 [T]: the documents of THIS shard as CSR of
+        term ids; idf f64 [n_terms] (0 for unknown terms), avgdl, k1, b: global tables
+        copied from the host index.  doc_len int32 [N] overrides diff(doc_ptr) (the
+        reference keeps ``doc_lengths`` separately).  Sorting / counting uses torch on the
+        device (index build is not the hot path); impacts come from rr_bm25_impacts."""
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        _lib.init(dev.index or 0)
+        ptr = to_device(doc_ptr, dev, torch.int64)
+        terms = to_device(doc_terms, dev, torch.int64)
+        n = int(ptr.numel() - 1)
+        v = int(n_terms)
+        if n <= 0 or v <= 0 or terms.numel() == 0:
+            z64 = torch.zeros((1, max(v, 0) + 1), dtype=torch.int64, device=dev)
+            return cls(dev, 0, v, tile_docs, z64, torch.zeros(0, dtype=torch.int32, device=dev),
+                       torch.zeros(0, dtype=torch.float64, device=dev), row_base)
+        lens = ptr[1:] - ptr[:-1]
+        dlen = lens.to(torch.int32) if doc_len is None else to_device(doc_len, dev, torch.int32)
+        n_tiles = (n + tile_docs - 1) // tile_docs
+        rows = torch.repeat_interleave(torch.arange(n, dtype=torch.int64, device=dev), lens)
+        # key = (tile * V + term) * tile_docs + row_in_tile  -> sorted by (tile, term, row)
+        key = ((rows // tile_docs) * v + terms) * tile_docs + (rows % tile_docs)
+        del rows, terms
+        key, _ = torch.sort(key)
+        ukey, tf = torch.unique_consecutive(key, return_counts=True)
+        del key
+        tt = ukey // tile_docs  # tile * V + term
+        post_row64 = (tt // v) * tile_docs + (ukey % tile_docs)
+        term = tt % v
+        counts = torch.bincount(tt, minlength=n_tiles * v)
+        csum = torch.zeros(n_tiles * v + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=csum[1:])
+        del counts, tt, ukey
+        gather = (torch.arange(n_tiles, dtype=torch.int64, device=dev)[:, None] * v
+                  + torch.arange(v + 1, dtype=torch.int64, device=dev)[None, :])
+        tile_term_ptr = csum[gather].contiguous()
+        del gather, csum
+        idf_t = to_device(idf, dev, torch.float64)
+        post_idf = idf_t[term].contiguous()
+        post_len = dlen[post_row64].contiguous()
+        post_tf = tf.to(torch.int32).contiguous()
+        post_impact = torch.empty(post_tf.shape, dtype=torch.float64, device=dev)
+        _lib.call("rr_bm25_impacts", post_tf.data_ptr(), post_len.data_ptr(), post_idf.data_ptr(),
+                  post_tf.numel(), float(k1), float(b), float(avgdl), post_impact.data_ptr(), _stream())
+        post_row = post_row64.to(torch.int32).contiguous()
+        torch.cuda.current_stream().synchronize()  # temporaries die here
+        return cls(dev, n, v, tile_docs, tile_term_ptr, post_row, post_impact, row_base)
+
+    def search_batch(self, q_terms, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """q_terms int32 [Q, L] term ids in query-token order, -1 = unknown / padding.
+        -> (idx int64 [Q,k] (-1 padded), score f64 [Q,k], count int32 [Q]);
+        order (score desc, row asc), score > 0 only."""
+        if torch.cuda.current_device() != (self.device.index or 0):
+            torch.cuda.set_device(self.device)
+        qt = to_device(q_terms, self.device, torch.int32)
+        if qt.ndim == 1:
+            qt = qt[None, :]
+        q, ql = qt.shape
+        score = torch.empty((q, k), dtype=torch.float64, device=self.device)
+        idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        count = torch.empty((q,), dtype=torch.int32, device=self.device)
+        lib = _lib.load()
+        ws_bytes = lib.rr_bm25_topk_workspace_bytes(self.n_tiles, q, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        _lib.call("rr_bm25_topk", self.tile_term_ptr.data_ptr(), self.post_row.data_ptr(),
+                  self.post_impact.data_ptr(), self.n_tiles, self.tile_docs, self.n_terms, self.n_docs,
+                  qt.data_ptr(), q, ql, k, self.row_base, score.data_ptr(), idx.data_ptr(),
+                  count.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+        return idx, score, count
+
+
+class BM25Index:
+    """Host bookkeeping with the reference's attribute names; ``search`` runs on the GPU.
+
+    Attributes kept for callers that reach in (reference orchestrator / persistent
+    wrapper): doc_ids, doc_tokens, doc_id_set, doc_id_to_idx, k1, b, avgdl, doc_lengths,
+    idf, term_doc_freqs, dirty, needs_rebuild.
+    """
+
+    def __init__(
+        self,
+        doc_ids: Optional[List[str]] = None,
+        doc_tokens: Optional[List[List[str]]] = None,
+        k1: float = 1.5,
+        b: float = 0.75,
+        needs_rebuild: bool = True,
+        device: int = 0,
+        tile_docs: int = 8192,
+    ) -> None:
+        self.doc_ids: List[str] = list(doc_ids or [])
+        self.doc_tokens: List[List[str]] = list(doc_tokens or [])
+        self.doc_id_set: Set[str] = set(self.doc_ids)
+        self.doc_id_to_idx: Dict[str, int] = {d: i for i, d in enumerate(self.doc_ids)}
+        self.k1 = k1
+        self.b = b
+        self.avgdl = 0.0
+        self.doc_lengths: List[int] = []
+        self.idf: Dict[str, float] = {}
+        self.term_doc_freqs: Dict[str, int] = {}
+        self.dirty = False
+        self.needs_rebuild = needs_rebuild
+        self._device = device
+        self._tile_docs = tile_docs
+        self._vocab: Dict[str, int] = {}
+        self._doc_term_ids: List[np.ndarray] = []
+        self._gpu: Optional[Bm25DeviceIndex] = None
+        self._gpu_params: Tuple[float, float] = (k1, b)
+        for toks in self.doc_tokens:
+            self._doc_term_ids.append(self._term_ids(toks, create=True))
+        if self.doc_ids and self.needs_rebuild:
+            self._rebuild_index()
+
+    # ---- vocabulary -----------------------------------------------------------------
+    def _term_ids(self, tokens: Sequence[str], create: bool) -> np.ndarray:
+        vocab = self._vocab
+        if create:
+            return np.fromiter((vocab.setdefault(t, len(vocab)) for t in tokens), dtype=np.int32,
+                               count=len(tokens))
+        return np.fromiter((vocab.get(t, -1) for t in tokens), dtype=np.int32, count=len(tokens))
+
+    # ---- bookkeeping (same arithmetic as the reference) --------------------------------
+    def _rebuild_index(self) -> None:
+        self._gpu = None
+        if not self.doc_ids:
+            self.avgdl = 0.0
+            self.doc_lengths = []
+            self.idf = {}
+            self.term_doc_freqs = {}
+            self.needs_rebuild = False
+            return
+        self.doc_id_set = set(self.doc_ids)
+        self.doc_id_to_idx = {d: i for i, d in enumerate(self.doc_ids)}
+        self.doc_lengths = [len(t) for t in self.doc_tokens]
+        self.avgdl = sum(self.doc_lengths) / len(self.doc_lengths) if self.doc_lengths else 0.0
+        df: Dict[str, int] = {}
+        for toks in self.doc_tokens:
+            for t in set(toks):
+                df[t] = df.get(t, 0) + 1
+        self.term_doc_freqs = df
+        n = len(self.doc_ids)
+        self.idf = {t: np.log((n - d + 0.5) / (d + 0.5) + 1.0) for t, d in df.items()}
+        self.needs_rebuild = False
+
+    def add_document(self, doc_id: str, tokens: List[str]) -> bool:
+        if doc_id in self.doc_id_set:
+            return False
+        self.doc_ids.append(doc_id)
+        self.doc_tokens.append(tokens)
+        self._doc_term_ids.append(self._term_ids(tokens, create=True))
+        self.doc_id_set.add(doc_id)
+        self.doc_id_to_idx[doc_id] = len(self.doc_ids) - 1
+        self.doc_lengths.append(len(tokens))
+        n = len(self.doc_ids)
+        self.avgdl = (self.avgdl * (n - 1) + len(tokens)) / n
+        # only the new document's own terms get a fresh idf (with the current n)
+        for t in set(tokens):
+            d = self.term_doc_freqs.get(t, 0) + 1
+            self.term_doc_freqs[t] = d
+            self.idf[t] = np.log((n - d + 0.5) / (d + 0.5) + 1.0)
+        self.dirty = True
+        self._gpu = None
+        return True
+
+    def remove_document(self, doc_id: str) -> bool:
+        if doc_id not in self.doc_id_set:
+            return False
+        i = self.doc_id_to_idx.pop(doc_id)
+        del self.doc_ids[i]
+        del self.doc_tokens[i]
+        del self._doc_term_ids[i]
+        self.doc_id_set.discard(doc_id)
+        for other, j in self.doc_id_to_idx.items():
+            if j > i:
+                self.doc_id_to_idx[other] = j - 1
+        self.needs_rebuild = True
+        self.dirty = True
+        self._gpu = None
+        return True
+
+    # ---- device index ---------------------------------------------------------------
+    def device_index(self) -> Bm25DeviceIndex:
+        """Build (or reuse) the GPU index from the CURRENT host tables."""
+        if self.needs_rebuild:
+            self._rebuild_index()
+        if self._gpu is not None and self._gpu_params == (self.k1, self.b):
+            return self._gpu
+        lens = np.fromiter((a.size for a in self._doc_term_ids), dtype=np.int64,
+                           count=len(self._doc_term_ids))
+        ptr = np.zeros(lens.size + 1, dtype=np.int64)
+        np.cumsum(lens, out=ptr[1:])
+        terms = (np.concatenate(self._doc_term_ids) if self._doc_term_ids
+                 else np.zeros(0, dtype=np.int32))
+        v = len(self._vocab)
+        idf = np.zeros(v, dtype=np.float64)
+        for t, val in self.idf.items():
+            tid = self._vocab.get(t)
+            if tid is not None:
+                idf[tid] = float(val)
+        self._gpu = Bm25DeviceIndex.build(
+            ptr, terms, v, idf, float(self.avgdl), float(self.k1), float(self.b), device=self._device,
+            tile_docs=self._tile_docs, doc_len=np.asarray(self.doc_lengths, dtype=np.int32))
+        self._gpu_params = (self.k1, self.b)
+        return self._gpu
+
+    def _query_term_ids(self, query_tokens: Sequence[str]) -> np.ndarray:
+        ids = self._term_ids(query_tokens, create=False)
+        # "if term not in self.idf: continue" - a vocabulary term whose idf was dropped by a
+        # rebuild (all its documents removed) is unknown too
+        for i, t in enumerate(query_tokens):
+            if ids[i] >= 0 and t not in self.idf:
+                ids[i] = -1
+        return ids
+
+    def search_batch(self, queries_tokens: Sequence[Sequence[str]], top_k: int
+                     ) -> List[List[Tuple[str, float]]]:
+        if self.needs_rebuild:
+            self._rebuild_index()
+        nq = len(queries_tokens)
+        if not self.doc_ids or nq == 0:
+            return [[] for _ in range(nq)]
+        width = max(1, max(len(q) for q in queries_tokens))
+        qt = np.full((nq, width), -1, dtype=np.int32)
+        for i, toks in enumerate(queries_tokens):
+            if toks:
+                qt[i, : len(toks)] = self._query_term_ids(toks)
+        k = max(1, min(int(top_k), _lib.RR_MAX_K))
+        idx, score, count = self.device_index().search_batch(qt, k)
+        idx_h, score_h, count_h = idx.cpu().tolist(), score.cpu().tolist(), count.cpu().tolist()
+        out: List[List[Tuple[str, float]]] = []
+        for i in range(nq):
+            m = min(count_h[i], top_k)
+            out.append([(self.doc_ids[r], float(s)) for r, s in zip(idx_h[i][:m], score_h[i][:m])])
+        return out
+
+    def search(self, query_tokens: List[str], top_k: int) -> List[Tuple[str, float]]:
+        """[(doc_id, score)] by (score desc, row asc); scores are the reference's float64
+        values bit for bit."""
+        if not query_tokens or top_k <= 0:
+            return []
+        return self.search_batch([query_tokens], top_k)[0]
+
+    def __len__(self) -> int:
+        return len(self.doc_ids)
+
+    # ---- serialisation (same JSON schema as the reference, version 2) -----------------------
+    def to_dict(self) -> Dict[str, Any]:
+        return {"version": 2, "doc_ids": self.doc_ids, "doc_tokens": self.doc_tokens,
+                "k1": self.k1, "b": self.b}
+
+    @classmethod
+    def from_dict(cls, data: Dict[str, Any], device: int = 0) -> "BM25Index":
+        index = cls(doc_ids=data.get("doc_ids", []), doc_tokens=data.get("doc_tokens", []),
+                    k1=data.get("k1", 1.5), b=data.get("b", 0.75), needs_rebuild=True, device=device)
+        if index.doc_ids and index.needs_rebuild:
+            index._rebuild_index()
+        return index
+
+    @classmethod
+    def from_reference(cls, ref_index, device: int = 0, tile_docs: int = 8192) -> "BM25Index":
+        """Adopt a live reference ``BM25Index`` INCLUDING its current idf / avgdl / df tables
+        (they may be stale after incremental adds; they are copied, not recomputed)."""
+        inst = cls(doc_ids=list(ref_index.doc_ids), doc_tokens=list(ref_index.doc_tokens),
+                   k1=ref_index.k1, b=ref_index.b, needs_rebuild=False, device=device,
+                   tile_docs=tile_docs)
+        inst.avgdl = float(ref_index.avgdl)
+        inst.doc_lengths = list(ref_index.doc_lengths)
+        inst.idf = dict(ref_index.idf)
+        inst.term_doc_freqs = dict(ref_index.term_doc_freqs)
+        inst.needs_rebuild = bool(ref_index.needs_rebuild)
+        return inst
+
+
+class PersistentBM25Index:
+    """Thread-safe, persistent wrapper with the reference's method set
+    (reference bm25_index.py:330-709); ``search`` hydrates ``StoredDoc``s from the store."""
+
+    def __init__(self, config: Any, store: Any, device: int = 0) -> None:
+        self._config = config
+        self._store = store
+        self._device = device
+        self._lock = threading.RLock()
+        self._index: Optional[BM25Index] = None
+        self._unsaved_count = 0
+        Path(config.index_path).parent.mkdir(parents=True, exist_ok=True)
+
+    def _paths(self) -> Tuple[Path, Path]:
+        base = _normalize_index_path(Path(self._config.index_path))
+        return base.with_suffix(".json.gz"), base.with_suffix(".tmp.gz")
+
+    def _load_or_create_index(self) -> BM25Index:
+        json_path, _ = self._paths()
+        if json_path.exists():
+            try:
+                with gzip.open(json_path, "rt", encoding="utf-8") as f:
+                    data = json.load(f)
+                index = BM25Index.from_dict(data, device=self._device)
+                index.k1 = self._config.k1
+                index.b = self._config.b
+                logger.info(f"Loaded BM25 index (JSON) with {len(index)} documents")
+                return index
+            except Exception as e:
+                logger.warning(f"Failed to load JSON BM25 index: {e}")
+        # legacy pickle files of the reference hold reference-class instances; they are
+        # migrated by the reference itself, not unpickled here (out of scope, security)
+        return BM25Index(k1=self._config.k1, b=self._config.b, device=self._device)
+
+    @property
+    def index(self) -> BM25Index:
+        if self._index is None:
+            with self._lock:
+                if self._index is None:
+                    self._index = self._load_or_create_index()
+        return self._index
+
+    def save(self) -> bool:
+        with self._lock:
+            if self._index is None or not self._index.dirty:
+                return True
+            json_path, tmp_path = self._paths()
+            try:
+                with gzip.open(tmp_path, "wt", encoding="utf-8") as f:
+                    json.dump(self._index.to_dict(), f, separators=(",", ":"))
+                os.replace(tmp_path, json_path)
+                self._index.dirty = False
+                self._unsaved_count = 0
+                return True
+            except Exception as e:
+                logger.error(f"Failed to save BM25 index: {e}")
+                try:
+                    if tmp_path.exists():
+                        tmp_path.unlink()
+                except Exception:
+                    pass
+                return False
+
+    def _maybe_auto_save(self) -> None:
+        if self._unsaved_count >= self._config.auto_save_threshold:
+            self.save()
+
+    def add_document(self, doc_id: str, content: str) -> bool:
+        tokens = _tokenize(content)
+        if not tokens:
+            return False
+        with self._lock:
+            added = self.index.add_document(doc_id, tokens)
+            if added:
+                self._unsaved_count += 1
+                self._maybe_auto_save()
+            return added
+
+    def add_documents_batch(self, documents: List[Tuple[str, str]]) -> int:
+        added = 0
+        with self._lock:
+            for doc_id, content in documents:
+                tokens = _tokenize(content)
+                if tokens and self.index.add_document(doc_id, tokens):
+                    added += 1
+            if added:
+                self._unsaved_count += added
+                self._maybe_auto_save()
+        return added
+
+    def remove_document(self, doc_id: str) -> bool:
+        with self._lock:
+            removed = self.index.remove_document(doc_id)
+            if removed:
+                self._unsaved_count += 1
+                self._maybe_auto_save()
+            return removed
+
+    def _hydrate(self, results: List[Tuple[str, float]]) -> List[Tuple[StoredDoc, float]]:
+        out: List[Tuple[StoredDoc, float]] = []
+        for doc_id, score in results:
+            doc = self._store.get_doc(doc_id)
+            if doc is not None:  # documents missing from the store are dropped silently
+                out.append((doc, score))
+        return out
+
+    def search(self, query: str, top_k: int) -> List[Tuple[StoredDoc, float]]:
+        tokens = _tokenize(query)
+        if not tokens:
+            return []
+        with self._lock:
+            results = self.index.search(tokens, top_k)
+        return self._hydrate(results)
+
+    def search_batch(self, queries: List[str], top_k: int) -> List[List[Tuple[StoredDoc, float]]]:
+        """New batched surface: one kernel launch for all queries."""
+        toks = [_tokenize(q) for q in queries]
+        with self._lock:
+            results = self.index.search_batch(toks, top_k)
+        return [self._hydrate(r) for r in results]
+
+    def build_from_store(self, limit: int = 0) -> int:
+        max_docs = limit or self._config.max_documents
+        doc_ids = self._store.list_doc_ids_with_embeddings(limit=max_docs)
+        documents: List[Tuple[str, str]] = []
+        for doc_id in doc_ids:
+            doc = self._store.get_doc(doc_id)
+            if doc and doc.content:
+                documents.append((doc_id, doc.content))
+        with self._lock:
+            self._index = BM25Index(k1=self._config.k1, b=self._config.b, device=self._device)
+            for doc_id, content in documents:
+                tokens = _tokenize(content)
+                if tokens:
+                    self._index.add_document(doc_id, tokens)  # incremental path, as the reference
+            self._index.dirty = True
+            self.save()
+        return len(self._index)
+
+    def sync_with_store(self) -> Tuple[int, int]:
+        store_ids = set(self._store.list_doc_ids_with_embeddings(limit=self._config.max_documents))
+        with self._lock:
+            index_ids = set(self.index.doc_ids)
+            removed = sum(1 for d in index_ids - store_ids if self.index.remove_document(d))
+            added = 0
+            for doc_id in store_ids - index_ids:
+                doc = self._store.get_doc(doc_id)
+                if doc and doc.content:
+                    tokens = _tokenize(doc.content)
+                    if tokens and self.index.add_document(doc_id, tokens):
+                        added += 1
+            if added or removed:
+                self._index.dirty = True
+                self.save()
+        return added, removed
+
+    def clear(self) -> None:
+        with self._lock:
+            self._index = BM25Index(k1=self._config.k1, b=self._config.b, device=self._device)
+            self._unsaved_count = 0
+            json_path, _ = self._paths()
+            for p in (json_path, json_path.with_name(json_path.name.replace(".json.gz", ".pkl"))):
+                if p.exists():
+                    try:
+                        p.unlink()
+                    except Exception as e:
+                        logger.warning(f"Failed to delete index file {p}: {e}")
+
+    def __len__(self) -> int:
+        return len(self.index)
+
+    def get_stats(self) -> Dict[str, Any]:
+        with self._lock:
+            idx = self.index
+            json_path, _ = self._paths()
+            return {
+                "document_count": len(idx),
+                "unique_terms": len(idx.idf),
+                "avg_doc_length": idx.avgdl,
+                "k1": idx.k1,
+                "b": idx.b,
+                "dirty": idx.dirty,
+                "needs_rebuild": idx.needs_rebuild,
+                "index_path": str(json_path),
+                "storage_format": "json.gz" if json_path.exists() else "json.gz (pending)",
+            }

@@ -1,0 +1,361 @@
+// R3: stage-2 rescoring of the stage-1 candidates.
+//
+// Replaces rescore_candidates (reference radiant/storage/quantization.py:185-222) and
+// the caller's cut + threshold (radiant/storage/redis_store.py:850-854):
+//   score_c = float32(dot(q_f32, float32(row_c)));  stable sort by score desc;
+//   keep the first top_k, then those with score >= min_similarity.
+//
+// One CTA per query.  Candidate rows are different for every query, so this is a
+// batched gather + GEMV (HBM-bound), not a GEMM: each warp streams one
+// candidate row with 128-bit loads, accumulates the products in float64 (every
+// f32*f32 and f32*int8 product is exact in double, so the sum is the correctly
+// rounded dot product up to one final rounding to float32), and the CTA orders the
+// (score, position) keys with a shared-memory bitonic sort.
+// Algorithmic bytes: q * c * dim * sizeof(row element) + q * dim * 4.
+#include <math.h>
+
+#include "common.cuh"
+#include "select.cuh"
+
+namespace rr {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i32(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// dot(q (shared, f32), row (global f32)) in float64, fixed summation order
+__device__ __forceinline__ double dot_f32_row(const float* sq, const float* row, int dim, int lane) {
+  double acc = 0.0;
+  if ((dim & 3) == 0) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    const float4* q4 = reinterpret_cast<const float4*>(sq);
+    for (int v = lane; v < (dim >> 2); v += 32) {
+      const float4 e = __ldg(r4 + v);
+      const float4 w = q4[v];
+      acc += (double)w.x * (double)e.x;
+      acc += (double)w.y * (double)e.y;
+      acc += (double)w.z * (double)e.z;
+      acc += (double)w.w * (double)e.w;
+    }
+  } else {
+    for (int d = lane; d < dim; d += 32) acc += (double)sq[d] * (double)__ldg(row + d);
+  }
+  return warp_sum_f64(acc);
+}
+
+__device__ __forceinline__ double dot_i8_row(const float* sq, const int8_t* row, int dim, int lane) {
+  double acc = 0.0;
+  if ((dim & 3) == 0) {
+    // lane-contiguous 4-byte groups: 128 B per warp request, query read as float4 (conflict-free)
+    const int* r4 = reinterpret_cast<const int*>(row);
+    const float4* q4 = reinterpret_cast<const float4*>(sq);
+    for (int v = lane; v < (dim >> 2); v += 32) {
+      const int e = __ldg(r4 + v);
+      const float4 w = q4[v];
+      acc += (double)w.x * (double)(int)(signed char)(e & 0xFF);
+      acc += (double)w.y * (double)(int)(signed char)((e >> 8) & 0xFF);
+      acc += (double)w.z * (double)(int)(signed char)((e >> 16) & 0xFF);
+      acc += (double)w.w * (double)(int)(signed char)((e >> 24) & 0xFF);
+    }
+  } else {
+    for (int d = lane; d < dim; d += 32) acc += (double)sq[d] * (double)(int)__ldg(row + d);
+  }
+  return warp_sum_f64(acc);
+}
+
+struct RescoreArgs {
+  const float* queries;
+  int dim;
+  const void* emb;
+  long long n;
+  long long row_base;
+  const long long* cand_idx;
+  int c;
+  int top_k;
+  double min_similarity;
+  float* out_score;
+  long long* out_idx;
+  int* out_count;
+};
+
+// Bitonic sort of p u64 keys ascending in shared memory.
+__device__ __forceinline__ void block_bitonic_sort_u64(u64* keys, int p) {
+  for (int size = 2; size <= p; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (p >> 1); t += RS_THREADS) {
+        const int i = ((t / stride) * (stride << 1)) + (t % stride);
+        const int j = i + stride;
+        const bool asc = ((i & size) == 0);
+        const u64 x = keys[i], y = keys[j];
+        if ((x > y) == asc) {
+          keys[i] = y;
+          keys[j] = x;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// keys[] hold (~orderable(score) << 32 | position) for valid candidates; sorts them and
+// writes the reference's cut + filter.
+__device__ __forceinline__ void rank_and_write_f32(u64* keys, int c, int p, const long long* cand,
+                                                   int top_k, double min_sim, float* out_score,
+                                                   long long* out_idx, int* out_count, int* s_cnt) {
+  for (int i = c + threadIdx.x; i < p; i += RS_THREADS) keys[i] = K1_INVALID;
+  if (threadIdx.x == 0) *s_cnt = 0;
+  __syncthreads();
+  block_bitonic_sort_u64(keys, p);
+  // scores are descending, so the entries >= min_sim form a prefix of the first top_k
+  for (int j = threadIdx.x; j < top_k; j += RS_THREADS) {
+    bool have = false;
+    float s = 0.0f;
+    long long id = -1;
+    if (j < c) {
+      const u64 key = keys[j];
+      if (key != K1_INVALID) {
+        s = f32_from_orderable(~(u32)(key >> 32));
+        if ((double)s >= min_sim) {
+          have = true;
+          id = cand[(u32)key];
+        }
+      }
+    }
+    out_score[j] = have ? s : 0.0f;
+    out_idx[j] = have ? id : -1;
+    if (have) atomicAdd(s_cnt, 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && out_count) *out_count = *s_cnt;
+}
+
+// MODE 0: full rescore (score, sort, cut, filter).  MODE 1: scores only.
+template <int EMB, int MODE>
+__global__ void __launch_bounds__(RS_THREADS) rescore_f32_kernel(const RescoreArgs a, int p) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  float* sq = reinterpret_cast<float*>(rs_smem);
+  u64* keys = reinterpret_cast<u64*>(rs_smem + align_up_dev((size_t)a.dim * 4));
+  __shared__ int s_cnt;
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = threadIdx.x; d < a.dim; d += RS_THREADS) sq[d] = a.queries[(size_t)q * a.dim + d];
+  __syncthreads();
+  const long long* cand = a.cand_idx + (size_t)q * a.c;
+  for (int ci = warp; ci < a.c; ci += RS_WARPS) {
+    const long long idx = cand[ci];
+    const long long local = idx - a.row_base;
+    const bool valid = idx >= 0 && local >= 0 && local < a.n;
+    float s = -INFINITY;
+    if (valid) {
+      double acc;
+      if (EMB == RR_F32)
+        acc = dot_f32_row(sq, reinterpret_cast<const float*>(a.emb) + (size_t)local * a.dim, a.dim, lane);
+      else
+        acc = dot_i8_row(sq, reinterpret_cast<const int8_t*>(a.emb) + (size_t)local * a.dim, a.dim, lane);
+      s = (float)acc;
+    }
+    if (lane == 0) {
+      if (MODE == 0)
+        keys[ci] = valid ? (((u64)(~f32_orderable(s)) << 32) | (u64)(u32)ci) : K1_INVALID;
+      else
+        a.out_score[(size_t)q * a.c + ci] = s;
+    }
+  }
+  if (MODE == 0) {
+    __syncthreads();
+    rank_and_write_f32(keys, a.c, p, cand, a.top_k, a.min_similarity,
+                       a.out_score + (size_t)q * a.top_k, a.out_idx + (size_t)q * a.top_k,
+                       a.out_count ? a.out_count + q : nullptr, &s_cnt);
+  }
+}
+
+__global__ void __launch_bounds__(RS_THREADS)
+    rank_scored_f32_kernel(const float* scores, const long long* cand_idx, int c, int p, int top_k,
+                           double min_sim, float* out_score, long long* out_idx, int* out_count) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  u64* keys = reinterpret_cast<u64*>(rs_smem);
+  __shared__ int s_cnt;
+  const int q = blockIdx.x;
+  const long long* cand = cand_idx + (size_t)q * c;
+  for (int ci = threadIdx.x; ci < c; ci += RS_THREADS) {
+    const float s = scores[(size_t)q * c + ci];
+    const bool valid = cand[ci] >= 0 && s != -INFINITY;
+    keys[ci] = valid ? (((u64)(~f32_orderable(s)) << 32) | (u64)(u32)ci) : K1_INVALID;
+  }
+  __syncthreads();
+  rank_and_write_f32(keys, c, p, cand, top_k, min_sim, out_score + (size_t)q * top_k,
+                     out_idx + (size_t)q * top_k, out_count ? out_count + q : nullptr, &s_cnt);
+}
+
+// symmetric int8 x int8 -> int32 (extension mode), exact
+__global__ void __launch_bounds__(RS_THREADS)
+    rescore_i8_kernel(const int8_t* queries, int dim, const int8_t* emb, long long n,
+                      long long row_base, const long long* cand_idx, int c, int p, int top_k,
+                      int* out_score, long long* out_idx, int* out_count) {
+  extern __shared__ __align__(16) unsigned char rs_smem[];
+  int8_t* sq = reinterpret_cast<int8_t*>(rs_smem);
+  u64* keys = reinterpret_cast<u64*>(rs_smem + align_up_dev((size_t)dim));
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = threadIdx.x; d < dim; d += RS_THREADS) sq[d] = queries[(size_t)q * dim + d];
+  __syncthreads();
+  const long long* cand = cand_idx + (size_t)q * c;
+  for (int ci = warp; ci < c; ci += RS_WARPS) {
+    const long long idx = cand[ci];
+    const long long local = idx - row_base;
+    const bool valid = idx >= 0 && local >= 0 && local < n;
+    int acc = 0;
+    if (valid) {
+      const int8_t* row = emb + (size_t)local * dim;
+      if ((dim & 15) == 0) {
+        const int4* r16 = reinterpret_cast<const int4*>(row);
+        const int4* q16 = reinterpret_cast<const int4*>(sq);
+        for (int v = lane; v < (dim >> 4); v += 32) {
+          const int4 e = __ldg(r16 + v);
+          const int4 w = q16[v];
+          acc = __dp4a(e.x, w.x, acc);
+          acc = __dp4a(e.y, w.y, acc);
+          acc = __dp4a(e.z, w.z, acc);
+          acc = __dp4a(e.w, w.w, acc);
+        }
+      } else {
+        for (int d = lane; d < dim; d += 32) acc += (int)row[d] * (int)sq[d];
+      }
+      acc = warp_sum_i32(acc);
+    }
+    if (lane == 0)
+      keys[ci] = valid ? (((u64)(~i32_orderable(acc)) << 32) | (u64)(u32)ci) : K1_INVALID;
+  }
+  for (int i = c + threadIdx.x; i < p; i += RS_THREADS) keys[i] = K1_INVALID;
+  __syncthreads();
+  block_bitonic_sort_u64(keys, p);
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  for (int j = threadIdx.x; j < top_k; j += RS_THREADS) {
+    const size_t o = (size_t)q * top_k + j;
+    bool have = false;
+    if (j < c) {
+      const u64 key = keys[j];
+      if (key != K1_INVALID) {
+        have = true;
+        out_score[o] = i32_from_orderable(~(u32)(key >> 32));
+        out_idx[o] = cand[(u32)key];
+        atomicAdd(&s_cnt, 1);
+      }
+    }
+    if (!have) {
+      out_score[o] = (int)0x80000000;
+      out_idx[o] = -1;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && out_count) out_count[q] = s_cnt;
+}
+
+static int pow2_at_least(int c) {
+  int p = 1;
+  while (p < c) p <<= 1;
+  return p;
+}
+
+}  // namespace rr
+
+using namespace rr;
+
+static int check_rescore_args(int32_t q, int32_t dim, int32_t c, int32_t top_k) {
+  RR_CHECK_ARG(q >= 0 && dim > 0, "bad size");
+  RR_CHECK_ARG(c >= 1 && c <= RR_MAX_K, "candidate count out of range");
+  RR_CHECK_ARG(top_k >= 1 && top_k <= RR_MAX_K, "top_k out of range");
+  RR_CHECK_ARG(dim <= 8192, "dim > 8192 unsupported");
+  return RR_OK;
+}
+
+extern "C" int rr_rescore_f32(const float* queries, int32_t q, int32_t dim, const void* emb,
+                              int32_t emb_dtype, int64_t n, int64_t row_base,
+                              const int64_t* cand_idx, int32_t c, int32_t top_k,
+                              double min_similarity, float* out_score, int64_t* out_idx,
+                              int32_t* out_count, void* stream) {
+  int rc = check_rescore_args(q, dim, c, top_k);
+  if (rc != RR_OK) return rc;
+  if (q == 0) return RR_OK;
+  RR_CHECK_ARG(queries && cand_idx && out_score && out_idx, "null pointer");
+  RR_CHECK_ARG(emb || n == 0, "emb is null");
+  RR_CHECK_ARG(emb_dtype == RR_F32 || emb_dtype == RR_I8, "emb_dtype must be RR_F32 or RR_I8");
+  RescoreArgs a{queries, dim, emb, n, row_base, (const long long*)cand_idx, c, top_k,
+                min_similarity, out_score, (long long*)out_idx, out_count};
+  const int p = pow2_at_least(c);
+  const size_t smem = align_up((size_t)dim * 4, 16) + (size_t)p * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (emb_dtype == RR_F32)
+    rescore_f32_kernel<RR_F32, 0><<<q, RS_THREADS, smem, st>>>(a, p);
+  else
+    rescore_f32_kernel<RR_I8, 0><<<q, RS_THREADS, smem, st>>>(a, p);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
+extern "C" int rr_score_candidates_f32(const float* queries, int32_t q, int32_t dim, const void* emb,
+                                       int32_t emb_dtype, int64_t n, int64_t row_base,
+                                       const int64_t* cand_idx, int32_t c, float* out_score,
+                                       void* stream) {
+  int rc = check_rescore_args(q, dim, c, 1);
+  if (rc != RR_OK) return rc;
+  if (q == 0) return RR_OK;
+  RR_CHECK_ARG(queries && cand_idx && out_score, "null pointer");
+  RR_CHECK_ARG(emb || n == 0, "emb is null");
+  RR_CHECK_ARG(emb_dtype == RR_F32 || emb_dtype == RR_I8, "emb_dtype must be RR_F32 or RR_I8");
+  RescoreArgs a{queries, dim, emb, n, row_base, (const long long*)cand_idx, c, 1,
+                0.0, out_score, nullptr, nullptr};
+  const size_t smem = align_up((size_t)dim * 4, 16) + 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (emb_dtype == RR_F32)
+    rescore_f32_kernel<RR_F32, 1><<<q, RS_THREADS, smem, st>>>(a, 1);
+  else
+    rescore_f32_kernel<RR_I8, 1><<<q, RS_THREADS, smem, st>>>(a, 1);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
+extern "C" int rr_rank_scored_f32(const float* scores, const int64_t* cand_idx, int32_t q, int32_t c,
+                                  int32_t top_k, double min_similarity, float* out_score,
+                                  int64_t* out_idx, int32_t* out_count, void* stream) {
+  int rc = check_rescore_args(q, 1, c, top_k);
+  if (rc != RR_OK) return rc;
+  if (q == 0) return RR_OK;
+  RR_CHECK_ARG(scores && cand_idx && out_score && out_idx, "null pointer");
+  const int p = pow2_at_least(c);
+  rank_scored_f32_kernel<<<q, RS_THREADS, (size_t)p * 8, (cudaStream_t)stream>>>(
+      scores, (const long long*)cand_idx, c, p, top_k, min_similarity, out_score,
+      (long long*)out_idx, out_count);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
+extern "C" int rr_rescore_i8(const int8_t* queries_i8, int32_t q, int32_t dim, const int8_t* emb,
+                             int64_t n, int64_t row_base, const int64_t* cand_idx, int32_t c,
+                             int32_t top_k, int32_t* out_score, int64_t* out_idx,
+                             int32_t* out_count, void* stream) {
+  int rc = check_rescore_args(q, dim, c, top_k);
+  if (rc != RR_OK) return rc;
+  if (q == 0) return RR_OK;
+  RR_CHECK_ARG(queries_i8 && cand_idx && out_score && out_idx, "null pointer");
+  RR_CHECK_ARG(emb || n == 0, "emb is null");
+  const int p = pow2_at_least(c);
+  const size_t smem = align_up((size_t)dim, 16) + (size_t)p * 8;
+  rescore_i8_kernel<<<q, RS_THREADS, smem, (cudaStream_t)stream>>>(
+      queries_i8, dim, emb, n, row_base, (const long long*)cand_idx, c, p, top_k, out_score,
+      (long long*)out_idx, out_count);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}

@@ -1,0 +1,404 @@
+"""Device-resident quantised index of ONE shard and the batched search entry points.
+
+This is the "quantized index layout in radiant/storage" the north-star names.  HBM
+layout (row = position in upsert order, all arrays row-major, rows contiguous):
+
+    codes  uint8 [cap, words*4]   packed sign bits, np.packbits byte order, row padded
+                                  with zero bits to a multiple of 16 bytes
+    int8   int8  [cap, dim]       optional (precision "int8"/"both")
+    f32    f32   [cap, dim]       optional (float rescoring / exact scan)
+    tags   uint8 [cap]            bits 0-1 doc_level (1 child, 2 parent), bits 2-7 language id
+
+torch is used for allocation, streams and host<->device copies only; every
+computation goes through the C ABI (``_lib.call``) into the sm_100a kernels.
+"""
+
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib
+from .synthetic import value_shift
+
+ArrayLike = Union[np.ndarray, torch.Tensor]
+
+LEVEL_CHILD = 1
+LEVEL_PARENT = 2
+_LEVEL_BITS = {"child": LEVEL_CHILD, "parent": LEVEL_PARENT}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def code_words(dim: int) -> int:
+    """u32 words per packed row: ceil(dim/32) rounded up to a multiple of 4 (16 bytes)."""
+    w = (dim + 31) // 32
+    return (w + 3) // 4 * 4
+
+
+def to_device(x: ArrayLike, device: torch.device, dtype: torch.dtype) -> torch.Tensor:
+    """Host array (pinned on the way) or tensor -> contiguous device tensor of dtype."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if t.device != device:
+        if t.device.type == "cpu" and not t.is_pinned():
+            t = t.pin_memory()
+        t = t.to(device, non_blocking=True)
+    return t.contiguous()
+
+
+class LanguageTable:
+    """language code <-> 6-bit id stored in the tag byte (0 = none)."""
+
+    def __init__(self) -> None:
+        self._ids: Dict[str, int] = {}
+
+    def id_for(self, code: Optional[str], create: bool = False) -> int:
+        if not code:
+            return 0
+        if code in self._ids:
+            return self._ids[code]
+        if not create:
+            return 63  # never assigned to a row unless the table is full: matches nothing new
+        if len(self._ids) >= 62:
+            raise ValueError("more than 62 distinct language codes in one index")
+        self._ids[code] = len(self._ids) + 1
+        return self._ids[code]
+
+
+def make_tag(doc_level: Optional[str], lang_id: int) -> int:
+    return _LEVEL_BITS.get(doc_level or "child", LEVEL_CHILD) | (lang_id << 2)
+
+
+def tag_predicate(level_value: Optional[str], lang_id: int) -> Tuple[int, int]:
+    """(mask, value) such that a row passes when (tag & mask) == value."""
+    mask = 0
+    value = 0
+    if level_value in _LEVEL_BITS:
+        mask |= 0x03
+        value |= _LEVEL_BITS[level_value]
+    if lang_id:
+        mask |= 0xFC
+        value |= lang_id << 2
+    return mask, value
+
+
+class DenseIndex:
+    """Packed binary codes + int8 / float32 rows of one shard, resident in HBM."""
+
+    def __init__(
+        self,
+        dim: int,
+        device: Union[int, str, torch.device] = 0,
+        store_int8: bool = True,
+        store_f32: bool = True,
+        int8_ranges: Optional[ArrayLike] = None,
+        row_base: int = 0,
+        capacity: int = 0,
+    ) -> None:
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.RadiantB200Error("DenseIndex needs a CUDA device; there is no CPU fallback")
+        _lib.init(self.device.index or 0)
+        self.dim = int(dim)
+        self.words = code_words(self.dim)
+        if self.words > _lib.RR_MAX_WORDS:
+            raise ValueError(f"dim {dim} > {_lib.RR_MAX_WORDS * 32} unsupported by the Hamming scan")
+        self.store_int8 = bool(store_int8)
+        self.store_f32 = bool(store_f32)
+        self.row_base = int(row_base)
+        self.n = 0
+        self._cap = 0
+        self.codes: Optional[torch.Tensor] = None
+        self.int8: Optional[torch.Tensor] = None
+        self.f32: Optional[torch.Tensor] = None
+        self.tags: Optional[torch.Tensor] = None
+        self.tags_uniform = True  # every row has the default tag: the scan can skip the tag read
+        self.ranges: Optional[torch.Tensor] = None
+        if int8_ranges is not None:
+            self.set_int8_ranges(int8_ranges)
+        if capacity:
+            self._reserve(capacity)
+
+    def _activate(self) -> None:
+        """CUDA's current device is per host thread; the reference drives retrieval from
+        worker threads (radiant/orchestrator.py:994-998), so select ours on entry."""
+        if torch.cuda.current_device() != (self.device.index or 0):
+            torch.cuda.set_device(self.device)
+
+    # ---- storage ---------------------------------------------------------------
+    def _reserve(self, cap: int) -> None:
+        if cap <= self._cap:
+            return
+        cap = max(cap, int(self._cap * 1.5), 1024)
+
+        def grow(old: Optional[torch.Tensor], shape, dtype) -> torch.Tensor:
+            new = torch.empty(shape, dtype=dtype, device=self.device)
+            if old is not None and self.n:
+                new[: self.n].copy_(old[: self.n])
+            return new
+
+        self.codes = grow(self.codes, (cap, self.words * 4), torch.uint8)
+        self.tags = grow(self.tags, (cap,), torch.uint8)
+        if self.store_int8:
+            self.int8 = grow(self.int8, (cap, self.dim), torch.int8)
+        if self.store_f32:
+            self.f32 = grow(self.f32, (cap, self.dim), torch.float32)
+        self._cap = cap
+
+    def set_int8_ranges(self, ranges: ArrayLike) -> None:
+        """[2, dim] min/max calibration (reference calculate_int8_ranges,
+        radiant/storage/quantization.py:159-182, or the .npy of tools/calibrate_int8_ranges.py)."""
+        r = to_device(ranges, self.device, torch.float32)
+        if tuple(r.shape) != (2, self.dim):
+            raise ValueError(f"int8 ranges must have shape (2, {self.dim}), got {tuple(r.shape)}")
+        self.ranges = r
+
+    def add(self, emb: ArrayLike, tags: Optional[ArrayLike] = None) -> Tuple[int, int]:
+        """Append float32 rows [m, dim]: quantises to ubinary (+ int8) on device.
+        Returns the local row range [lo, hi)."""
+        self._activate()
+        e = to_device(emb, self.device, torch.float32)
+        if e.ndim == 1:
+            e = e[None, :]
+        if e.shape[1] != self.dim:
+            raise ValueError(f"embedding dim {e.shape[1]} != index dim {self.dim}")
+        m = e.shape[0]
+        lo, hi = self.n, self.n + m
+        self._reserve(hi)
+        _lib.call("rr_quantize_ubinary", e.data_ptr(), m, self.dim, self.codes[lo:hi].data_ptr(),
+                  self.words * 4, _stream())
+        if self.store_int8:
+            if self.ranges is None:
+                raise ValueError("int8 storage needs calibration ranges (set_int8_ranges)")
+            _lib.call("rr_quantize_int8", e.data_ptr(), m, self.dim, self.ranges.data_ptr(),
+                      self.int8[lo:hi].data_ptr(), _stream())
+        if self.store_f32:
+            self.f32[lo:hi].copy_(e)
+        if tags is None:
+            self.tags[lo:hi].fill_(LEVEL_CHILD)
+        else:
+            self.tags[lo:hi].copy_(to_device(tags, self.device, torch.uint8))
+            self.tags_uniform = False
+        self.n = hi
+        return lo, hi
+
+    def set_row(self, row: int, emb: ArrayLike, tag: int) -> None:
+        """Overwrite one existing row (upsert of a known doc_id)."""
+        self._activate()
+        e = to_device(emb, self.device, torch.float32).reshape(1, self.dim)
+        _lib.call("rr_quantize_ubinary", e.data_ptr(), 1, self.dim, self.codes[row:row + 1].data_ptr(),
+                  self.words * 4, _stream())
+        if self.store_int8:
+            _lib.call("rr_quantize_int8", e.data_ptr(), 1, self.dim, self.ranges.data_ptr(),
+                      self.int8[row:row + 1].data_ptr(), _stream())
+        if self.store_f32:
+            self.f32[row].copy_(e[0])
+        self.tags[row] = tag
+        if tag != LEVEL_CHILD:
+            self.tags_uniform = False
+
+    def set_tag(self, row: int, tag: int) -> None:
+        self.tags[row] = tag
+        if tag != LEVEL_CHILD:
+            self.tags_uniform = False
+
+    def clear(self) -> None:
+        self.n = 0
+        self.tags_uniform = True
+
+    # ---- kernels -----------------------------------------------------------------
+    def quantize_queries(self, queries: ArrayLike) -> Tuple[torch.Tensor, torch.Tensor]:
+        """f32 [q, dim] -> (device f32 queries, device packed codes uint8 [q, words*4])."""
+        self._activate()
+        qf = to_device(queries, self.device, torch.float32)
+        if qf.ndim == 1:
+            qf = qf[None, :]
+        qc = torch.empty((qf.shape[0], self.words * 4), dtype=torch.uint8, device=self.device)
+        _lib.call("rr_quantize_ubinary", qf.data_ptr(), qf.shape[0], self.dim, qc.data_ptr(),
+                  self.words * 4, _stream())
+        return qf, qc
+
+    def _tag_args(self, tag_mask: int, tag_value: int):
+        if tag_mask == 0 or self.tags is None:
+            return None, 0, 0
+        if self.tags_uniform:
+            # every row carries the default tag: decide the predicate once on the host
+            if (LEVEL_CHILD & tag_mask) == tag_value:
+                return None, 0, 0
+        return self.tags.data_ptr(), tag_mask, tag_value
+
+    def hamming_topk(self, qcodes: torch.Tensor, k: int, tag_mask: int = 0,
+                     tag_value: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Exact top-k by (dist asc, row asc).  -> (dist int32 [q,k], idx int64 [q,k])."""
+        q = qcodes.shape[0]
+        dist = torch.empty((q, k), dtype=torch.int32, device=self.device)
+        idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        lib = _lib.load()
+        ws_bytes = lib.rr_hamming_topk_workspace_bytes(self.n, self.words, q, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        tptr, tm, tv = self._tag_args(tag_mask, tag_value)
+        _lib.call("rr_hamming_topk", self.codes.data_ptr() if self.codes is not None else None, self.n,
+                  self.words, tptr, tm, tv, qcodes.data_ptr(), q, k, self.row_base, dist.data_ptr(),
+                  idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+        return dist, idx
+
+    def rescore_source(self, prefer_int8: bool = True) -> Tuple[torch.Tensor, int]:
+        """int8 rows preferred, float32 fallback (reference redis_store.py:820-840)."""
+        if prefer_int8 and self.int8 is not None:
+            return self.int8, _lib.RR_I8
+        if self.f32 is not None:
+            return self.f32, _lib.RR_F32
+        if self.int8 is not None:
+            return self.int8, _lib.RR_I8
+        raise _lib.RadiantB200Error("index stores neither int8 nor float32 rows: cannot rescore")
+
+    def rescore(self, queries: torch.Tensor, cand_idx: torch.Tensor, top_k: int,
+                min_similarity: float = 0.0, prefer_int8: bool = True
+                ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """-> (score f32 [q,top_k], idx int64 [q,top_k] (-1 padded), count int32 [q])."""
+        q, c = cand_idx.shape
+        rows, dt = self.rescore_source(prefer_int8)
+        score = torch.empty((q, top_k), dtype=torch.float32, device=self.device)
+        idx = torch.empty((q, top_k), dtype=torch.int64, device=self.device)
+        count = torch.empty((q,), dtype=torch.int32, device=self.device)
+        _lib.call("rr_rescore_f32", queries.data_ptr(), q, self.dim, rows.data_ptr(), dt, self.n,
+                  self.row_base, cand_idx.data_ptr(), c, top_k, float(min_similarity), score.data_ptr(),
+                  idx.data_ptr(), count.data_ptr(), _stream())
+        return score, idx, count
+
+    def score_candidates(self, queries: torch.Tensor, cand_idx: torch.Tensor,
+                         prefer_int8: bool = True) -> torch.Tensor:
+        """Scores of the candidates THIS shard owns, -inf elsewhere.  f32 [q, c]."""
+        q, c = cand_idx.shape
+        rows, dt = self.rescore_source(prefer_int8)
+        out = torch.empty((q, c), dtype=torch.float32, device=self.device)
+        _lib.call("rr_score_candidates_f32", queries.data_ptr(), q, self.dim, rows.data_ptr(), dt,
+                  self.n, self.row_base, cand_idx.data_ptr(), c, out.data_ptr(), _stream())
+        return out
+
+    def rescore_int8_symmetric(self, queries_i8: torch.Tensor, cand_idx: torch.Tensor, top_k: int
+                               ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Extension mode: exact int8 x int8 -> int32 rescoring."""
+        if self.int8 is None:
+            raise _lib.RadiantB200Error("index has no int8 rows")
+        q, c = cand_idx.shape
+        score = torch.empty((q, top_k), dtype=torch.int32, device=self.device)
+        idx = torch.empty((q, top_k), dtype=torch.int64, device=self.device)
+        count = torch.empty((q,), dtype=torch.int32, device=self.device)
+        _lib.call("rr_rescore_i8", queries_i8.data_ptr(), q, self.dim, self.int8.data_ptr(), self.n,
+                  self.row_base, cand_idx.data_ptr(), c, top_k, score.data_ptr(), idx.data_ptr(),
+                  count.data_ptr(), _stream())
+        return score, idx, count
+
+    def search_quantized(
+        self,
+        queries: ArrayLike,
+        top_k: int,
+        rescore_multiplier: float = 4.0,
+        use_rescoring: bool = True,
+        min_similarity: float = 0.0,
+        tag_mask: int = 0,
+        tag_value: int = 0,
+        prefer_int8: bool = True,
+    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Batched two-stage retrieval (reference redis_store.py:757-861 for one query).
+
+        -> (idx int64 [q, top_k] (-1 padded), score f32 [q, top_k], count int32 [q]).
+        Without rescoring the score is the placeholder 1.0 (reference chroma_store.py:624-631).
+        """
+        qf, qc = self.quantize_queries(queries)
+        candidate_k = int(top_k * rescore_multiplier) if use_rescoring else top_k
+        candidate_k = max(1, min(candidate_k, _lib.RR_MAX_K))
+        _dist, cand = self.hamming_topk(qc, candidate_k, tag_mask, tag_value)
+        if not use_rescoring:
+            idx = cand[:, :top_k].contiguous()
+            score = torch.ones(idx.shape, dtype=torch.float32, device=self.device)
+            count = (idx >= 0).sum(dim=1).to(torch.int32)
+            return idx, score, count
+        score, idx, count = self.rescore(qf, cand, top_k, min_similarity, prefer_int8)
+        return idx, score, count
+
+    def search_exact(self, queries: ArrayLike, top_k: int, min_similarity: float = 0.0,
+                     tag_mask: int = 0, tag_value: int = 0
+                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Exact float32 cosine scan (reference redis_store.py:863-952), batched."""
+        self._activate()
+        if self.f32 is None:
+            raise _lib.RadiantB200Error("index has no float32 rows: exact search unavailable")
+        qf = to_device(queries, self.device, torch.float32)
+        if qf.ndim == 1:
+            qf = qf[None, :]
+        q = qf.shape[0]
+        score = torch.empty((q, top_k), dtype=torch.float32, device=self.device)
+        idx = torch.empty((q, top_k), dtype=torch.int64, device=self.device)
+        count = torch.empty((q,), dtype=torch.int32, device=self.device)
+        lib = _lib.load()
+        ws_bytes = lib.rr_exact_search_f32_workspace_bytes(self.n, q, top_k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        tptr, tm, tv = self._tag_args(tag_mask, tag_value)
+        _lib.call("rr_exact_search_f32", self.f32.data_ptr(), self.n, self.dim, tptr, tm, tv,
+                  qf.data_ptr(), q, top_k, float(min_similarity), self.row_base, score.data_ptr(),
+                  idx.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+        return idx, score, count
+
+    def search_int8_exact(self, queries_i8: ArrayLike, top_k: int, tag_mask: int = 0,
+                          tag_value: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Exact int8 x int8 -> int32 search (BASELINE config 4).  -> (idx, score int32)."""
+        self._activate()
+        if self.int8 is None:
+            raise _lib.RadiantB200Error("index has no int8 rows")
+        qi = to_device(queries_i8, self.device, torch.int8)
+        if qi.ndim == 1:
+            qi = qi[None, :]
+        q = qi.shape[0]
+        score = torch.empty((q, top_k), dtype=torch.int32, device=self.device)
+        idx = torch.empty((q, top_k), dtype=torch.int64, device=self.device)
+        lib = _lib.load()
+        ws_bytes = lib.rr_int8_search_topk_workspace_bytes(self.n, q, top_k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        tptr, tm, tv = self._tag_args(tag_mask, tag_value)
+        _lib.call("rr_int8_search_topk", self.int8.data_ptr(), self.n, self.dim, tptr, tm, tv,
+                  qi.data_ptr(), q, top_k, self.row_base, score.data_ptr(), idx.data_ptr(),
+                  ws.data_ptr(), ws_bytes, _stream())
+        return idx, score
+
+    def quantize_int8_queries(self, queries: ArrayLike) -> torch.Tensor:
+        """Query-side int8 codes for the symmetric extension mode (same affine map)."""
+        self._activate()
+        qf = to_device(queries, self.device, torch.float32)
+        if qf.ndim == 1:
+            qf = qf[None, :]
+        out = torch.empty(qf.shape, dtype=torch.int8, device=self.device)
+        _lib.call("rr_quantize_int8", qf.data_ptr(), qf.shape[0], self.dim, self.ranges.data_ptr(),
+                  out.data_ptr(), _stream())
+        return out
+
+
+# ---- synthetic rows generated on device (bench / tests) -----------------------------
+
+def synth_rows_device(row_start: int, n_rows: int, dim: int, seed: int,
+                      device: Union[int, torch.device] = 0) -> torch.Tensor:
+    dev = torch.device("cuda", device) if isinstance(device, int) else device
+    _lib.init(dev.index or 0)
+    out = torch.empty((n_rows, dim), dtype=torch.float32, device=dev)
+    _lib.call("rr_synth_rows_f32", out.data_ptr(), row_start, n_rows, dim, seed, value_shift(dim), _stream())
+    return out
+
+
+def synth_query_rows_device(q_start: int, n_q: int, dim: int, seed: int, n_corpus: int,
+                            device: Union[int, torch.device] = 0) -> torch.Tensor:
+    dev = torch.device("cuda", device) if isinstance(device, int) else device
+    _lib.init(dev.index or 0)
+    out = torch.empty((n_q, dim), dtype=torch.float32, device=dev)
+    _lib.call("rr_synth_query_rows_f32", out.data_ptr(), q_start, n_q, dim, seed, n_corpus,
+              value_shift(dim), _stream())
+    return out

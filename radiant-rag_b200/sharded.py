@@ -1,0 +1,154 @@
+"""Row-sharded retrieval across the GPUs of one box.
+
+One process per GPU (torchrun), ``torch.distributed`` over NCCL/NVLink.  The corpus is
+cut into contiguous row blocks ``[g*N/G, (g+1)*N/G)``; queries are replicated.  Only
+candidate lists cross NVLink:
+
+  dense, exact single-index semantics in two small steps
+    1. local Hamming top-k'           -> all_gather [G, Q, k'] -> merge (dist asc, row asc)
+    2. each shard scores the global candidates it OWNS (-inf elsewhere)
+                                      -> all_reduce(MAX) [Q, k'] -> rank, cut, filter
+  BM25     local top-k (global idf/avgdl baked into the shard's impacts)
+                                      -> all_gather -> merge (score desc, row asc)
+  RRF      runs on the merged, replicated lists on every rank.
+
+Payloads are tiny (Q*k'*12 B per rank), so the collectives are latency-bound; they are
+issued on the same stream as the kernels (NCCL stream semantics) with no host sync in
+between.  The compute ops are injected (``ops``): ``GpuShardOps`` (the product; CUDA
+only, no CPU fallback) or a test double that the world_size-2 gloo tests supply.
+"""
+
+from __future__ import annotations
+
+from typing import Any, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .index import DenseIndex, _stream
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous row block of `rank`: [lo, hi)."""
+    per = (n_total + world - 1) // world
+    lo = min(rank * per, n_total)
+    return lo, min(lo + per, n_total)
+
+
+class GpuShardOps:
+    """Compute ops of one shard, all through the C ABI."""
+
+    def __init__(self, index: DenseIndex) -> None:
+        self.index = index
+        self.device = index.device
+
+    def quantize_queries(self, queries):
+        return self.index.quantize_queries(queries)
+
+    def hamming_topk(self, qcodes, k, tag_mask=0, tag_value=0):
+        return self.index.hamming_topk(qcodes, k, tag_mask, tag_value)
+
+    def merge_hamming(self, dist_all: torch.Tensor, idx_all: torch.Tensor, k: int):
+        q, n_in = idx_all.shape
+        out_d = torch.empty((q, k), dtype=torch.int32, device=self.device)
+        out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        _lib.call("rr_merge_hamming", dist_all.data_ptr(), idx_all.data_ptr(), q, n_in, k,
+                  out_d.data_ptr(), out_i.data_ptr(), _stream())
+        return out_d, out_i
+
+    def score_candidates(self, queries_f32, cand_idx, prefer_int8=True):
+        return self.index.score_candidates(queries_f32, cand_idx, prefer_int8)
+
+    def rank_scored(self, scores, cand_idx, top_k, min_similarity):
+        q, c = cand_idx.shape
+        out_s = torch.empty((q, top_k), dtype=torch.float32, device=self.device)
+        out_i = torch.empty((q, top_k), dtype=torch.int64, device=self.device)
+        out_c = torch.empty((q,), dtype=torch.int32, device=self.device)
+        _lib.call("rr_rank_scored_f32", scores.data_ptr(), cand_idx.data_ptr(), q, c, top_k,
+                  float(min_similarity), out_s.data_ptr(), out_i.data_ptr(), out_c.data_ptr(), _stream())
+        return out_i, out_s, out_c
+
+    def merge_scores_f64(self, score_all: torch.Tensor, idx_all: torch.Tensor, k: int):
+        q, n_in = idx_all.shape
+        out_s = torch.empty((q, k), dtype=torch.float64, device=self.device)
+        out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        out_c = torch.empty((q,), dtype=torch.int32, device=self.device)
+        _lib.call("rr_merge_scores_f64", score_all.data_ptr(), idx_all.data_ptr(), q, n_in, k,
+                  out_s.data_ptr(), out_i.data_ptr(), out_c.data_ptr(), _stream())
+        return out_i, out_s, out_c
+
+    def merge_scores_i32(self, score_all: torch.Tensor, idx_all: torch.Tensor, k: int):
+        q, n_in = idx_all.shape
+        out_s = torch.empty((q, k), dtype=torch.int32, device=self.device)
+        out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        _lib.call("rr_merge_scores_i32", score_all.data_ptr(), idx_all.data_ptr(), q, n_in, k,
+                  out_s.data_ptr(), out_i.data_ptr(), _stream())
+        return out_i, out_s
+
+
+def _gather_lists(t: torch.Tensor, group: Optional[Any]) -> torch.Tensor:
+    """[Q, k] on every rank -> [Q, G*k] (rank-major within a query) on every rank."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return t
+    t = t.contiguous()
+    buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(buf, t, group=group)
+    return buf.permute(1, 0, 2).reshape(t.shape[0], world * t.shape[1]).contiguous()
+
+
+class ShardedDenseSearch:
+    """Two-stage quantised retrieval over a row-sharded corpus with single-index results."""
+
+    def __init__(self, ops: Any, group: Optional[Any] = None) -> None:
+        self.ops = ops
+        self.group = group
+
+    def search_quantized(self, queries, top_k: int, rescore_multiplier: float = 4.0,
+                         use_rescoring: bool = True, min_similarity: float = 0.0,
+                         tag_mask: int = 0, tag_value: int = 0, prefer_int8: bool = True
+                         ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """queries f32 [Q, D], identical on every rank.  -> (idx [Q,top_k] global rows,
+        score f32 [Q,top_k], count int32 [Q]), identical on every rank."""
+        ops = self.ops
+        qf, qc = ops.quantize_queries(queries)
+        candidate_k = int(top_k * rescore_multiplier) if use_rescoring else top_k
+        candidate_k = max(1, min(candidate_k, _lib.RR_MAX_K))
+        d_loc, i_loc = ops.hamming_topk(qc, candidate_k, tag_mask, tag_value)
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world > 1:
+            d_all = _gather_lists(d_loc, self.group)
+            i_all = _gather_lists(i_loc, self.group)
+            _d, cand = ops.merge_hamming(d_all, i_all, candidate_k)
+        else:
+            cand = i_loc
+        if not use_rescoring:
+            idx = cand[:, :top_k].contiguous()
+            score = torch.ones(idx.shape, dtype=torch.float32, device=idx.device)
+            count = (idx >= 0).sum(dim=1).to(torch.int32)
+            return idx, score, count
+        s = ops.score_candidates(qf, cand, prefer_int8)
+        if world > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.MAX, group=self.group)
+        return ops.rank_scored(s, cand, top_k, min_similarity)
+
+
+class ShardedBM25Search:
+    """BM25 over a row-sharded document space.  ``local`` is a Bm25DeviceIndex (or a test
+    double with the same ``search_batch``) built over this rank's documents with the
+    GLOBAL idf / avgdl tables and ``row_base`` = first global row of the shard."""
+
+    def __init__(self, local: Any, ops: Any, group: Optional[Any] = None) -> None:
+        self.local = local
+        self.ops = ops
+        self.group = group
+
+    def search_batch(self, q_terms, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        idx, score, count = self.local.search_batch(q_terms, k)
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1:
+            return idx, score, count
+        s_all = _gather_lists(score, self.group)
+        i_all = _gather_lists(idx, self.group)
+        return self.ops.merge_scores_f64(s_all, i_all, k)
