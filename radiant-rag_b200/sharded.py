@@ -94,7 +94,10 @@ def _gather_lists(t: torch.Tensor, group: Optional[Any]) -> torch.Tensor:
         return t
     t = t.contiguous()
     buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(buf, t, group=group)
+    if t.is_cuda:
+        dist.all_gather_into_tensor(buf, t, group=group)
+    else:  # gloo (CPU tests of the host logic)
+        dist.all_gather(list(buf.unbind(0)), t, group=group)
     return buf.permute(1, 0, 2).reshape(t.shape[0], world * t.shape[1]).contiguous()
 
 
