@@ -391,8 +391,13 @@ def gen_agent_chain() -> None:
         d = dense.run(query=qtext).data
         s = sparse.run(query=qtext).data
         f = rrf.run(runs=[d, s]).data
+        from radiant.storage.bm25_index import _tokenize as _tok
+        full = bm.index.search(_tok(qtext), top_k=len(CORPUS_TEXTS))
         cases.append({
             "query": qtext,
+            # every matching document: lets the test apply the canonical (score desc, row asc)
+            # order where the reference's argpartition/argsort leaves ties unspecified
+            "bm25_full": [[doc_id, float(v)] for doc_id, v in full],
             "dense": [[x.doc_id, float(v)] for x, v in d],
             "bm25": [[x.doc_id, float(v)] for x, v in s],
             "fused": [[x.doc_id, float(v)] for x, v in f],
