@@ -7,18 +7,31 @@
 //
 // Layout: codes u32 [n, W] row-major (W = dim/32 rounded up to a multiple of 4 so a
 // row is a whole number of 16-byte vectors).  A CTA owns one slab of rows and one
-// tile of queries.  Each thread keeps one row in registers (W/4 128-bit loads) and
-// walks the query tile, whose packed codes sit in shared memory and are read as
-// warp-wide broadcasts; XOR + POPC + IADD3 give the distance.  Per query the CTA
-// keeps a shared-memory candidate queue guarded by a running threshold (the k-th
-// best key seen so far): a row is appended only when its 32-bit key
-// (dist << 21 | row-in-slab) beats the threshold, appends are warp-aggregated, and a
-// full queue is cut back to its k best by a warp-level radix select.  The per-slab
-// lists are merged by merge_pairs_kernel (select.cuh).
+// tile of queries.
+//   * Rows are streamed from HBM into a ring of shared-memory tiles (256 rows each) by
+//     the TMA bulk-copy engine (cp.async.bulk + mbarrier complete_tx); the next tiles
+//     are in flight while the current one is scored, so the single-query case runs at
+//     memory speed.
+//   * Each thread pulls one row of the tile into registers with 128-bit loads in a
+//     rotated chunk order (lane i reads chunk (j+i) mod V at step j), which is
+//     bank-conflict-free on the dense tile without a swizzle, then walks the query
+//     tile (packed query codes in shared memory, read with the same rotation).
+//   * XOR then a first-level carry-save adder tree (LOP3) folds three words into a
+//     "ones" and a "twos" word, so only 2/3 of the POPCs of the naive loop issue on the
+//     quarter-rate POPC pipe, which is the pipe that bounds the batched scan.
+//   * Per query the CTA keeps a shared-memory candidate queue guarded by a running
+//     threshold: a row is appended only when its 32-bit key (dist << 21 | row-in-slab)
+//     beats the threshold; appends are warp-aggregated; a full queue is cut back to its
+//     k best by a warp-level radix select.  Each cut also publishes (atomicMin) the
+//     distance of the CTA's k-th best as a bound every other CTA of that query may prune
+//     with - k rows at or below it exist, so nothing above it can be in the answer.
+// The per-slab lists are merged by merge_pairs_kernel (merge.cuh).
 //
 // Roofline: algorithmic bytes per launch = n * W * 4 (one pass over the
 // codes; the query tiles of one slab run back to back so re-reads hit L2); integer
-// work = q * n * W popcounts.  HBM-bound for q <= 3, POPC-pipe-bound above.
+// work = q * n * W word XOR+POPC.  HBM-bound for q <= 3, POPC-pipe-bound above.
+
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "merge.cuh"
@@ -252,6 +265,281 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) hamming_scan_kernel(const Sca
 }
 
 
+// ---------------------------------------------------------------------------------------
+// v2: TMA bulk-copy staged tiles, rotated conflict-free reads, CSA popcount, cross-CTA bound
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+  u32 done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+
+struct Scan2Plan {
+  int q_tile, n_qtiles, cap, slabs, stages;
+  long long rows_per_slab;
+  size_t smem;
+};
+
+constexpr int SCAN_TILE_ROWS = SCAN_THREADS;
+constexpr size_t SCAN_SMEM_BUDGET = 112 * 1024;  // two CTAs per SM
+
+static size_t scan2_smem(int words, int stages, int q_tile, int cap) {
+  return (size_t)stages * SCAN_TILE_ROWS * words * 4 + (size_t)q_tile * ((size_t)words * 4 + (size_t)cap * 4 + 8) +
+         SCAN_WARPS * 256 * sizeof(int) + 8 * (size_t)stages + 32;
+}
+
+static Scan2Plan plan_scan2(long long n, int words, int q, int k) {
+  Scan2Plan p;
+  p.cap = (int)align_up((size_t)k + 2 * SCAN_THREADS, 32);
+  // memory-bound regime (a few queries): deep ring; compute-bound regime: 2 stages
+  p.stages = (q <= 4) ? 4 : 2;
+  int qt = 0;
+  while (true) {
+    const int want = q < 64 ? q : 64;
+    qt = want;
+    while (qt > 1 && scan2_smem(words, p.stages, qt, p.cap) > SCAN_SMEM_BUDGET) --qt;
+    if (scan2_smem(words, p.stages, qt, p.cap) <= SCAN_SMEM_BUDGET || p.stages == 1) break;
+    --p.stages;
+  }
+  p.n_qtiles = (q + qt - 1) / qt;
+  p.q_tile = (q + p.n_qtiles - 1) / p.n_qtiles;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  // two resident CTAs per SM; one wave when memory-bound, two when compute-bound
+  long long target = (q <= 4 ? 2LL : 4LL) * sms;
+  long long slabs = (target + p.n_qtiles - 1) / p.n_qtiles;
+  const long long max_slabs = (n + 2047) / 2048;
+  if (slabs > max_slabs) slabs = max_slabs;
+  if (slabs < 1) slabs = 1;
+  long long rps = (n + slabs - 1) / slabs;
+  rps = (long long)align_up((size_t)rps, SCAN_TILE_ROWS);
+  const long long max_rps = 1LL << SCAN_ROW_BITS;
+  if (rps > max_rps) rps = max_rps;
+  p.rows_per_slab = rps;
+  p.slabs = (int)((n + rps - 1) / rps);
+  if (p.slabs < 1) p.slabs = 1;
+  p.smem = scan2_smem(words, p.stages, p.q_tile, p.cap);
+  return p;
+}
+
+struct Scan2Args {
+  const uint4* codes;
+  long long n;
+  const uint8_t* tags;
+  unsigned tag_mask;
+  unsigned tag_value;
+  const u32* qcodes;
+  int q;
+  int k;
+  int q_tile;
+  int n_qtiles;
+  int cap;
+  int slabs;
+  int stages;
+  long long rows_per_slab;
+  u64* part_k1;  // [q][slabs][k]
+  u32* part_k2;
+  u32* gbound;   // [q] cross-CTA pruning bound (key space), starts at 0xFFFFFFFF
+};
+
+// popcount of W xor-words through one level of 3:2 carry-save adders
+template <int W>
+__device__ __forceinline__ int csa_popcount(const u32 (&x)[W]) {
+  constexpr int T = W / 3;
+  int ones = 0, twos = 0;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    const u32 a = x[3 * t], b = x[3 * t + 1], c = x[3 * t + 2];
+    const u32 s = a ^ b ^ c;                 // LOP3
+    const u32 h = (a & b) | (c & (a ^ b));   // LOP3 (majority)
+    ones += __popc(s);
+    twos += __popc(h);
+  }
+#pragma unroll
+  for (int w = 3 * T; w < W; ++w) ones += __popc(x[w]);
+  return ones + 2 * twos;
+}
+
+template <int W>
+__global__ void __launch_bounds__(SCAN_THREADS, 2) hamming_scan2_kernel(const Scan2Args a) {
+  extern __shared__ __align__(128) unsigned char smem2_raw[];
+  unsigned char* smem_raw = smem2_raw;
+  constexpr int V = W / 4;                          // 16-byte chunks per row
+  constexpr int TILE_BYTES = SCAN_TILE_ROWS * W * 4;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int slab = blockIdx.x / a.n_qtiles;
+  const int qt = blockIdx.x % a.n_qtiles;
+  const int q0 = qt * a.q_tile;
+  const int nq = min(a.q_tile, a.q - q0);
+
+  unsigned char* tiles = smem_raw;                                                     // [stages][TILE_BYTES]
+  unsigned char* sq = tiles + (size_t)a.stages * TILE_BYTES;                           // [q_tile][W*4]
+  u32* queue = reinterpret_cast<u32*>(sq + (size_t)a.q_tile * W * 4);                  // [q_tile][cap]
+  u32* thr = queue + (size_t)a.q_tile * a.cap;                                         // [q_tile]
+  int* cnt = reinterpret_cast<int*>(thr + a.q_tile);                                   // [q_tile]
+  int* whist = cnt + a.q_tile;                                                         // [warps][256]
+  u64* mbar = reinterpret_cast<u64*>(align_up_dev((size_t)(whist + SCAN_WARPS * 256), 8));  // [stages]
+
+  const long long row_lo = (long long)slab * a.rows_per_slab;
+  const long long row_hi = min(a.n, row_lo + a.rows_per_slab);
+  const int ntiles = (int)((row_hi - row_lo + SCAN_TILE_ROWS - 1) / SCAN_TILE_ROWS);
+
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) mbar_init(smem_addr(mbar + s), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < nq * V; i += SCAN_THREADS)
+    reinterpret_cast<uint4*>(sq)[i] = reinterpret_cast<const uint4*>(a.qcodes)[(size_t)q0 * V + i];
+  for (int i = tid; i < nq; i += SCAN_THREADS) {
+    thr[i] = SCAN_KEY_MAX;
+    cnt[i] = 0;
+  }
+  __syncthreads();
+
+  auto issue_tile = [&](int t) {
+    const int s = t % a.stages;
+    const long long r0 = row_lo + (long long)t * SCAN_TILE_ROWS;
+    const long long rows = min((long long)SCAN_TILE_ROWS, row_hi - r0);
+    const u32 bytes = (u32)(rows * W * 4);
+    const u32 bar = smem_addr(mbar + s);
+    mbar_expect_tx(bar, bytes);
+    bulk_copy_g2s(smem_addr(tiles + (size_t)s * TILE_BYTES), a.codes + (size_t)r0 * V, bytes, bar);
+  };
+  if (tid == 0) {
+    const int pre = ntiles < a.stages ? ntiles : a.stages;
+    for (int t = 0; t < pre; ++t) issue_tile(t);
+  }
+
+  // rotated chunk order: at step j this lane handles chunk (j + lane) mod V
+  int coff[V];
+  {
+    const int l = lane % V;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      int c = l + j;
+      if (c >= V) c -= V;
+      coff[j] = c * 16;
+    }
+  }
+
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t % a.stages;
+    mbar_wait(smem_addr(mbar + s), (u32)((t / a.stages) & 1));
+    const long long row = row_lo + (long long)t * SCAN_TILE_ROWS + tid;
+    bool valid = row < row_hi;
+    if (valid && a.tags != nullptr) valid = ((unsigned)a.tags[row] & a.tag_mask) == a.tag_value;
+    uint4 r[V];
+    {
+      const unsigned char* src = tiles + (size_t)s * TILE_BYTES + (size_t)tid * (W * 4);
+#pragma unroll
+      for (int j = 0; j < V; ++j) r[j] = *reinterpret_cast<const uint4*>(src + coff[j]);
+    }
+    const u32 local = (u32)(row - row_lo);
+#pragma unroll 1
+    for (int qi = 0; qi < nq; ++qi) {
+      const unsigned char* qb = sq + (size_t)qi * (W * 4);
+      u32 x[W];
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        const uint4 c = *reinterpret_cast<const uint4*>(qb + coff[j]);
+        x[4 * j + 0] = r[j].x ^ c.x;
+        x[4 * j + 1] = r[j].y ^ c.y;
+        x[4 * j + 2] = r[j].z ^ c.z;
+        x[4 * j + 3] = r[j].w ^ c.w;
+      }
+      const int d = csa_popcount<W>(x);
+      const u32 key = ((u32)d << SCAN_ROW_BITS) | local;
+      const bool pass = valid && (key < thr[qi]);
+      const unsigned bal = __ballot_sync(0xffffffffu, pass);
+      if (bal) {
+        int slot = 0;
+        if (lane == (__ffs(bal) - 1)) slot = atomicAdd(&cnt[qi], __popc(bal));
+        slot = __shfl_sync(0xffffffffu, slot, __ffs(bal) - 1);
+        if (pass) queue[(size_t)qi * a.cap + slot + __popc(bal & ((1u << lane) - 1u))] = key;
+      }
+    }
+    __syncthreads();  // every thread has its row in registers and is done appending
+    if (tid == 0 && t + a.stages < ntiles) issue_tile(t + a.stages);  // refill the freed slot
+    for (int qi = warp; qi < nq; qi += SCAN_WARPS) {
+      const int c = cnt[qi];
+      u32 tl = thr[qi];
+      if (c > a.cap - SCAN_THREADS) {
+        tl = warp_compact_queue(queue + (size_t)qi * a.cap, c, a.k, whist + warp * 256);
+        if (lane == 0) {
+          cnt[qi] = a.k;
+          // k rows with dist <= dist(kth) exist: nothing with a larger dist can be in the answer
+          atomicMin(a.gbound + q0 + qi, ((tl >> SCAN_ROW_BITS) + 1u) << SCAN_ROW_BITS);
+        }
+      }
+      if (lane == 0) {
+        const u32 g = *reinterpret_cast<volatile u32*>(a.gbound + q0 + qi);
+        thr[qi] = tl < g ? tl : g;
+      }
+    }
+    __syncthreads();
+  }
+
+  // final cut and write-out of this slab's list for each query of the tile
+  for (int qi = warp; qi < nq; qi += SCAN_WARPS) {
+    int c = cnt[qi];
+    u32* qu = queue + (size_t)qi * a.cap;
+    if (c > a.k) {
+      const u32 kth = warp_compact_queue(qu, c, a.k, whist + warp * 256);
+      c = a.k;
+      if (lane == 0) atomicMin(a.gbound + q0 + qi, ((kth >> SCAN_ROW_BITS) + 1u) << SCAN_ROW_BITS);
+    }
+    __syncwarp();
+    const u32 g = *reinterpret_cast<volatile u32*>(a.gbound + q0 + qi);
+    const size_t o = ((size_t)(q0 + qi) * a.slabs + slab) * a.k;
+    for (int j = lane; j < a.k; j += 32) {
+      const u32 key = (j < c) ? qu[j] : SCAN_KEY_MAX;
+      if (j < c && key < g) {
+        a.part_k1[o + j] = (u64)(key >> SCAN_ROW_BITS);
+        a.part_k2[o + j] = (u32)(row_lo + (key & ((1u << SCAN_ROW_BITS) - 1u)));
+      } else {
+        a.part_k1[o + j] = K1_INVALID;
+        a.part_k2[o + j] = K2_INVALID;
+      }
+    }
+  }
+}
+
+template <int W>
+static int launch_scan2(const Scan2Args& a, const Scan2Plan& p, cudaStream_t st) {
+  RR_CUDA(cudaFuncSetAttribute(hamming_scan2_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)p.smem));
+  hamming_scan2_kernel<W><<<p.slabs * p.n_qtiles, SCAN_THREADS, p.smem, st>>>(a);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
+static bool use_scan_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RR_SCAN_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+
 __global__ void fill_missing_hamming_kernel(int* dist, long long* idx, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) {
@@ -275,8 +563,11 @@ using namespace rr;
 
 extern "C" size_t rr_hamming_topk_workspace_bytes(int64_t n, int32_t words, int32_t q, int32_t k) {
   if (n <= 0 || q <= 0 || k <= 0 || words <= 0) return 256;
-  const ScanPlan p = plan_scan(n, words, q, k);
-  return align_up((size_t)q * p.slabs * k * 8, 256) + align_up((size_t)q * p.slabs * k * 4, 256) + 256;
+  const ScanPlan p1 = plan_scan(n, words, q, k);
+  const Scan2Plan p2 = plan_scan2(n, words, q, k);
+  const size_t slabs = (size_t)(p1.slabs > p2.slabs ? p1.slabs : p2.slabs);
+  return align_up((size_t)q * slabs * k * 8, 256) + align_up((size_t)q * slabs * k * 4, 256) +
+         align_up((size_t)q * 4, 256) + 256;
 }
 
 extern "C" int rr_hamming_topk(const uint32_t* codes, int64_t n, int32_t words, const uint8_t* tags,
@@ -305,40 +596,79 @@ extern "C" int rr_hamming_topk(const uint32_t* codes, int64_t n, int32_t words, 
     set_error("rr_hamming_topk: workspace %zu < %zu", workspace_bytes, need);
     return RR_ERR_WORKSPACE;
   }
-  const ScanPlan p = plan_scan(n, words, q, k);
-  ScanArgs a;
-  a.codes = (const uint4*)codes;
-  a.n = n;
-  a.tags = tags;
-  a.tag_mask = tag_mask;
-  a.tag_value = tag_value;
-  a.qcodes = qcodes;
-  a.q = q;
-  a.k = k;
-  a.q_tile = p.q_tile;
-  a.n_qtiles = p.n_qtiles;
-  a.cap = p.cap;
-  a.slabs = p.slabs;
-  a.rows_per_slab = p.rows_per_slab;
-  a.part_k1 = (u64*)workspace;
-  a.part_k2 = (u32*)((char*)workspace + align_up((size_t)q * p.slabs * k * 8, 256));
+  u64* part_k1 = nullptr;
+  u32* part_k2 = nullptr;
+  int slabs = 0;
   int rc = RR_ERR_INVALID;
-  switch (words) {
-    case 4: rc = launch_scan<4>(a, p, st); break;
-    case 8: rc = launch_scan<8>(a, p, st); break;
-    case 12: rc = launch_scan<12>(a, p, st); break;
-    case 16: rc = launch_scan<16>(a, p, st); break;
-    case 20: rc = launch_scan<20>(a, p, st); break;
-    case 24: rc = launch_scan<24>(a, p, st); break;
-    case 28: rc = launch_scan<28>(a, p, st); break;
-    case 32: rc = launch_scan<32>(a, p, st); break;
-    default: break;
+  if (use_scan_v1()) {
+    const ScanPlan p = plan_scan(n, words, q, k);
+    ScanArgs a;
+    a.codes = (const uint4*)codes;
+    a.n = n;
+    a.tags = tags;
+    a.tag_mask = tag_mask;
+    a.tag_value = tag_value;
+    a.qcodes = qcodes;
+    a.q = q;
+    a.k = k;
+    a.q_tile = p.q_tile;
+    a.n_qtiles = p.n_qtiles;
+    a.cap = p.cap;
+    a.slabs = slabs = p.slabs;
+    a.rows_per_slab = p.rows_per_slab;
+    a.part_k1 = part_k1 = (u64*)workspace;
+    a.part_k2 = part_k2 = (u32*)((char*)workspace + align_up((size_t)q * p.slabs * k * 8, 256));
+    switch (words) {
+      case 4: rc = launch_scan<4>(a, p, st); break;
+      case 8: rc = launch_scan<8>(a, p, st); break;
+      case 12: rc = launch_scan<12>(a, p, st); break;
+      case 16: rc = launch_scan<16>(a, p, st); break;
+      case 20: rc = launch_scan<20>(a, p, st); break;
+      case 24: rc = launch_scan<24>(a, p, st); break;
+      case 28: rc = launch_scan<28>(a, p, st); break;
+      case 32: rc = launch_scan<32>(a, p, st); break;
+      default: break;
+    }
+  } else {
+    const Scan2Plan p = plan_scan2(n, words, q, k);
+    Scan2Args a;
+    a.codes = (const uint4*)codes;
+    a.n = n;
+    a.tags = tags;
+    a.tag_mask = tag_mask;
+    a.tag_value = tag_value;
+    a.qcodes = qcodes;
+    a.q = q;
+    a.k = k;
+    a.q_tile = p.q_tile;
+    a.n_qtiles = p.n_qtiles;
+    a.cap = p.cap;
+    a.slabs = slabs = p.slabs;
+    a.stages = p.stages;
+    a.rows_per_slab = p.rows_per_slab;
+    const size_t o1 = align_up((size_t)q * p.slabs * k * 8, 256);
+    const size_t o2 = o1 + align_up((size_t)q * p.slabs * k * 4, 256);
+    a.part_k1 = part_k1 = (u64*)workspace;
+    a.part_k2 = part_k2 = (u32*)((char*)workspace + o1);
+    a.gbound = (u32*)((char*)workspace + o2);
+    RR_CUDA(cudaMemsetAsync(a.gbound, 0xFF, (size_t)q * 4, st));
+    switch (words) {
+      case 4: rc = launch_scan2<4>(a, p, st); break;
+      case 8: rc = launch_scan2<8>(a, p, st); break;
+      case 12: rc = launch_scan2<12>(a, p, st); break;
+      case 16: rc = launch_scan2<16>(a, p, st); break;
+      case 20: rc = launch_scan2<20>(a, p, st); break;
+      case 24: rc = launch_scan2<24>(a, p, st); break;
+      case 28: rc = launch_scan2<28>(a, p, st); break;
+      case 32: rc = launch_scan2<32>(a, p, st); break;
+      default: break;
+    }
   }
   if (rc != RR_OK) return rc;
   MergeArgs m;
-  m.k1 = a.part_k1;
-  m.k2 = a.part_k2;
-  m.n_in = (long long)p.slabs * k;
+  m.k1 = part_k1;
+  m.k2 = part_k2;
+  m.n_in = (long long)slabs * k;
   m.k = k;
   m.cap = 0;
   m.row_base = row_base;

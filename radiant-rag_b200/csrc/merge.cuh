@@ -69,12 +69,12 @@ __device__ __forceinline__ void merge_write(void* out_a, long long* out_idx, siz
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(MERGE_THREADS) merge_pairs_kernel(const MergeArgs a) {
+template <int MODE, int THREADS>
+__global__ void __launch_bounds__(THREADS) merge_pairs_kernel(const MergeArgs a) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
   u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
   u32* s_k2 = reinterpret_cast<u32*>(s_k1 + a.cap);
-  __shared__ SelectScratch<MERGE_THREADS> sc;
+  __shared__ SelectScratch<THREADS> sc;
   const int q = blockIdx.x;
   const u64* k1 = a.k1 + (size_t)q * a.n_in;
   const u32* k2 = a.k2 ? a.k2 + (size_t)q * a.n_in : nullptr;
@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(MERGE_THREADS) merge_pairs_kernel(const MergeA
     x = k1[i];
     y = k2 ? k2[i] : 0u;
   };
-  const int m = block_select_sorted<MERGE_THREADS>(get, a.n_in, a.k, s_k1, s_k2, a.cap, sc);
-  for (int j = threadIdx.x; j < a.k; j += MERGE_THREADS) {
+  const int m = block_select_sorted<THREADS>(get, a.n_in, a.k, s_k1, s_k2, a.cap, sc);
+  for (int j = threadIdx.x; j < a.k; j += THREADS) {
     const bool have = j < m;
     merge_write<MODE>(a.out_a, a.out_idx, (size_t)q * a.k + j, have, have ? s_k1[j] : 0,
                       have ? s_k2[j] : 0, a.row_base);
@@ -99,10 +99,15 @@ static inline int merge_cap(int k) {
   return c;
 }
 
+// Few queries and long lists: one CTA per query is all the parallelism there is, so use
+// the widest block; otherwise 256 threads and several CTAs per SM.
 template <int MODE>
 static int launch_merge_pairs(MergeArgs a, int q, cudaStream_t st) {
   a.cap = merge_cap(a.k);
-  merge_pairs_kernel<MODE><<<q, MERGE_THREADS, (size_t)a.cap * 12, st>>>(a);
+  if (q <= 64 && a.n_in >= 8192)
+    merge_pairs_kernel<MODE, 1024><<<q, 1024, (size_t)a.cap * 12, st>>>(a);
+  else
+    merge_pairs_kernel<MODE, MERGE_THREADS><<<q, MERGE_THREADS, (size_t)a.cap * 12, st>>>(a);
   RR_LAUNCH_CHECK();
   return RR_OK;
 }
