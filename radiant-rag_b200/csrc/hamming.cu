@@ -321,15 +321,21 @@ static Scan2Plan plan_scan2(long long n, int words, int q, int k) {
   p.q_tile = (q + p.n_qtiles - 1) / p.n_qtiles;
   const int sms = sm_count() > 0 ? sm_count() : 148;
   // two resident CTAs per SM; one wave when memory-bound, two when compute-bound
+  // whole waves only: slabs * n_qtiles <= target, rounded DOWN (a few CTAs over a wave
+  // boundary cost a full extra wave)
   long long target = (q <= 4 ? 2LL : 4LL) * sms;
-  long long slabs = (target + p.n_qtiles - 1) / p.n_qtiles;
+  long long slabs = target / p.n_qtiles;
   const long long max_slabs = (n + 2047) / 2048;
   if (slabs > max_slabs) slabs = max_slabs;
   if (slabs < 1) slabs = 1;
-  long long rps = (n + slabs - 1) / slabs;
-  rps = (long long)align_up((size_t)rps, SCAN_TILE_ROWS);
   const long long max_rps = 1LL << SCAN_ROW_BITS;
-  if (rps > max_rps) rps = max_rps;
+  long long rps;
+  while (true) {
+    rps = (n + slabs - 1) / slabs;
+    rps = (long long)align_up((size_t)rps, SCAN_TILE_ROWS);
+    if (rps <= max_rps) break;
+    ++slabs;  // very large shards: more slabs than one wave, rows per slab capped by the key width
+  }
   p.rows_per_slab = rps;
   p.slabs = (int)((n + rps - 1) / rps);
   if (p.slabs < 1) p.slabs = 1;
@@ -452,8 +458,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) hamming_scan2_kernel(const Sc
       for (int j = 0; j < V; ++j) r[j] = *reinterpret_cast<const uint4*>(src + coff[j]);
     }
     const u32 local = (u32)(row - row_lo);
-#pragma unroll 1
-    for (int qi = 0; qi < nq; ++qi) {
+    auto distance = [&](int qi) -> int {
       const unsigned char* qb = sq + (size_t)qi * (W * 4);
       u32 x[W];
 #pragma unroll
@@ -464,7 +469,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) hamming_scan2_kernel(const Sc
         x[4 * j + 2] = r[j].z ^ c.z;
         x[4 * j + 3] = r[j].w ^ c.w;
       }
-      const int d = csa_popcount<W>(x);
+      return csa_popcount<W>(x);
+    };
+    auto offer = [&](int qi, int d) {
       const u32 key = ((u32)d << SCAN_ROW_BITS) | local;
       const bool pass = valid && (key < thr[qi]);
       const unsigned bal = __ballot_sync(0xffffffffu, pass);
@@ -474,7 +481,18 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) hamming_scan2_kernel(const Sc
         slot = __shfl_sync(0xffffffffu, slot, __ffs(bal) - 1);
         if (pass) queue[(size_t)qi * a.cap + slot + __popc(bal & ((1u << lane) - 1u))] = key;
       }
+    };
+    // two independent distance chains per iteration keep the POPC pipe busy across the
+    // (rarely taken) append branches
+    int qi = 0;
+#pragma unroll 1
+    for (; qi + 1 < nq; qi += 2) {
+      const int d0 = distance(qi);
+      const int d1 = distance(qi + 1);
+      offer(qi, d0);
+      offer(qi + 1, d1);
     }
+    if (qi < nq) offer(qi, distance(qi));
     __syncthreads();  // every thread has its row in registers and is done appending
     if (tid == 0 && t + a.stages < ntiles) issue_tile(t + a.stages);  // refill the freed slot
     for (int qi = warp; qi < nq; qi += SCAN_WARPS) {
