@@ -82,6 +82,32 @@ int rr_hamming_topk(const uint32_t* codes, int64_t n, int32_t words, const uint8
                     int32_t k, int64_t row_base, int32_t* out_dist, int64_t* out_idx,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- Tensor-core (tcgen05 kind::i8, TMEM accumulators, TMA-fed) formulation of the BATCHED
+ * stage-1 search: codes expanded once to +-1 int8 rows (rr_unpack_codes_pm1), hamming =
+ * (dim - dot) / 2 exactly.  Same results as rr_hamming_topk, bit for bit.  dim must be a
+ * multiple of 128 in [128, 1024].  *overflow (device u32, zeroed by the caller) is incremented
+ * when a query's filtered list outgrew its capacity; the caller must then redo the call with
+ * rr_hamming_topk (results of the overflowed call are not exact). */
+int rr_unpack_codes_pm1(const uint8_t* codes, int64_t n, int32_t code_stride, int32_t dim,
+                        int8_t* out, void* stream);
+size_t rr_tc_search_workspace_bytes(int64_t n, int32_t q, int32_t k);
+int rr_hamming_topk_tc(const int8_t* pm1, int64_t n, int32_t dim, const uint8_t* tags,
+                       uint8_t tag_mask, uint8_t tag_value, const int8_t* q_pm1, int32_t q,
+                       int32_t k, int64_t row_base, int32_t* out_dist, int64_t* out_idx,
+                       uint32_t* overflow, void* workspace, size_t workspace_bytes, void* stream);
+/* BASELINE config 4 on tensor cores: exact int8 x int8 -> int32 search, (score desc, row asc);
+ * same contract as rr_int8_search_topk, workspace from rr_tc_search_workspace_bytes. */
+int rr_int8_search_topk_tc(const int8_t* emb, int64_t n, int32_t dim, const uint8_t* tags,
+                           uint8_t tag_mask, uint8_t tag_value, const int8_t* queries_i8,
+                           int32_t q, int32_t top_k, int64_t row_base, int32_t* out_score,
+                           int64_t* out_idx, uint32_t* overflow, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+/* Test/debug: raw tensor-core scores as order-preserving keys, u32 [q][ceil(n/128)*128]
+ * (key = ~(score ^ 0x80000000), 0xFFFFFFFF = padded row). */
+int rr_tc_dense_keys(const int8_t* emb, int64_t n, int32_t dim, const int8_t* queries_i8, int32_t q,
+                     uint32_t* out_keys, void* stream);
+
 /* ---- R3: rescore_candidates (radiant/storage/quantization.py:185-222) plus the
  * caller's cut/filter (radiant/storage/redis_store.py:850-854).
  * queries f32 [q, dim]; emb rows [n, dim] of emb_dtype (RR_I8 rows are cast to f32,

@@ -40,6 +40,11 @@ PROTOTYPES = {
     "rr_quantize_int8": (_i32, [_p, _i64, _i32, _p, _p, _p]),
     "rr_hamming_topk_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "rr_hamming_topk": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _sz, _p]),
+    "rr_unpack_codes_pm1": (_i32, [_p, _i64, _i32, _i32, _p, _p]),
+    "rr_tc_search_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "rr_hamming_topk_tc": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
+    "rr_int8_search_topk_tc": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
+    "rr_tc_dense_keys": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p]),
     "rr_rescore_f32": (_i32, [_p, _i32, _i32, _p, _i32, _i64, _i64, _p, _i32, _i32, _f64, _p, _p, _p, _p]),
     "rr_score_candidates_f32": (_i32, [_p, _i32, _i32, _p, _i32, _i64, _i64, _p, _i32, _p, _p]),
     "rr_rank_scored_f32": (_i32, [_p, _p, _i32, _i32, _i32, _f64, _p, _p, _p, _p]),
@@ -72,6 +77,7 @@ _KERNELS_PER_CALL = {
     "rr_score_candidates_f32": 1, "rr_rank_scored_f32": 1, "rr_rescore_i8": 1,
     "rr_exact_search_f32": 2, "rr_int8_search_topk": 2, "rr_bm25_topk": 2, "rr_bm25_impacts": 1,
     "rr_rrf_fuse": 1, "rr_merge_hamming": 1, "rr_merge_scores_f64": 1, "rr_merge_scores_i32": 1,
+    "rr_unpack_codes_pm1": 1, "rr_tc_dense_keys": 1, "rr_hamming_topk_tc": 5, "rr_int8_search_topk_tc": 5,
     "rr_synth_rows_f32": 1, "rr_synth_query_rows_f32": 1, "rr_synth_doc_lengths": 1,
     "rr_synth_zipf_tokens": 1,
 }

@@ -1,0 +1,588 @@
+// Tensor-core exact search: int8 x int8 -> int32 scores on tcgen05 with a fused filter
+// epilogue, for (a) BASELINE config 4 (exact int8 search, "tensor-core rescoring") and
+// (b) the BATCHED Hamming scan, where the packed sign bits are expanded once to +-1 int8
+// rows and  hamming = (D - dot) / 2  exactly (above ~3 queries per
+// pass the POPC pipe, not HBM, bounds the popcount formulation).
+//
+// Kernel (one CTA per SM, 192 threads, warp-specialised):
+//   warp 0      TMA producer: the CTA's 128 queries (B operand, K-major, SWIZZLE_128B) are
+//               loaded once and stay resident in shared memory; corpus tiles of 128 rows x
+//               128 bytes of K (A operand) stream through a 4-stage mbarrier ring.
+//   warp 1      allocates TMEM and issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128,
+//               K=32 per instruction); two 128x128 int32 accumulators in TMEM are
+//               double-buffered against the epilogue.
+//   warps 2-5   epilogue: tcgen05.ld 32x32b.x32 brings a thread's row of 32 query scores to
+//               registers; a score is appended to its query's list only when it reaches the
+//               query's threshold tau_q.
+// Exact top-k without materialising Q x N scores (164 GB in config 4):
+//   pass 0  the same kernel in DENSE mode over a strided sample of row tiles (1/32 of the
+//           rows) -> per-query k-th best sample score tau_q (select_keys32 on the samples).
+//           At least k rows score >= tau_q in the full set, so
+//   pass 1  the FILTER pass over all rows keeps exactly the rows with score >= tau_q
+//           (about 32*k per query) and
+//   pass 2  block_select_sorted takes the exact top-k by (score desc, row asc).
+// A list that outgrows its capacity raises an overflow counter and the caller falls back
+// to the CUDA-core path (never observed on the synthetic corpora; guards adversarial data).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "merge.cuh"
+
+namespace rr {
+
+constexpr int TC_BM = 128;          // corpus rows per MMA tile (TMEM lanes)
+constexpr int TC_BN = 128;          // queries per CTA (TMEM columns per accumulator)
+constexpr int TC_BK = 128;          // bytes of K per stage = one 128B swizzle atom row
+constexpr int TC_STAGES = 4;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK;  // 16 KB
+constexpr int TC_MAX_KB = 8;                  // dim <= 1024
+
+// ---- PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ u32 tc_smem(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(u32 bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(u32 bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(u32 bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(u32 bar, u32 parity) {
+  u32 done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tc_tma_load_2d(u32 dst, const CUtensorMap* map, int c0, int c1, u32 bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(u32 bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(u32 d_tmem, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4 | LBO = 1 (unused for swizzled K-major) | SBO = 1024 B (8-row group) |
+// version 1 (Blackwell) | layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ u64 tc_smem_desc(u32 saddr) {
+  return (u64)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor for kind::i8: D = S32, A = B = signed int8, both K-major,
+// N = 128 (>>3 at bit 17), M = 128 (>>4 at bit 24).
+constexpr u32 TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((u32)(TC_BN >> 3) << 17) | ((u32)(TC_BM >> 4) << 24);
+
+struct TcArgs {
+  long long n;          // corpus rows
+  int q;                // queries
+  int kb;               // K blocks of 128 bytes (dim / 128)
+  long long tile_stride;  // launched tile i covers corpus tile i * tile_stride
+  long long n_tiles;      // launched tiles
+  const uint8_t* tags;
+  unsigned tag_mask, tag_value;
+  const int* tau;       // [q] thresholds or nullptr (keep everything; dense mode)
+  int dense;            // 1: write keys [q][n_tiles*128]; 0: filtered lists
+  u32* dense_keys;      // dense mode output (order-preserving ~score keys, 0xFFFFFFFF invalid)
+  u32* cnt;             // [q] list lengths
+  int* list_score;      // [q][cap]
+  u32* list_row;        // [q][cap]
+  int cap;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    tc_i8_search_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                        const TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+  // 1024-byte aligned carve-up: B blocks, A stages, then small state
+  unsigned char* base = reinterpret_cast<unsigned char*>(align_up_dev((size_t)tc_smem_raw, 1024));
+  unsigned char* sb = base;                                   // [kb][16 KB]
+  unsigned char* sa = sb + (size_t)a.kb * TC_TILE_BYTES;      // [stages][16 KB]
+  int* thr = reinterpret_cast<int*>(sa + (size_t)TC_STAGES * TC_TILE_BYTES);  // [128]
+  u64* bars = reinterpret_cast<u64*>(thr + TC_BN);
+  u64* full_a = bars;                  // [stages]
+  u64* empty_a = bars + TC_STAGES;     // [stages]
+  u64* b_full = bars + 2 * TC_STAGES;  // [1]
+  u64* tmem_full = b_full + 1;         // [2]
+  u64* tmem_empty = tmem_full + 2;     // [2]
+  u32* tmem_ptr = reinterpret_cast<u32*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int qb = blockIdx.y;           // query block of 128
+  const int q0 = qb * TC_BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      tc_mbar_init(tc_smem(full_a + s), 1);
+      tc_mbar_init(tc_smem(empty_a + s), 1);
+    }
+    tc_mbar_init(tc_smem(b_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      tc_mbar_init(tc_smem(tmem_full + s), 1);
+      tc_mbar_init(tc_smem(tmem_empty + s), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: 2 accumulators x 128 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(tmem_ptr)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    const int t = threadIdx.x - 64;  // 0..127
+    const int qq = q0 + t;
+    thr[t] = (a.tau != nullptr && qq < a.q) ? a.tau[qq] : (int)0x80000000;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const u32 tmem_base = *reinterpret_cast<volatile u32*>(tmem_ptr);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      tc_mbar_expect_tx(tc_smem(b_full), (u32)(a.kb * TC_TILE_BYTES));
+      for (int kb = 0; kb < a.kb; ++kb)
+        tc_tma_load_2d(tc_smem(sb + (size_t)kb * TC_TILE_BYTES), &map_b, kb * TC_BK, q0, tc_smem(b_full));
+      u32 it = 0;
+      for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x) {
+        const long long row0 = i * a.tile_stride * TC_BM;
+        for (int kb = 0; kb < a.kb; ++kb, ++it) {
+          const u32 s = it % TC_STAGES;
+          tc_mbar_wait(tc_smem(empty_a + s), ((it / TC_STAGES) & 1u) ^ 1u);
+          tc_mbar_expect_tx(tc_smem(full_a + s), TC_TILE_BYTES);
+          tc_tma_load_2d(tc_smem(sa + (size_t)s * TC_TILE_BYTES), &map_a, kb * TC_BK, (int)row0, tc_smem(full_a + s));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    tc_mbar_wait(tc_smem(b_full), 0);
+    tc_fence_after();
+    u32 it = 0, tcount = 0;
+    for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
+      const u32 as = tcount & 1u;
+      tc_mbar_wait(tc_smem(tmem_empty + as), ((tcount >> 1) & 1u) ^ 1u);
+      tc_fence_after();
+      const u32 d_tmem = tmem_base + as * TC_BN;
+      for (int kb = 0; kb < a.kb; ++kb, ++it) {
+        const u32 s = it % TC_STAGES;
+        tc_mbar_wait(tc_smem(full_a + s), (it / TC_STAGES) & 1u);
+        tc_fence_after();
+        if (lane == 0) {
+          const u32 a_addr = tc_smem(sa + (size_t)s * TC_TILE_BYTES);
+          const u32 b_addr = tc_smem(sb + (size_t)kb * TC_TILE_BYTES);
+#pragma unroll
+          for (int k4 = 0; k4 < TC_BK / 32; ++k4)
+            tc_mma_i8(d_tmem, tc_smem_desc(a_addr + k4 * 32), tc_smem_desc(b_addr + k4 * 32), TC_IDESC,
+                      (kb | k4) != 0 ? 1u : 0u);
+          tc_commit(tc_smem(empty_a + s));  // frees the A stage when these MMAs have read it
+        }
+        __syncwarp();
+      }
+      if (lane == 0) tc_commit(tc_smem(tmem_full + as));  // accumulator complete
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int lq = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    u32 tcount = 0;
+    for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
+      const u32 as = tcount & 1u;
+      tc_mbar_wait(tc_smem(tmem_full + as), (tcount >> 1) & 1u);
+      tc_fence_after();
+      const long long row = i * a.tile_stride * TC_BM + lq * 32 + lane;
+      bool valid = row < a.n;
+      if (valid && a.tags != nullptr) valid = ((unsigned)a.tags[row] & a.tag_mask) == a.tag_value;
+      const long long dense_col = i * TC_BM + lq * 32 + lane;  // position among the launched rows
+      const long long dense_ld = a.n_tiles * TC_BM;
+#pragma unroll 1
+      for (int c = 0; c < TC_BN / 32; ++c) {
+        u32 v[32];
+        const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + as * TC_BN + c * 32;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int qq = q0 + c * 32 + j;
+          const int s = (int)v[j];
+          if (a.dense) {
+            if (qq < a.q) a.dense_keys[(size_t)qq * dense_ld + dense_col] = valid ? ~i32_orderable(s) : 0xFFFFFFFFu;
+          } else if (valid && qq < a.q && s >= thr[c * 32 + j]) {
+            const u32 slot = atomicAdd(a.cnt + qq, 1u);
+            if (slot < (u32)a.cap) {
+              a.list_score[(size_t)qq * a.cap + slot] = s;
+              a.list_row[(size_t)qq * a.cap + slot] = (u32)row;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      tc_mbar_arrive(tc_smem(tmem_empty + as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// tau_q = k-th best sample score, or INT_MIN when the sample holds fewer than k valid rows
+__global__ void tc_tau_kernel(const int* sample_scores, const int* sample_count, int q, int k, int* tau) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < q) tau[i] = (sample_count[i] >= k) ? sample_scores[(size_t)i * k + (k - 1)] : (int)0x80000000;
+}
+
+// exact top-k of each query's filtered list, (score desc, row asc)
+template <int MODE>  // MERGE_I32_DESC: scores as is; MERGE_HAMMING: dist = (dim - score) / 2
+__global__ void __launch_bounds__(MERGE_THREADS)
+    tc_select_lists_kernel(const u32* cnt, const int* list_score, const u32* list_row, int cap, int k, int kcap,
+                           int dim, long long row_base, void* out_a, long long* out_idx, int* out_count,
+                           unsigned* overflow) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
+  u32* s_k2 = reinterpret_cast<u32*>(s_k1 + kcap);
+  __shared__ SelectScratch<MERGE_THREADS> sc;
+  const int q = blockIdx.x;
+  const u32 c = cnt[q];
+  if (c > (u32)cap && threadIdx.x == 0) atomicAdd(overflow, 1u);
+  const long long n = c < (u32)cap ? c : cap;
+  const int* ls = list_score + (size_t)q * cap;
+  const u32* lr = list_row + (size_t)q * cap;
+  auto get = [&](long long i, u64& x, u32& y) {
+    x = (u64)(~i32_orderable(ls[i]));
+    y = lr[i];
+  };
+  const int m = block_select_sorted<MERGE_THREADS>(get, n, k, s_k1, s_k2, kcap, sc);
+  for (int j = threadIdx.x; j < k; j += MERGE_THREADS) {
+    const size_t o = (size_t)q * k + j;
+    if (j < m) {
+      const int s = i32_from_orderable((u32)(~s_k1[j]));
+      reinterpret_cast<int*>(out_a)[o] = (MODE == MERGE_HAMMING) ? (dim - s) / 2 : s;
+      out_idx[o] = (long long)s_k2[j] + row_base;
+    } else {
+      reinterpret_cast<int*>(out_a)[o] = (MODE == MERGE_HAMMING) ? 0x7fffffff : (int)0x80000000;
+      out_idx[o] = -1;
+    }
+  }
+  if (out_count && threadIdx.x == 0) out_count[q] = m;
+}
+
+// packed sign bits (np.packbits order) -> +-1 int8 rows
+__global__ void __launch_bounds__(256) unpack_pm1_kernel(const uint8_t* __restrict__ codes, long long n,
+                                                         int stride_bytes, int dim, int8_t* __restrict__ out) {
+  const int bytes_per_row = dim >> 3;
+  const long long total = n * bytes_per_row;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+    const long long row = i / bytes_per_row;
+    const int b = (int)(i % bytes_per_row);
+    const unsigned byte = codes[row * stride_bytes + b];
+    u32 lo = 0, hi = 0;  // dims 8b..8b+3 and 8b+4..8b+7; dim 8b is bit 7
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      lo |= (((byte >> (7 - j)) & 1u) ? 0x01u : 0xFFu) << (8 * j);
+      hi |= (((byte >> (3 - j)) & 1u) ? 0x01u : 0xFFu) << (8 * j);
+    }
+    *reinterpret_cast<uint2*>(out + row * dim + 8 * b) = make_uint2(lo, hi);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// rows x dim int8 matrix, K-major; box = 128 rows x 128 bytes, SWIZZLE_128B
+static int make_map(CUtensorMap* map, const void* ptr, long long rows, int dim) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return RR_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)dim};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld dim=%d", (int)r, rows, dim);
+    return RR_ERR_CUDA;
+  }
+  return RR_OK;
+}
+
+constexpr int TC_SAMPLE_STRIDE = 32;  // pass 0 scores every 32nd row tile
+
+struct TcPlan {
+  long long tiles, sample_tiles;
+  int cap;
+  size_t off_keys, off_sscore, off_sidx, off_scount, off_tau, off_cnt, off_ls, off_lr, off_ovf, total;
+};
+
+static TcPlan tc_plan(long long n, int q, int k) {
+  TcPlan p;
+  p.tiles = (n + TC_BM - 1) / TC_BM;
+  p.sample_tiles = (p.tiles + TC_SAMPLE_STRIDE - 1) / TC_SAMPLE_STRIDE;
+  // the sample must be able to hold k rows; tiny corpora are sampled completely
+  if (p.sample_tiles * TC_BM < 4LL * k || p.sample_tiles * TC_BM < 2048) p.sample_tiles = p.tiles;
+  long long expect = (long long)k * (p.tiles / p.sample_tiles + 1);
+  long long cap = 4 * expect + 1024;
+  if (cap > n + 128) cap = n + 128;
+  p.cap = (int)cap;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
+  p.off_keys = take((size_t)q * p.sample_tiles * TC_BM * 4);
+  p.off_sscore = take((size_t)q * k * 4);
+  p.off_sidx = take((size_t)q * k * 8);
+  p.off_scount = take((size_t)q * 4);
+  p.off_tau = take((size_t)q * 4);
+  p.off_cnt = take((size_t)q * 4);
+  p.off_ls = take((size_t)q * p.cap * 4);
+  p.off_lr = take((size_t)q * p.cap * 4);
+  p.off_ovf = take(256);
+  p.total = o + 256;
+  return p;
+}
+
+static size_t tc_smem_bytes(int kb) {
+  return 1024 + (size_t)kb * TC_TILE_BYTES + (size_t)TC_STAGES * TC_TILE_BYTES + TC_BN * 4 + 16 * 8 + 64;
+}
+
+// select_keys32_kernel lives in exact.cu; the tensor-core path needs the same selection on
+// its dense sample keys, so a local copy of the launch is kept here.
+template <int MODE>
+__global__ void __launch_bounds__(MERGE_THREADS)
+    tc_select_keys32_kernel(const u32* keys, long long n, int k, int cap, void* out_a, long long* out_idx,
+                            int* out_count) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
+  u32* s_k2 = reinterpret_cast<u32*>(s_k1 + cap);
+  __shared__ SelectScratch<MERGE_THREADS> sc;
+  const int q = blockIdx.x;
+  const u32* kq = keys + (size_t)q * n;
+  auto get = [&](long long i, u64& x, u32& y) {
+    const u32 key = kq[i];
+    x = (key == 0xFFFFFFFFu) ? K1_INVALID : (u64)key;
+    y = (u32)i;
+  };
+  const int m = block_select_sorted<MERGE_THREADS>(get, n, k, s_k1, s_k2, cap, sc);
+  for (int j = threadIdx.x; j < k; j += MERGE_THREADS) {
+    const bool have = j < m;
+    merge_write<MODE>(out_a, out_idx, (size_t)q * k + j, have, have ? s_k1[j] : 0, have ? s_k2[j] : 0, 0);
+  }
+  if (out_count && threadIdx.x == 0) out_count[q] = m;
+}
+
+// mode: 0 = int8 scores (score desc), 1 = Hamming over +-1 rows (dist asc)
+static int tc_search(const int8_t* emb, long long n, int dim, const uint8_t* tags, unsigned tag_mask,
+                     unsigned tag_value, const int8_t* queries, int q, int k, long long row_base, int hamming,
+                     int* out_a, long long* out_idx, unsigned* overflow_out, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  const TcPlan p = tc_plan(n, q, k);
+  if (!ws || ws_bytes < p.total) {
+    set_error("tensor-core search: workspace %zu < %zu", ws_bytes, p.total);
+    return RR_ERR_WORKSPACE;
+  }
+  char* w = (char*)ws;
+  CUtensorMap map_a, map_b;
+  int rc = make_map(&map_a, emb, n, dim);
+  if (rc != RR_OK) return rc;
+  rc = make_map(&map_b, queries, q, dim);
+  if (rc != RR_OK) return rc;
+  const int kb = dim / TC_BK;
+  const size_t smem = tc_smem_bytes(kb);
+  RR_CUDA(cudaFuncSetAttribute(tc_i8_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int qblocks = (q + TC_BN - 1) / TC_BN;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int ctas_x = sms / qblocks;
+  if (ctas_x < 1) ctas_x = 1;
+
+  TcArgs a;
+  a.n = n;
+  a.q = q;
+  a.kb = kb;
+  a.tags = tags;
+  a.tag_mask = tag_mask;
+  a.tag_value = tag_value;
+  a.cnt = (u32*)(w + p.off_cnt);
+  a.list_score = (int*)(w + p.off_ls);
+  a.list_row = (u32*)(w + p.off_lr);
+  a.cap = p.cap;
+  a.dense_keys = (u32*)(w + p.off_keys);
+
+  // ---- pass 0: dense scores of a strided sample of row tiles -> tau
+  const bool full_sample = p.sample_tiles == p.tiles;
+  a.tile_stride = full_sample ? 1 : TC_SAMPLE_STRIDE;
+  a.n_tiles = p.sample_tiles;
+  a.tau = nullptr;
+  a.dense = 1;
+  {
+    dim3 grid((unsigned)(a.n_tiles < ctas_x ? a.n_tiles : ctas_x), qblocks);
+    tc_i8_search_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
+    RR_LAUNCH_CHECK();
+  }
+  const int kcap = merge_cap(k);
+  tc_select_keys32_kernel<MERGE_I32_DESC><<<q, MERGE_THREADS, (size_t)kcap * 12, st>>>(
+      a.dense_keys, p.sample_tiles * TC_BM, k, kcap, w + p.off_sscore, (long long*)(w + p.off_sidx),
+      (int*)(w + p.off_scount));
+  RR_LAUNCH_CHECK();
+  tc_tau_kernel<<<(q + 255) / 256, 256, 0, st>>>((const int*)(w + p.off_sscore), (const int*)(w + p.off_scount), q,
+                                                 k, (int*)(w + p.off_tau));
+  RR_LAUNCH_CHECK();
+
+  // ---- pass 1: filter pass over all rows
+  RR_CUDA(cudaMemsetAsync(w + p.off_cnt, 0, (size_t)q * 4, st));
+  a.tile_stride = 1;
+  a.n_tiles = p.tiles;
+  a.tau = (const int*)(w + p.off_tau);
+  a.dense = 0;
+  {
+    dim3 grid((unsigned)(a.n_tiles < ctas_x ? a.n_tiles : ctas_x), qblocks);
+    tc_i8_search_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
+    RR_LAUNCH_CHECK();
+  }
+  // ---- pass 2: exact top-k of each list
+  if (hamming)
+    tc_select_lists_kernel<MERGE_HAMMING><<<q, MERGE_THREADS, (size_t)kcap * 12, st>>>(
+        a.cnt, a.list_score, a.list_row, p.cap, k, kcap, dim, row_base, out_a, out_idx, nullptr, overflow_out);
+  else
+    tc_select_lists_kernel<MERGE_I32_DESC><<<q, MERGE_THREADS, (size_t)kcap * 12, st>>>(
+        a.cnt, a.list_score, a.list_row, p.cap, k, kcap, dim, row_base, out_a, out_idx, nullptr, overflow_out);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
+}  // namespace rr
+
+using namespace rr;
+
+extern "C" int rr_unpack_codes_pm1(const uint8_t* codes, int64_t n, int32_t code_stride, int32_t dim,
+                                   int8_t* out, void* stream) {
+  RR_CHECK_ARG(n >= 0 && dim > 0 && dim % 8 == 0 && code_stride * 8 >= dim, "bad size (dim must be a multiple of 8)");
+  if (n == 0) return RR_OK;
+  RR_CHECK_ARG(codes && out, "null pointer");
+  const long long total = (long long)n * (dim / 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148LL * 32) blocks = 148LL * 32;
+  unpack_pm1_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(codes, n, code_stride, dim, out);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
+extern "C" size_t rr_tc_search_workspace_bytes(int64_t n, int32_t q, int32_t k) {
+  if (n <= 0 || q <= 0 || k <= 0) return 256;
+  return tc_plan(n, q, k).total;
+}
+
+static int tc_check(int64_t n, int32_t dim, int32_t q, int32_t k) {
+  RR_CHECK_ARG(n >= 1 && q >= 1, "bad size");
+  RR_CHECK_ARG(dim % TC_BK == 0 && dim >= TC_BK && dim <= TC_BK * TC_MAX_KB,
+               "tensor-core path needs dim to be a multiple of 128 in [128, 1024]");
+  RR_CHECK_ARG(k >= 1 && k <= RR_MAX_K, "k out of range");
+  RR_CHECK_ARG(n < (1LL << 31), "shard larger than 2^31 rows");
+  return RR_OK;
+}
+
+extern "C" int rr_hamming_topk_tc(const int8_t* pm1, int64_t n, int32_t dim, const uint8_t* tags,
+                                  uint8_t tag_mask, uint8_t tag_value, const int8_t* q_pm1, int32_t q,
+                                  int32_t k, int64_t row_base, int32_t* out_dist, int64_t* out_idx,
+                                  uint32_t* overflow, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = tc_check(n, dim, q, k);
+  if (rc != RR_OK) return rc;
+  RR_CHECK_ARG(pm1 && q_pm1 && out_dist && out_idx && overflow, "null pointer");
+  return tc_search(pm1, n, dim, tags, tag_mask, tag_value, q_pm1, q, k, row_base, 1, out_dist,
+                   (long long*)out_idx, overflow, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int rr_int8_search_topk_tc(const int8_t* emb, int64_t n, int32_t dim, const uint8_t* tags,
+                                      uint8_t tag_mask, uint8_t tag_value, const int8_t* queries_i8, int32_t q,
+                                      int32_t top_k, int64_t row_base, int32_t* out_score, int64_t* out_idx,
+                                      uint32_t* overflow, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  int rc = tc_check(n, dim, q, top_k);
+  if (rc != RR_OK) return rc;
+  RR_CHECK_ARG(emb && queries_i8 && out_score && out_idx && overflow, "null pointer");
+  return tc_search(emb, n, dim, tags, tag_mask, tag_value, queries_i8, q, top_k, row_base, 0, out_score,
+                   (long long*)out_idx, overflow, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// Debug / test entry: raw tensor-core scores of every row as order-preserving keys
+// (key = ~(score ^ 0x80000000); 0xFFFFFFFF marks padded or filtered rows), u32 [q][ld] with
+// ld = ceil(n / 128) * 128.  Lets the parity tests check the MMA path in isolation.
+extern "C" int rr_tc_dense_keys(const int8_t* emb, int64_t n, int32_t dim, const int8_t* queries_i8, int32_t q,
+                                uint32_t* out_keys, void* stream) {
+  int rc = tc_check(n, dim, q, 1);
+  if (rc != RR_OK) return rc;
+  RR_CHECK_ARG(emb && queries_i8 && out_keys, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUtensorMap map_a, map_b;
+  rc = make_map(&map_a, emb, n, dim);
+  if (rc != RR_OK) return rc;
+  rc = make_map(&map_b, queries_i8, q, dim);
+  if (rc != RR_OK) return rc;
+  const int kb = dim / TC_BK;
+  const size_t smem = tc_smem_bytes(kb);
+  RR_CUDA(cudaFuncSetAttribute(tc_i8_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int qblocks = (q + TC_BN - 1) / TC_BN;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int ctas_x = sms / qblocks;
+  if (ctas_x < 1) ctas_x = 1;
+  TcArgs a;
+  a.n = n;
+  a.q = q;
+  a.kb = kb;
+  a.tile_stride = 1;
+  a.n_tiles = (n + TC_BM - 1) / TC_BM;
+  a.tags = nullptr;
+  a.tag_mask = a.tag_value = 0;
+  a.tau = nullptr;
+  a.dense = 1;
+  a.dense_keys = out_keys;
+  a.cnt = nullptr;
+  a.list_score = nullptr;
+  a.list_row = nullptr;
+  a.cap = 0;
+  dim3 grid((unsigned)(a.n_tiles < ctas_x ? a.n_tiles : ctas_x), qblocks);
+  tc_i8_search_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}

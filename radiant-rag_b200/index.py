@@ -103,7 +103,11 @@ class DenseIndex:
         int8_ranges: Optional[ArrayLike] = None,
         row_base: int = 0,
         capacity: int = 0,
+        store_pm1: bool = False,
     ) -> None:
+        """store_pm1: also keep the codes expanded to +-1 int8 rows [cap, dim] (8x the code
+        bytes) so BATCHED stage-1 searches run on the tensor cores (rr_hamming_topk_tc);
+        needs dim to be a multiple of 128, ignored otherwise."""
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         if self.device.type != "cuda":
             raise _lib.RadiantB200Error("DenseIndex needs a CUDA device; there is no CPU fallback")
@@ -122,6 +126,10 @@ class DenseIndex:
         self.f32: Optional[torch.Tensor] = None
         self.tags: Optional[torch.Tensor] = None
         self.tags_uniform = True  # every row has the default tag: the scan can skip the tag read
+        self.store_pm1 = bool(store_pm1) and self.dim % 128 == 0 and 128 <= self.dim <= 1024
+        self.pm1: Optional[torch.Tensor] = None
+        self.tc_min_queries = 16  # below this the POPC scan (memory-bound) is the faster path
+        self._tc_overflow: Optional[torch.Tensor] = None
         self.ranges: Optional[torch.Tensor] = None
         if int8_ranges is not None:
             self.set_int8_ranges(int8_ranges)
@@ -152,6 +160,8 @@ class DenseIndex:
             self.int8 = grow(self.int8, (cap, self.dim), torch.int8)
         if self.store_f32:
             self.f32 = grow(self.f32, (cap, self.dim), torch.float32)
+        if self.store_pm1:
+            self.pm1 = grow(self.pm1, (cap, self.dim), torch.int8)
         self._cap = cap
 
     def set_int8_ranges(self, ranges: ArrayLike) -> None:
@@ -176,6 +186,9 @@ class DenseIndex:
         self._reserve(hi)
         _lib.call("rr_quantize_ubinary", e.data_ptr(), m, self.dim, self.codes[lo:hi].data_ptr(),
                   self.words * 4, _stream())
+        if self.store_pm1:
+            _lib.call("rr_unpack_codes_pm1", self.codes[lo:hi].data_ptr(), m, self.words * 4, self.dim,
+                      self.pm1[lo:hi].data_ptr(), _stream())
         if self.store_int8:
             if self.ranges is None:
                 raise ValueError("int8 storage needs calibration ranges (set_int8_ranges)")
@@ -197,6 +210,9 @@ class DenseIndex:
         e = to_device(emb, self.device, torch.float32).reshape(1, self.dim)
         _lib.call("rr_quantize_ubinary", e.data_ptr(), 1, self.dim, self.codes[row:row + 1].data_ptr(),
                   self.words * 4, _stream())
+        if self.store_pm1:
+            _lib.call("rr_unpack_codes_pm1", self.codes[row:row + 1].data_ptr(), 1, self.words * 4, self.dim,
+                      self.pm1[row:row + 1].data_ptr(), _stream())
         if self.store_int8:
             _lib.call("rr_quantize_int8", e.data_ptr(), 1, self.dim, self.ranges.data_ptr(),
                       self.int8[row:row + 1].data_ptr(), _stream())
@@ -236,9 +252,8 @@ class DenseIndex:
                 return None, 0, 0
         return self.tags.data_ptr(), tag_mask, tag_value
 
-    def hamming_topk(self, qcodes: torch.Tensor, k: int, tag_mask: int = 0,
-                     tag_value: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
-        """Exact top-k by (dist asc, row asc).  -> (dist int32 [q,k], idx int64 [q,k])."""
+    def _hamming_topk_popc(self, qcodes: torch.Tensor, k: int, tag_mask: int, tag_value: int
+                           ) -> Tuple[torch.Tensor, torch.Tensor]:
         q = qcodes.shape[0]
         dist = torch.empty((q, k), dtype=torch.int32, device=self.device)
         idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
@@ -250,6 +265,56 @@ class DenseIndex:
                   self.words, tptr, tm, tv, qcodes.data_ptr(), q, k, self.row_base, dist.data_ptr(),
                   idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
         return dist, idx
+
+    def _hamming_topk_tc(self, qcodes: torch.Tensor, k: int, tag_mask: int, tag_value: int
+                         ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Tensor-core path; also returns the device overflow counter of this call."""
+        q = qcodes.shape[0]
+        q_pm1 = torch.empty((q, self.dim), dtype=torch.int8, device=self.device)
+        _lib.call("rr_unpack_codes_pm1", qcodes.data_ptr(), q, self.words * 4, self.dim, q_pm1.data_ptr(),
+                  _stream())
+        dist = torch.empty((q, k), dtype=torch.int32, device=self.device)
+        idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        ovf = torch.zeros(1, dtype=torch.int32, device=self.device)
+        lib = _lib.load()
+        ws_bytes = lib.rr_tc_search_workspace_bytes(self.n, q, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        tptr, tm, tv = self._tag_args(tag_mask, tag_value)
+        _lib.call("rr_hamming_topk_tc", self.pm1.data_ptr(), self.n, self.dim, tptr, tm, tv, q_pm1.data_ptr(),
+                  q, k, self.row_base, dist.data_ptr(), idx.data_ptr(), ovf.data_ptr(), ws.data_ptr(),
+                  ws_bytes, _stream())
+        return dist, idx, ovf
+
+    def hamming_topk(self, qcodes: torch.Tensor, k: int, tag_mask: int = 0, tag_value: int = 0,
+                     use_tc: Optional[bool] = None, check_overflow: bool = True
+                     ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Exact top-k by (dist asc, row asc).  -> (dist int32 [q,k], idx int64 [q,k]).
+
+        Batches of >= tc_min_queries run on the tensor cores when the index keeps +-1 rows
+        (store_pm1); both paths return identical results.  The tensor-core path keeps, per
+        query, the rows that beat a sampled bound in a bounded list: if a list overflows
+        (adversarial data) the call is redone on the POPC path.  check_overflow=False skips
+        that host-side check (one device sync) and accumulates the counter in
+        ``tc_overflow_total()`` for the caller to verify later."""
+        self._activate()
+        q = qcodes.shape[0]
+        if use_tc is None:
+            use_tc = self.pm1 is not None and q >= self.tc_min_queries and self.n >= 4096
+        if not use_tc or self.pm1 is None or self.n == 0:
+            return self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
+        dist, idx, ovf = self._hamming_topk_tc(qcodes, k, tag_mask, tag_value)
+        if check_overflow:
+            if int(ovf.item()) != 0:
+                return self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
+        else:
+            if self._tc_overflow is None:
+                self._tc_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self._tc_overflow += ovf
+        return dist, idx
+
+    def tc_overflow_total(self) -> int:
+        """Overflow events of tensor-core calls made with check_overflow=False (0 = all exact)."""
+        return 0 if self._tc_overflow is None else int(self._tc_overflow.item())
 
     def rescore_source(self, prefer_int8: bool = True) -> Tuple[torch.Tensor, int]:
         """int8 rows preferred, float32 fallback (reference redis_store.py:820-840)."""
@@ -309,6 +374,7 @@ class DenseIndex:
         tag_mask: int = 0,
         tag_value: int = 0,
         prefer_int8: bool = True,
+        check_overflow: bool = True,
     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Batched two-stage retrieval (reference redis_store.py:757-861 for one query).
 
@@ -318,7 +384,7 @@ class DenseIndex:
         qf, qc = self.quantize_queries(queries)
         candidate_k = int(top_k * rescore_multiplier) if use_rescoring else top_k
         candidate_k = max(1, min(candidate_k, _lib.RR_MAX_K))
-        _dist, cand = self.hamming_topk(qc, candidate_k, tag_mask, tag_value)
+        _dist, cand = self.hamming_topk(qc, candidate_k, tag_mask, tag_value, check_overflow=check_overflow)
         if not use_rescoring:
             idx = cand[:, :top_k].contiguous()
             score = torch.ones(idx.shape, dtype=torch.float32, device=self.device)
@@ -351,7 +417,8 @@ class DenseIndex:
         return idx, score, count
 
     def search_int8_exact(self, queries_i8: ArrayLike, top_k: int, tag_mask: int = 0,
-                          tag_value: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+                          tag_value: int = 0, use_tc: Optional[bool] = None
+                          ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Exact int8 x int8 -> int32 search (BASELINE config 4).  -> (idx, score int32)."""
         self._activate()
         if self.int8 is None:
@@ -363,9 +430,20 @@ class DenseIndex:
         score = torch.empty((q, top_k), dtype=torch.int32, device=self.device)
         idx = torch.empty((q, top_k), dtype=torch.int64, device=self.device)
         lib = _lib.load()
+        tptr, tm, tv = self._tag_args(tag_mask, tag_value)
+        use_tc = (self.dim % 128 == 0 and 128 <= self.dim <= 1024 and q >= 8 and self.n >= 4096
+                  if use_tc is None else use_tc)
+        if use_tc:
+            ovf = torch.zeros(1, dtype=torch.int32, device=self.device)
+            ws_bytes = lib.rr_tc_search_workspace_bytes(self.n, q, top_k)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            _lib.call("rr_int8_search_topk_tc", self.int8.data_ptr(), self.n, self.dim, tptr, tm, tv,
+                      qi.data_ptr(), q, top_k, self.row_base, score.data_ptr(), idx.data_ptr(),
+                      ovf.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+            if int(ovf.item()) == 0:
+                return idx, score
         ws_bytes = lib.rr_int8_search_topk_workspace_bytes(self.n, q, top_k)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-        tptr, tm, tv = self._tag_args(tag_mask, tag_value)
         _lib.call("rr_int8_search_topk", self.int8.data_ptr(), self.n, self.dim, tptr, tm, tv,
                   qi.data_ptr(), q, top_k, self.row_base, score.data_ptr(), idx.data_ptr(),
                   ws.data_ptr(), ws_bytes, _stream())

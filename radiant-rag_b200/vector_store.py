@@ -40,12 +40,14 @@ class B200VectorStore(BaseVectorStore):
         int8_ranges: Optional[np.ndarray] = None,
         inner: Optional[Any] = None,
         max_content_chars: int = 200_000,
+        tensor_core_batches: bool = False,
     ) -> None:
         """quantization: a QuantizationConfig (this package's or the reference's);
         int8_ranges: [2, D] calibration, or loaded from ``quantization.int8_ranges_file``
         (reference redis_store.py:174-181); inner: optional reference store that keeps
         the documents themselves."""
         self._device = device
+        self._tensor_core_batches = tensor_core_batches  # keep +-1 rows: batched stage 1 on tcgen05
         self._quant_config = quantization or QuantizationConfig()
         self._inner = inner
         self._max_chars = max_content_chars
@@ -84,7 +86,8 @@ class B200VectorStore(BaseVectorStore):
                                "rescoring falls back to float32 rows")
             self._embedding_dim = dim
             self._index = DenseIndex(dim, device=self._device, store_int8=want_int8, store_f32=True,
-                                     int8_ranges=self._int8_ranges if want_int8 else None)
+                                     int8_ranges=self._int8_ranges if want_int8 else None,
+                                     store_pm1=self._tensor_core_batches)
 
     @property
     def index(self) -> Optional[DenseIndex]:
@@ -181,6 +184,8 @@ class B200VectorStore(BaseVectorStore):
                         idx.int8[row].copy_(idx.int8[last])
                     if idx.f32 is not None:
                         idx.f32[row].copy_(idx.f32[last])
+                    if idx.pm1 is not None:
+                        idx.pm1[row].copy_(idx.pm1[last])
                     moved = self._id_of[last]
                     self._id_of[row] = moved
                     self._row_of[moved] = row
