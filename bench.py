@@ -196,11 +196,15 @@ def run_gpu_arm(args) -> None:
     }
 
     def step_device():
-        return search.search_quantized(queries_dev, top_k, rescore_multiplier=mult, prefer_int8=False)
+        # tensor-core stage 1: the overflow counter is accumulated on device and verified
+        # once after the timed region (no host sync inside a step)
+        return search.search_quantized(queries_dev, top_k, rescore_multiplier=mult, prefer_int8=False,
+                                       check_overflow=False)
 
     def step_e2e():
         q = queries_host.to(dev, non_blocking=True)  # H2D of this step's queries (pinned)
-        idx, score, count = search.search_quantized(q, top_k, rescore_multiplier=mult, prefer_int8=False)
+        idx, score, count = search.search_quantized(q, top_k, rescore_multiplier=mult, prefer_int8=False,
+                                                    check_overflow=True)
         out_host["idx"].copy_(idx, non_blocking=True)
         out_host["score"].copy_(score, non_blocking=True)
         out_host["count"].copy_(count, non_blocking=True)
@@ -238,6 +242,8 @@ def run_gpu_arm(args) -> None:
     launches_per_step = launches // (args.steps + args.warmup)
     e2e_ms = timed(step_e2e, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else {}
+    if index.tc_overflow_total() != 0:
+        raise SystemExit("tensor-core candidate lists overflowed during the timed region: results not exact")
 
     if rank != 0:
         if world > 1:
@@ -266,11 +272,12 @@ def run_gpu_arm(args) -> None:
         return sum(a.elapsed_time(b) for a, b in evs) / reps
 
     reps = max(5, min(args.steps, 20))
-    scan_ms = time_stage(lambda: index.hamming_topk(qc, cand_k), reps)
+    scan_ms = time_stage(lambda: index.hamming_topk(qc, cand_k, check_overflow=False), reps)
+    scan_popc_ms = time_stage(lambda: index.hamming_topk(qc, cand_k, use_tc=False), reps)
     _d, cand = index.hamming_topk(qc, cand_k)
     rescore_ms = time_stage(lambda: index.rescore(qf, cand, top_k, 0.0, prefer_int8=False), reps)
     quant_ms = time_stage(lambda: index.quantize_queries(queries_dev), reps)
-    scan1_ms = time_stage(lambda: index.hamming_topk(qc[:1], cand_k), reps)
+    scan1_ms = time_stage(lambda: index.hamming_topk(qc[:1].contiguous(), cand_k), reps)
 
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
@@ -281,18 +288,26 @@ def run_gpu_arm(args) -> None:
     achieved = code_bytes / (scan_ms * 1e-3) / 1e9
     sm_clock = (clocks.get("sm_max_mhz") or 1965.0) * 1e6
     popc_peak = 148 * 16 * sm_clock  # 32-bit POPC lanes per second (16 / clk / SM)
-    popc_rate = nq * n_local * index.words / (scan_ms * 1e-3)
+    popc_rate = nq * n_local * index.words / (scan_popc_ms * 1e-3)
+    int8_ops = 2.0 * nq * n_local * index.words * 32
+    bf16_peak = float(json.loads(peaks_path.read_text()).get("bf16_tflops", 1590.0)) if peaks_path.exists() else 1590.0
     roofline = {
-        "kernel": "hamming_scan_kernel<24> + merge_pairs_kernel (rr_hamming_topk)",
-        "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "traffic": None, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": code_bytes,
-        "note": "at 256 queries per pass the scan is bound by the integer POPC pipe, not HBM (SURVEY 8d); see "
-                "int_pipe and the single-query figure, where HBM is the true bound",
-        "int_pipe": {"bound": "popc", "achieved": popc_rate / 1e12, "peak": popc_peak / 1e12,
-                     "unit": "T popc32/s", "frac": popc_rate / popc_peak},
-        "single_query": {"ms": scan1_ms, "achieved": code_bytes / (scan1_ms * 1e-3) / 1e9,
-                         "frac": code_bytes / (scan1_ms * 1e-3) / 1e9 / hbm_peak, "unit": "GB/s"},
+        "kernel": "rr_hamming_topk_tc: tc_i8_search_kernel (tcgen05 kind::i8) x2 + select kernels",
+        "bound": "tensor", "achieved": int8_ops / (scan_ms * 1e-3) / 1e12, "peak": 2.0 * bf16_peak,
+        "unit": "TOP/s", "frac": int8_ops / (scan_ms * 1e-3) / 1e12 / (2.0 * bf16_peak), "traffic": None,
+        "peak_source": "2 x measured dense bf16 cuBLAS burst (MEASURED_PEAKS.json); int8 is nominally 2x bf16",
+        "algorithmic_ops_per_launch": int8_ops, "algorithmic_bytes_per_launch": code_bytes,
+        "note": "batched stage 1 runs as a +-1 int8 GEMM on tcgen05 with packed codes expanded in shared "
+                "memory; HBM traffic is the packed codes only. hbm / popc views of the same stage below.",
+        "hbm_view": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "peak_source": peak_src},
+        "popc_path": {"ms": scan_popc_ms, "bound": "popc", "achieved": popc_rate / 1e12, "peak": popc_peak / 1e12,
+                      "unit": "T popc32/s", "frac": popc_rate / popc_peak},
+        "single_query": {"kernel": "hamming_scan2_kernel (POPC, TMA bulk staged)", "ms": scan1_ms, "bound": "hbm",
+                         "achieved": code_bytes / (scan1_ms * 1e-3) / 1e9,
+                         "frac": code_bytes / (scan1_ms * 1e-3) / 1e9 / hbm_peak, "unit": "GB/s",
+                         "note": "1M x 768 is only 96 MB; on the 12.5M x 1024 shard of the 100M-row config the "
+                                 "same kernel reaches 0.84 of the measured HBM peak (profiles/, tools/scan_bench.py)"},
     }
 
     # ---- CPU baseline: the oracle on a bounded sample of the same workload, 1 thread
@@ -327,7 +342,7 @@ def run_gpu_arm(args) -> None:
     line = {
         "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u8 codes (popc) + f32 rescore", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8 codes as +-1 int8 (tcgen05) + f32 rescore", "data": "synthetic",
         "config": {"workload": WORKLOAD, "corpus_rows": n, "dim": dim, "batch_queries": nq, "candidates": cand_k,
                    "top_k": top_k, "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}",
                    "l2": "flushed between timed iterations (256 MB fill)"},

@@ -83,15 +83,19 @@ int rr_hamming_topk(const uint32_t* codes, int64_t n, int32_t words, const uint8
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- Tensor-core (tcgen05 kind::i8, TMEM accumulators, TMA-fed) formulation of the BATCHED
- * stage-1 search: codes expanded once to +-1 int8 rows (rr_unpack_codes_pm1), hamming =
- * (dim - dot) / 2 exactly.  Same results as rr_hamming_topk, bit for bit.  dim must be a
- * multiple of 128 in [128, 1024].  *overflow (device u32, zeroed by the caller) is incremented
- * when a query's filtered list outgrew its capacity; the caller must then redo the call with
- * rr_hamming_topk (results of the overflowed call are not exact). */
+ * stage-1 search.  The packed codes are read as they are (1 bit per dimension from HBM) and
+ * expanded to +-1 int8 operand tiles in shared memory; hamming = (32*words - dot) / 2 exactly.
+ * Same arguments and bit-identical results as rr_hamming_topk, except:
+ *   q_pm1     i8 [q, 32*words]  the query codes expanded by rr_unpack_codes_pm1(qcodes, q,
+ *             4*words, 32*words, ...);
+ *   *overflow device u32, zeroed by the caller; incremented when a query's bounded candidate
+ *             list overflowed - the caller must then redo the call with rr_hamming_topk
+ *             (the results of an overflowed call are not exact);
+ *   workspace from rr_tc_search_workspace_bytes. */
 int rr_unpack_codes_pm1(const uint8_t* codes, int64_t n, int32_t code_stride, int32_t dim,
                         int8_t* out, void* stream);
 size_t rr_tc_search_workspace_bytes(int64_t n, int32_t q, int32_t k);
-int rr_hamming_topk_tc(const int8_t* pm1, int64_t n, int32_t dim, const uint8_t* tags,
+int rr_hamming_topk_tc(const uint32_t* codes, int64_t n, int32_t words, const uint8_t* tags,
                        uint8_t tag_mask, uint8_t tag_value, const int8_t* q_pm1, int32_t q,
                        int32_t k, int64_t row_base, int32_t* out_dist, int64_t* out_idx,
                        uint32_t* overflow, void* workspace, size_t workspace_bytes, void* stream);

@@ -1,13 +1,19 @@
 // Tensor-core exact search: int8 x int8 -> int32 scores on tcgen05 with a fused filter
 // epilogue, for (a) BASELINE config 4 (exact int8 search, "tensor-core rescoring") and
-// (b) the BATCHED Hamming scan, where the packed sign bits are expanded once to +-1 int8
-// rows and  hamming = (D - dot) / 2  exactly (above ~3 queries per
+// (b) the BATCHED Hamming scan, where the packed sign bits are expanded to +-1 int8 operand
+// tiles IN SHARED MEMORY (HBM traffic stays at 1 bit per dimension) and
+// hamming = (D - dot) / 2  exactly (above ~3 queries per
 // pass the POPC pipe, not HBM, bounds the popcount formulation).
 //
-// Kernel (one CTA per SM, 192 threads, warp-specialised):
+// Kernel (one CTA per SM, 320 threads, warp-specialised):
 //   warp 0      TMA producer: the CTA's 128 queries (B operand, K-major, SWIZZLE_128B) are
-//               loaded once and stay resident in shared memory; corpus tiles of 128 rows x
-//               128 bytes of K (A operand) stream through a 4-stage mbarrier ring.
+//               loaded once and stay resident in shared memory.  int8 mode: corpus tiles of
+//               128 rows x 128 bytes of K (A operand) stream through an mbarrier ring of TMA
+//               boxes.  Packed mode: each 128-row tile of packed codes is ONE contiguous
+//               bulk copy into a double buffer.
+//   warps 6-9   (packed mode) expand the tile's sign bits K block by K block into the A ring
+//               in the SWIZZLE_128B layout the UMMA descriptor expects (brev + multiply-spread,
+//               conflict-free 16-byte stores), fence.proxy.async, then signal the MMA warp.
 //   warp 1      allocates TMEM and issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128,
 //               K=32 per instruction); two 128x128 int32 accumulators in TMEM are
 //               double-buffered against the epilogue.
@@ -33,8 +39,8 @@ namespace rr {
 constexpr int TC_BM = 128;          // corpus rows per MMA tile (TMEM lanes)
 constexpr int TC_BN = 128;          // queries per CTA (TMEM columns per accumulator)
 constexpr int TC_BK = 128;          // bytes of K per stage = one 128B swizzle atom row
-constexpr int TC_STAGES = 4;
-constexpr int TC_THREADS = 192;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_THREADS = 320;  // producer, MMA, 4 epilogue warps, 4 unpack warps
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK;  // 16 KB
 constexpr int TC_MAX_KB = 8;                  // dim <= 1024
 
@@ -97,43 +103,68 @@ struct TcArgs {
   const int* tau;       // [q] thresholds or nullptr (keep everything; dense mode)
   int dense;            // 1: write keys [q][n_tiles*128]; 0: filtered lists
   u32* dense_keys;      // dense mode output (order-preserving ~score keys, 0xFFFFFFFF invalid)
-  u32* cnt;             // [q] list lengths
-  int* list_score;      // [q][cap]
-  u32* list_row;        // [q][cap]
-  int cap;
+  u32* cnt;             // [q][n_cta] list-segment lengths (written once per CTA at exit)
+  int* list_score;      // [q][n_cta][cap_cta]: every CTA appends to its own segment, so the
+  u32* list_row;        //   slot counters live in shared memory (no global atomics)
+  int cap_cta;
+  int stages;           // A-operand ring depth (<= TC_MAX_STAGES)
+  int packed;           // 1: A is built in shared memory from packed sign bits (packed_codes)
+  const uint8_t* packed_codes;  // [n][kb * 16] np.packbits rows (packed mode)
 };
 
+// Expand 32 packed sign bits (np.packbits order: dim 8b is the MSB of byte b, bytes in
+// little-endian word order) to 32 int8 values +1 / -1, as eight 32-bit words.
+__device__ __forceinline__ void tc_expand32(u32 w, u32 (&out)[8]) {
+  const u32 x = __byte_perm(__brev(w), 0, 0x0123);  // bit d = dim d
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const u32 nib = (x >> (4 * g)) & 0xFu;
+    const u32 t = (nib * 0x00204081u) & 0x01010101u;  // bit i of nib -> byte i
+    out[g] = ~(t * 0xFEu);                            // 1 -> 0x01 (+1), 0 -> 0xFF (-1)
+  }
+}
+
+// Thread layout: warp 0 producer, warp 1 MMA, warps 2-5 epilogue, warps 6-9 unpackers (only
+// in packed mode, where the A operand is built in shared memory from packed sign bits).
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_i8_search_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
-  // 1024-byte aligned carve-up: B blocks, A stages, then small state
+  // 1024-byte aligned carve-up: B blocks, A stages, [packed ring], then small state
   unsigned char* base = reinterpret_cast<unsigned char*>(align_up_dev((size_t)tc_smem_raw, 1024));
   unsigned char* sb = base;                                   // [kb][16 KB]
   unsigned char* sa = sb + (size_t)a.kb * TC_TILE_BYTES;      // [stages][16 KB]
-  int* thr = reinterpret_cast<int*>(sa + (size_t)TC_STAGES * TC_TILE_BYTES);  // [128]
-  u64* bars = reinterpret_cast<u64*>(thr + TC_BN);
-  u64* full_a = bars;                  // [stages]
-  u64* empty_a = bars + TC_STAGES;     // [stages]
-  u64* b_full = bars + 2 * TC_STAGES;  // [1]
-  u64* tmem_full = b_full + 1;         // [2]
-  u64* tmem_empty = tmem_full + 2;     // [2]
-  u32* tmem_ptr = reinterpret_cast<u32*>(tmem_empty + 2);
+  const int row_bytes = a.kb * 16;                            // packed bytes per row
+  unsigned char* spk = sa + (size_t)a.stages * TC_TILE_BYTES; // [2][128 * row_bytes] (packed mode)
+  int* thr = reinterpret_cast<int*>(spk + (a.packed ? 2 * (size_t)TC_BM * row_bytes : 0));  // [128]
+  u32* s_cnt = reinterpret_cast<u32*>(thr + TC_BN);                           // [128]
+  u64* bars = reinterpret_cast<u64*>(s_cnt + TC_BN);
+  u64* full_a = bars;                          // [stages]
+  u64* empty_a = bars + TC_MAX_STAGES;         // [stages]
+  u64* b_full = bars + 2 * TC_MAX_STAGES;      // [1]
+  u64* tmem_full = b_full + 1;                 // [2]
+  u64* tmem_empty = tmem_full + 2;             // [2]
+  u64* pk_full = tmem_empty + 2;               // [2]
+  u64* pk_empty = pk_full + 2;                 // [2]
+  u32* tmem_ptr = reinterpret_cast<u32*>(pk_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int qb = blockIdx.y;           // query block of 128
   const int q0 = qb * TC_BN;
+  const u32 stages = (u32)a.stages;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; ++s) {
-      tc_mbar_init(tc_smem(full_a + s), 1);
+    for (u32 s = 0; s < stages; ++s) {
+      tc_mbar_init(tc_smem(full_a + s), a.packed ? 128 : 1);
       tc_mbar_init(tc_smem(empty_a + s), 1);
     }
     tc_mbar_init(tc_smem(b_full), 1);
     for (int s = 0; s < 2; ++s) {
       tc_mbar_init(tc_smem(tmem_full + s), 1);
       tc_mbar_init(tc_smem(tmem_empty + s), 128);
+      tc_mbar_init(tc_smem(pk_full + s), 1);
+      tc_mbar_init(tc_smem(pk_empty + s), 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -141,10 +172,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(tmem_ptr)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= 2) {
+  if (warp >= 2 && warp < 6) {
     const int t = threadIdx.x - 64;  // 0..127
     const int qq = q0 + t;
     thr[t] = (a.tau != nullptr && qq < a.q) ? a.tau[qq] : (int)0x80000000;
+    s_cnt[t] = 0;
   }
   tc_fence_before();
   __syncthreads();
@@ -152,19 +184,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   const u32 tmem_base = *reinterpret_cast<volatile u32*>(tmem_ptr);
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== producer =====================
     if (lane == 0) {
       tc_mbar_expect_tx(tc_smem(b_full), (u32)(a.kb * TC_TILE_BYTES));
       for (int kb = 0; kb < a.kb; ++kb)
         tc_tma_load_2d(tc_smem(sb + (size_t)kb * TC_TILE_BYTES), &map_b, kb * TC_BK, q0, tc_smem(b_full));
-      u32 it = 0;
-      for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x) {
-        const long long row0 = i * a.tile_stride * TC_BM;
-        for (int kb = 0; kb < a.kb; ++kb, ++it) {
-          const u32 s = it % TC_STAGES;
-          tc_mbar_wait(tc_smem(empty_a + s), ((it / TC_STAGES) & 1u) ^ 1u);
-          tc_mbar_expect_tx(tc_smem(full_a + s), TC_TILE_BYTES);
-          tc_tma_load_2d(tc_smem(sa + (size_t)s * TC_TILE_BYTES), &map_a, kb * TC_BK, (int)row0, tc_smem(full_a + s));
+      if (!a.packed) {
+        // int8 rows straight from HBM: one 128-row x 128-byte TMA box per K block
+        u32 it = 0;
+        for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x) {
+          const long long row0 = i * a.tile_stride * TC_BM;
+          for (int kb = 0; kb < a.kb; ++kb, ++it) {
+            const u32 s = it % stages;
+            tc_mbar_wait(tc_smem(empty_a + s), ((it / stages) & 1u) ^ 1u);
+            tc_mbar_expect_tx(tc_smem(full_a + s), TC_TILE_BYTES);
+            tc_tma_load_2d(tc_smem(sa + (size_t)s * TC_TILE_BYTES), &map_a, kb * TC_BK, (int)row0, tc_smem(full_a + s));
+          }
+        }
+      } else {
+        // packed sign bits: the whole 128-row tile is one contiguous bulk copy
+        u32 tcount = 0;
+        for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
+          const long long row0 = i * a.tile_stride * TC_BM;
+          const u32 slot = tcount & 1u;
+          tc_mbar_wait(tc_smem(pk_empty + slot), ((tcount >> 1) & 1u) ^ 1u);
+          long long rows = a.n - row0;
+          if (rows > TC_BM) rows = TC_BM;
+          const u32 bytes = (u32)(rows * row_bytes);
+          tc_mbar_expect_tx(tc_smem(pk_full + slot), bytes);
+          asm volatile(
+              "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+              ::"r"(tc_smem(spk + (size_t)slot * TC_BM * row_bytes)),
+                "l"(a.packed_codes + (size_t)row0 * row_bytes), "r"(bytes), "r"(tc_smem(pk_full + slot)) : "memory");
         }
       }
     }
@@ -179,8 +230,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_after();
       const u32 d_tmem = tmem_base + as * TC_BN;
       for (int kb = 0; kb < a.kb; ++kb, ++it) {
-        const u32 s = it % TC_STAGES;
-        tc_mbar_wait(tc_smem(full_a + s), (it / TC_STAGES) & 1u);
+        const u32 s = it % stages;
+        tc_mbar_wait(tc_smem(full_a + s), (it / stages) & 1u);
         tc_fence_after();
         if (lane == 0) {
           const u32 a_addr = tc_smem(sa + (size_t)s * TC_TILE_BYTES);
@@ -196,7 +247,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (lane == 0) tc_commit(tc_smem(tmem_full + as));  // accumulator complete
       __syncwarp();
     }
-  } else {
+  } else if (warp < 6) {
     // ===================== epilogue (warps 2..5) =====================
     const int lq = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
     u32 tcount = 0;
@@ -223,23 +274,82 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (a.dense) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int qq = q0 + c * 32 + j;
-          const int s = (int)v[j];
-          if (a.dense) {
-            if (qq < a.q) a.dense_keys[(size_t)qq * dense_ld + dense_col] = valid ? ~i32_orderable(s) : 0xFFFFFFFFu;
-          } else if (valid && qq < a.q && s >= thr[c * 32 + j]) {
-            const u32 slot = atomicAdd(a.cnt + qq, 1u);
-            if (slot < (u32)a.cap) {
-              a.list_score[(size_t)qq * a.cap + slot] = s;
-              a.list_row[(size_t)qq * a.cap + slot] = (u32)row;
+          for (int j = 0; j < 32; ++j) {
+            const int qq = q0 + c * 32 + j;
+            if (qq < a.q)
+              a.dense_keys[(size_t)qq * dense_ld + dense_col] = valid ? ~i32_orderable((int)v[j]) : 0xFFFFFFFFu;
+          }
+        } else {
+          // thresholds of this chunk to registers first (vector loads), so the compare chain
+          // is not serialised behind the shared-memory counter updates
+          int t[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const int4 tv = reinterpret_cast<const int4*>(thr + c * 32)[j4];
+            t[4 * j4 + 0] = tv.x;
+            t[4 * j4 + 1] = tv.y;
+            t[4 * j4 + 2] = tv.z;
+            t[4 * j4 + 3] = tv.w;
+          }
+          const int qlim = a.q - (q0 + c * 32);  // columns >= qlim are padding
+          u32 hit = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if ((int)v[j] >= t[j] && j < qlim) hit |= 1u << j;
+          if (!valid) hit = 0;
+          while (hit) {  // rare: about k * 32 rows per query reach the sampled bound
+            const int j = __ffs(hit) - 1;
+            hit &= hit - 1;
+            int s = 0;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              if (jj == j) s = (int)v[jj];
+            const u32 slot = atomicAdd(s_cnt + c * 32 + j, 1u);  // shared-memory counter
+            if (slot < (u32)a.cap_cta) {
+              const size_t o = ((size_t)(q0 + c * 32 + j) * gridDim.x + blockIdx.x) * a.cap_cta + slot;
+              a.list_score[o] = s;
+              a.list_row[o] = (u32)row;
             }
           }
         }
       }
       tc_fence_before();
       tc_mbar_arrive(tc_smem(tmem_empty + as));
+    }
+    if (!a.dense) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      const int t = threadIdx.x - 64;
+      if (q0 + t < a.q) a.cnt[(size_t)(q0 + t) * gridDim.x + blockIdx.x] = s_cnt[t];
+    }
+  } else if (a.packed) {
+    // ===================== unpackers (warps 6..9): packed bits -> +-1 int8, swizzled =====================
+    const int u = threadIdx.x - 192;  // row of the tile handled by this thread
+    u32 it = 0, tcount = 0;
+    for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
+      const u32 slot = tcount & 1u;
+      tc_mbar_wait(tc_smem(pk_full + slot), (tcount >> 1) & 1u);
+      const unsigned char* prow = spk + (size_t)slot * TC_BM * row_bytes + (size_t)u * row_bytes;
+      for (int kb = 0; kb < a.kb; ++kb, ++it) {
+        const u32 s = it % stages;
+        const uint4 pw = *reinterpret_cast<const uint4*>(prow + kb * 16);  // 128 dims of this row
+        tc_mbar_wait(tc_smem(empty_a + s), ((it / stages) & 1u) ^ 1u);
+        unsigned char* dst = sa + (size_t)s * TC_TILE_BYTES + (size_t)u * TC_BK;
+        const u32 words[4] = {pw.x, pw.y, pw.z, pw.w};
+#pragma unroll
+        for (int wq = 0; wq < 4; ++wq) {
+          u32 o[8];
+          tc_expand32(words[wq], o);
+          // 16-byte chunks 2*wq and 2*wq+1 of this row, SWIZZLE_128B: chunk c lives at c ^ (row & 7)
+          const int c0 = (2 * wq) ^ (u & 7), c1 = (2 * wq + 1) ^ (u & 7);
+          *reinterpret_cast<uint4*>(dst + c0 * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(dst + c1 * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async (UMMA) reads
+        tc_mbar_arrive(tc_smem(full_a + s));
+      }
+      tc_mbar_arrive(tc_smem(pk_empty + slot));
     }
   }
 
@@ -257,27 +367,38 @@ __global__ void tc_tau_kernel(const int* sample_scores, const int* sample_count,
   if (i < q) tau[i] = (sample_count[i] >= k) ? sample_scores[(size_t)i * k + (k - 1)] : (int)0x80000000;
 }
 
-// exact top-k of each query's filtered list, (score desc, row asc)
+// exact top-k of each query's filtered list segments, (score desc, row asc)
 template <int MODE>  // MERGE_I32_DESC: scores as is; MERGE_HAMMING: dist = (dim - score) / 2
 __global__ void __launch_bounds__(MERGE_THREADS)
-    tc_select_lists_kernel(const u32* cnt, const int* list_score, const u32* list_row, int cap, int k, int kcap,
-                           int dim, long long row_base, void* out_a, long long* out_idx, int* out_count,
-                           unsigned* overflow) {
+    tc_select_lists_kernel(const u32* cnt, const int* list_score, const u32* list_row, int n_cta, int cap_cta,
+                           int k, int kcap, int dim, long long row_base, void* out_a, long long* out_idx,
+                           int* out_count, unsigned* overflow) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
   u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
   u32* s_k2 = reinterpret_cast<u32*>(s_k1 + kcap);
   __shared__ SelectScratch<MERGE_THREADS> sc;
+  __shared__ u32 s_seg[256];  // n_cta <= 148
   const int q = blockIdx.x;
-  const u32 c = cnt[q];
-  if (c > (u32)cap && threadIdx.x == 0) atomicAdd(overflow, 1u);
-  const long long n = c < (u32)cap ? c : cap;
-  const int* ls = list_score + (size_t)q * cap;
-  const u32* lr = list_row + (size_t)q * cap;
+  for (int i = threadIdx.x; i < n_cta; i += MERGE_THREADS) {
+    const u32 c = cnt[(size_t)q * n_cta + i];
+    if (c > (u32)cap_cta) atomicAdd(overflow, 1u);
+    s_seg[i] = c < (u32)cap_cta ? c : (u32)cap_cta;
+  }
+  __syncthreads();
+  const int* ls = list_score + (size_t)q * n_cta * cap_cta;
+  const u32* lr = list_row + (size_t)q * n_cta * cap_cta;
   auto get = [&](long long i, u64& x, u32& y) {
-    x = (u64)(~i32_orderable(ls[i]));
-    y = lr[i];
+    const int seg = (int)(i / cap_cta);
+    const int j = (int)(i - (long long)seg * cap_cta);
+    if ((u32)j < s_seg[seg]) {
+      x = (u64)(~i32_orderable(ls[i]));
+      y = lr[i];
+    } else {
+      x = K1_INVALID;
+      y = K2_INVALID;
+    }
   };
-  const int m = block_select_sorted<MERGE_THREADS>(get, n, k, s_k1, s_k2, kcap, sc);
+  const int m = block_select_sorted<MERGE_THREADS>(get, (long long)n_cta * cap_cta, k, s_k1, s_k2, kcap, sc);
   for (int j = threadIdx.x; j < k; j += MERGE_THREADS) {
     const size_t o = (size_t)q * k + j;
     if (j < m) {
@@ -354,8 +475,8 @@ constexpr int TC_SAMPLE_STRIDE = 32;  // pass 0 scores every 32nd row tile
 
 struct TcPlan {
   long long tiles, sample_tiles;
-  int cap;
-  size_t off_keys, off_sscore, off_sidx, off_scount, off_tau, off_cnt, off_ls, off_lr, off_ovf, total;
+  int qblocks, ctas_x, cap_cta;
+  size_t off_keys, off_sscore, off_sidx, off_scount, off_tau, off_cnt, off_ls, off_lr, total;
 };
 
 static TcPlan tc_plan(long long n, int q, int k) {
@@ -364,10 +485,18 @@ static TcPlan tc_plan(long long n, int q, int k) {
   p.sample_tiles = (p.tiles + TC_SAMPLE_STRIDE - 1) / TC_SAMPLE_STRIDE;
   // the sample must be able to hold k rows; tiny corpora are sampled completely
   if (p.sample_tiles * TC_BM < 4LL * k || p.sample_tiles * TC_BM < 2048) p.sample_tiles = p.tiles;
-  long long expect = (long long)k * (p.tiles / p.sample_tiles + 1);
-  long long cap = 4 * expect + 1024;
-  if (cap > n + 128) cap = n + 128;
-  p.cap = (int)cap;
+  p.qblocks = (q + TC_BN - 1) / TC_BN;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  p.ctas_x = sms / p.qblocks;
+  if (p.ctas_x < 1) p.ctas_x = 1;
+  if (p.ctas_x > p.tiles) p.ctas_x = (int)p.tiles;
+  // expected rows that reach the sampled bound: k * (tiles / sample_tiles); CTAs take tiles
+  // round-robin, so each sees an even share; 3x headroom + slack, overflow is detected
+  const long long expect = (long long)k * (p.tiles / p.sample_tiles + 1);
+  long long cap = 3 * (expect / p.ctas_x + 1) + 64;
+  const long long rows_per_cta = ((p.tiles + p.ctas_x - 1) / p.ctas_x) * TC_BM;
+  if (cap > rows_per_cta) cap = rows_per_cta;
+  p.cap_cta = (int)cap;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
   p.off_keys = take((size_t)q * p.sample_tiles * TC_BM * 4);
@@ -375,16 +504,30 @@ static TcPlan tc_plan(long long n, int q, int k) {
   p.off_sidx = take((size_t)q * k * 8);
   p.off_scount = take((size_t)q * 4);
   p.off_tau = take((size_t)q * 4);
-  p.off_cnt = take((size_t)q * 4);
-  p.off_ls = take((size_t)q * p.cap * 4);
-  p.off_lr = take((size_t)q * p.cap * 4);
-  p.off_ovf = take(256);
+  p.off_cnt = take((size_t)q * p.ctas_x * 4);
+  p.off_ls = take((size_t)q * p.ctas_x * p.cap_cta * 4);
+  p.off_lr = take((size_t)q * p.ctas_x * p.cap_cta * 4);
   p.total = o + 256;
   return p;
 }
 
-static size_t tc_smem_bytes(int kb) {
-  return 1024 + (size_t)kb * TC_TILE_BYTES + (size_t)TC_STAGES * TC_TILE_BYTES + TC_BN * 4 + 16 * 8 + 64;
+struct TcSmem {
+  int stages;
+  size_t bytes;
+};
+
+// B resident + A ring (+ packed double buffer) + thresholds / counters / barriers, inside 227 KB
+static TcSmem tc_smem_layout(int kb, bool packed) {
+  const size_t limit = 232448;  // 227 KB opt-in maximum per block
+  const size_t fixed = 1024 /*alignment slack*/ + (size_t)kb * TC_TILE_BYTES +
+                       (packed ? 2 * (size_t)TC_BM * kb * 16 : 0) + 2 * TC_BN * 4 + 32 * 8 + 64;
+  int stages = (int)((limit - fixed) / TC_TILE_BYTES);
+  const int max_stages = packed ? 4 : TC_MAX_STAGES;  // packed mode only decouples unpack from MMA
+  if (stages > max_stages) stages = max_stages;
+  TcSmem r;
+  r.stages = stages;
+  r.bytes = fixed + (size_t)stages * TC_TILE_BYTES;
+  return r;
 }
 
 // select_keys32_kernel lives in exact.cu; the tensor-core path needs the same selection on
@@ -413,8 +556,9 @@ __global__ void __launch_bounds__(MERGE_THREADS)
 }
 
 // mode: 0 = int8 scores (score desc), 1 = Hamming over +-1 rows (dist asc)
-static int tc_search(const int8_t* emb, long long n, int dim, const uint8_t* tags, unsigned tag_mask,
-                     unsigned tag_value, const int8_t* queries, int q, int k, long long row_base, int hamming,
+static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n, int dim, const uint8_t* tags,
+                     unsigned tag_mask, unsigned tag_value, const int8_t* queries, int q, int k, long long row_base,
+                     int hamming,
                      int* out_a, long long* out_idx, unsigned* overflow_out, void* ws, size_t ws_bytes,
                      cudaStream_t st) {
   const TcPlan p = tc_plan(n, q, k);
@@ -423,18 +567,23 @@ static int tc_search(const int8_t* emb, long long n, int dim, const uint8_t* tag
     return RR_ERR_WORKSPACE;
   }
   char* w = (char*)ws;
+  const bool packed = packed_codes != nullptr;
   CUtensorMap map_a, map_b;
-  int rc = make_map(&map_a, emb, n, dim);
+  int rc = make_map(&map_b, queries, q, dim);
   if (rc != RR_OK) return rc;
-  rc = make_map(&map_b, queries, q, dim);
-  if (rc != RR_OK) return rc;
+  if (packed) {
+    map_a = map_b;  // unused in packed mode
+  } else {
+    rc = make_map(&map_a, emb, n, dim);
+    if (rc != RR_OK) return rc;
+  }
   const int kb = dim / TC_BK;
-  const size_t smem = tc_smem_bytes(kb);
+  const TcSmem lay = tc_smem_layout(kb, packed);
+  RR_CHECK_ARG(lay.stages >= 2, "not enough shared memory for the operand ring");
+  const size_t smem = lay.bytes;
   RR_CUDA(cudaFuncSetAttribute(tc_i8_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int qblocks = (q + TC_BN - 1) / TC_BN;
-  const int sms = sm_count() > 0 ? sm_count() : 148;
-  int ctas_x = sms / qblocks;
-  if (ctas_x < 1) ctas_x = 1;
+  const int qblocks = p.qblocks;
+  const int ctas_x = p.ctas_x;
 
   TcArgs a;
   a.n = n;
@@ -446,8 +595,11 @@ static int tc_search(const int8_t* emb, long long n, int dim, const uint8_t* tag
   a.cnt = (u32*)(w + p.off_cnt);
   a.list_score = (int*)(w + p.off_ls);
   a.list_row = (u32*)(w + p.off_lr);
-  a.cap = p.cap;
+  a.cap_cta = p.cap_cta;
   a.dense_keys = (u32*)(w + p.off_keys);
+  a.stages = lay.stages;
+  a.packed = packed ? 1 : 0;
+  a.packed_codes = packed_codes;
 
   // ---- pass 0: dense scores of a strided sample of row tiles -> tau
   const bool full_sample = p.sample_tiles == p.tiles;
@@ -469,24 +621,25 @@ static int tc_search(const int8_t* emb, long long n, int dim, const uint8_t* tag
                                                  k, (int*)(w + p.off_tau));
   RR_LAUNCH_CHECK();
 
-  // ---- pass 1: filter pass over all rows
-  RR_CUDA(cudaMemsetAsync(w + p.off_cnt, 0, (size_t)q * 4, st));
+  // ---- pass 1: filter pass over all rows (every CTA of the grid writes its cnt entries)
   a.tile_stride = 1;
   a.n_tiles = p.tiles;
   a.tau = (const int*)(w + p.off_tau);
   a.dense = 0;
   {
-    dim3 grid((unsigned)(a.n_tiles < ctas_x ? a.n_tiles : ctas_x), qblocks);
+    dim3 grid((unsigned)ctas_x, qblocks);
     tc_i8_search_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
     RR_LAUNCH_CHECK();
   }
-  // ---- pass 2: exact top-k of each list
+  // ---- pass 2: exact top-k of each query's list segments
   if (hamming)
     tc_select_lists_kernel<MERGE_HAMMING><<<q, MERGE_THREADS, (size_t)kcap * 12, st>>>(
-        a.cnt, a.list_score, a.list_row, p.cap, k, kcap, dim, row_base, out_a, out_idx, nullptr, overflow_out);
+        a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, row_base, out_a, out_idx, nullptr,
+        overflow_out);
   else
     tc_select_lists_kernel<MERGE_I32_DESC><<<q, MERGE_THREADS, (size_t)kcap * 12, st>>>(
-        a.cnt, a.list_score, a.list_row, p.cap, k, kcap, dim, row_base, out_a, out_idx, nullptr, overflow_out);
+        a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, row_base, out_a, out_idx, nullptr,
+        overflow_out);
   RR_LAUNCH_CHECK();
   return RR_OK;
 }
@@ -522,15 +675,17 @@ static int tc_check(int64_t n, int32_t dim, int32_t q, int32_t k) {
   return RR_OK;
 }
 
-extern "C" int rr_hamming_topk_tc(const int8_t* pm1, int64_t n, int32_t dim, const uint8_t* tags,
+extern "C" int rr_hamming_topk_tc(const uint32_t* codes, int64_t n, int32_t words, const uint8_t* tags,
                                   uint8_t tag_mask, uint8_t tag_value, const int8_t* q_pm1, int32_t q,
                                   int32_t k, int64_t row_base, int32_t* out_dist, int64_t* out_idx,
                                   uint32_t* overflow, void* workspace, size_t workspace_bytes, void* stream) {
+  RR_CHECK_ARG(words >= 4 && words <= RR_MAX_WORDS && words % 4 == 0, "words must be a multiple of 4 in [4, 32]");
+  const int dim = words * 32;  // padded width; padding bits are 0 in rows and queries alike
   int rc = tc_check(n, dim, q, k);
   if (rc != RR_OK) return rc;
-  RR_CHECK_ARG(pm1 && q_pm1 && out_dist && out_idx && overflow, "null pointer");
-  return tc_search(pm1, n, dim, tags, tag_mask, tag_value, q_pm1, q, k, row_base, 1, out_dist,
-                   (long long*)out_idx, overflow, workspace, workspace_bytes, (cudaStream_t)stream);
+  RR_CHECK_ARG(codes && q_pm1 && out_dist && out_idx && overflow, "null pointer");
+  return tc_search(nullptr, (const uint8_t*)codes, n, dim, tags, tag_mask, tag_value, q_pm1, q, k, row_base, 1,
+                   out_dist, (long long*)out_idx, overflow, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int rr_int8_search_topk_tc(const int8_t* emb, int64_t n, int32_t dim, const uint8_t* tags,
@@ -541,7 +696,7 @@ extern "C" int rr_int8_search_topk_tc(const int8_t* emb, int64_t n, int32_t dim,
   int rc = tc_check(n, dim, q, top_k);
   if (rc != RR_OK) return rc;
   RR_CHECK_ARG(emb && queries_i8 && out_score && out_idx && overflow, "null pointer");
-  return tc_search(emb, n, dim, tags, tag_mask, tag_value, queries_i8, q, top_k, row_base, 0, out_score,
+  return tc_search(emb, nullptr, n, dim, tags, tag_mask, tag_value, queries_i8, q, top_k, row_base, 0, out_score,
                    (long long*)out_idx, overflow, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -560,7 +715,8 @@ extern "C" int rr_tc_dense_keys(const int8_t* emb, int64_t n, int32_t dim, const
   rc = make_map(&map_b, queries_i8, q, dim);
   if (rc != RR_OK) return rc;
   const int kb = dim / TC_BK;
-  const size_t smem = tc_smem_bytes(kb);
+  const TcSmem lay = tc_smem_layout(kb, false);
+  const size_t smem = lay.bytes;
   RR_CUDA(cudaFuncSetAttribute(tc_i8_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int qblocks = (q + TC_BN - 1) / TC_BN;
   const int sms = sm_count() > 0 ? sm_count() : 148;
@@ -580,7 +736,10 @@ extern "C" int rr_tc_dense_keys(const int8_t* emb, int64_t n, int32_t dim, const
   a.cnt = nullptr;
   a.list_score = nullptr;
   a.list_row = nullptr;
-  a.cap = 0;
+  a.cap_cta = 0;
+  a.stages = lay.stages;
+  a.packed = 0;
+  a.packed_codes = nullptr;
   dim3 grid((unsigned)(a.n_tiles < ctas_x ? a.n_tiles : ctas_x), qblocks);
   tc_i8_search_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
   RR_LAUNCH_CHECK();

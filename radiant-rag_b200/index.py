@@ -105,9 +105,8 @@ class DenseIndex:
         capacity: int = 0,
         store_pm1: bool = False,
     ) -> None:
-        """store_pm1: also keep the codes expanded to +-1 int8 rows [cap, dim] (8x the code
-        bytes) so BATCHED stage-1 searches run on the tensor cores (rr_hamming_topk_tc);
-        needs dim to be a multiple of 128, ignored otherwise."""
+        """store_pm1: deprecated no-op (the tensor-core scan now expands the packed codes in
+        shared memory and needs no extra copy in HBM)."""
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         if self.device.type != "cuda":
             raise _lib.RadiantB200Error("DenseIndex needs a CUDA device; there is no CPU fallback")
@@ -126,9 +125,8 @@ class DenseIndex:
         self.f32: Optional[torch.Tensor] = None
         self.tags: Optional[torch.Tensor] = None
         self.tags_uniform = True  # every row has the default tag: the scan can skip the tag read
-        self.store_pm1 = bool(store_pm1) and self.dim % 128 == 0 and 128 <= self.dim <= 1024
-        self.pm1: Optional[torch.Tensor] = None
-        self.tc_min_queries = 16  # below this the POPC scan (memory-bound) is the faster path
+        self.use_tensor_cores = True   # batched stage 1 on tcgen05 (rr_hamming_topk_tc)
+        self.tc_min_queries = 16       # below this the POPC scan (memory-bound) is the faster path
         self._tc_overflow: Optional[torch.Tensor] = None
         self.ranges: Optional[torch.Tensor] = None
         if int8_ranges is not None:
@@ -160,8 +158,6 @@ class DenseIndex:
             self.int8 = grow(self.int8, (cap, self.dim), torch.int8)
         if self.store_f32:
             self.f32 = grow(self.f32, (cap, self.dim), torch.float32)
-        if self.store_pm1:
-            self.pm1 = grow(self.pm1, (cap, self.dim), torch.int8)
         self._cap = cap
 
     def set_int8_ranges(self, ranges: ArrayLike) -> None:
@@ -186,9 +182,6 @@ class DenseIndex:
         self._reserve(hi)
         _lib.call("rr_quantize_ubinary", e.data_ptr(), m, self.dim, self.codes[lo:hi].data_ptr(),
                   self.words * 4, _stream())
-        if self.store_pm1:
-            _lib.call("rr_unpack_codes_pm1", self.codes[lo:hi].data_ptr(), m, self.words * 4, self.dim,
-                      self.pm1[lo:hi].data_ptr(), _stream())
         if self.store_int8:
             if self.ranges is None:
                 raise ValueError("int8 storage needs calibration ranges (set_int8_ranges)")
@@ -210,9 +203,6 @@ class DenseIndex:
         e = to_device(emb, self.device, torch.float32).reshape(1, self.dim)
         _lib.call("rr_quantize_ubinary", e.data_ptr(), 1, self.dim, self.codes[row:row + 1].data_ptr(),
                   self.words * 4, _stream())
-        if self.store_pm1:
-            _lib.call("rr_unpack_codes_pm1", self.codes[row:row + 1].data_ptr(), 1, self.words * 4, self.dim,
-                      self.pm1[row:row + 1].data_ptr(), _stream())
         if self.store_int8:
             _lib.call("rr_quantize_int8", e.data_ptr(), 1, self.dim, self.ranges.data_ptr(),
                       self.int8[row:row + 1].data_ptr(), _stream())
@@ -270,8 +260,9 @@ class DenseIndex:
                          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """Tensor-core path; also returns the device overflow counter of this call."""
         q = qcodes.shape[0]
-        q_pm1 = torch.empty((q, self.dim), dtype=torch.int8, device=self.device)
-        _lib.call("rr_unpack_codes_pm1", qcodes.data_ptr(), q, self.words * 4, self.dim, q_pm1.data_ptr(),
+        dpad = self.words * 32  # padded width: padding bits are 0 (-1) in rows and queries alike
+        q_pm1 = torch.empty((q, dpad), dtype=torch.int8, device=self.device)
+        _lib.call("rr_unpack_codes_pm1", qcodes.data_ptr(), q, self.words * 4, dpad, q_pm1.data_ptr(),
                   _stream())
         dist = torch.empty((q, k), dtype=torch.int32, device=self.device)
         idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
@@ -280,9 +271,9 @@ class DenseIndex:
         ws_bytes = lib.rr_tc_search_workspace_bytes(self.n, q, k)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         tptr, tm, tv = self._tag_args(tag_mask, tag_value)
-        _lib.call("rr_hamming_topk_tc", self.pm1.data_ptr(), self.n, self.dim, tptr, tm, tv, q_pm1.data_ptr(),
-                  q, k, self.row_base, dist.data_ptr(), idx.data_ptr(), ovf.data_ptr(), ws.data_ptr(),
-                  ws_bytes, _stream())
+        _lib.call("rr_hamming_topk_tc", self.codes.data_ptr(), self.n, self.words, tptr, tm, tv,
+                  q_pm1.data_ptr(), q, k, self.row_base, dist.data_ptr(), idx.data_ptr(), ovf.data_ptr(),
+                  ws.data_ptr(), ws_bytes, _stream())
         return dist, idx, ovf
 
     def hamming_topk(self, qcodes: torch.Tensor, k: int, tag_mask: int = 0, tag_value: int = 0,
@@ -290,8 +281,8 @@ class DenseIndex:
                      ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Exact top-k by (dist asc, row asc).  -> (dist int32 [q,k], idx int64 [q,k]).
 
-        Batches of >= tc_min_queries run on the tensor cores when the index keeps +-1 rows
-        (store_pm1); both paths return identical results.  The tensor-core path keeps, per
+        Batches of >= tc_min_queries run on the tensor cores (packed codes expanded to +-1
+        int8 operand tiles in shared memory); both paths return identical results.  The tensor-core path keeps, per
         query, the rows that beat a sampled bound in a bounded list: if a list overflows
         (adversarial data) the call is redone on the POPC path.  check_overflow=False skips
         that host-side check (one device sync) and accumulates the counter in
@@ -299,8 +290,8 @@ class DenseIndex:
         self._activate()
         q = qcodes.shape[0]
         if use_tc is None:
-            use_tc = self.pm1 is not None and q >= self.tc_min_queries and self.n >= 4096
-        if not use_tc or self.pm1 is None or self.n == 0:
+            use_tc = self.use_tensor_cores and q >= self.tc_min_queries and self.n >= 4096
+        if not use_tc or self.n == 0:
             return self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
         dist, idx, ovf = self._hamming_topk_tc(qcodes, k, tag_mask, tag_value)
         if check_overflow:

@@ -46,8 +46,8 @@ class GpuShardOps:
     def quantize_queries(self, queries):
         return self.index.quantize_queries(queries)
 
-    def hamming_topk(self, qcodes, k, tag_mask=0, tag_value=0):
-        return self.index.hamming_topk(qcodes, k, tag_mask, tag_value)
+    def hamming_topk(self, qcodes, k, tag_mask=0, tag_value=0, check_overflow=True):
+        return self.index.hamming_topk(qcodes, k, tag_mask, tag_value, check_overflow=check_overflow)
 
     def merge_hamming(self, dist_all: torch.Tensor, idx_all: torch.Tensor, k: int):
         q, n_in = idx_all.shape
@@ -110,7 +110,8 @@ class ShardedDenseSearch:
 
     def search_quantized(self, queries, top_k: int, rescore_multiplier: float = 4.0,
                          use_rescoring: bool = True, min_similarity: float = 0.0,
-                         tag_mask: int = 0, tag_value: int = 0, prefer_int8: bool = True
+                         tag_mask: int = 0, tag_value: int = 0, prefer_int8: bool = True,
+                         check_overflow: bool = True
                          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """queries f32 [Q, D], identical on every rank.  -> (idx [Q,top_k] global rows,
         score f32 [Q,top_k], count int32 [Q]), identical on every rank."""
@@ -118,7 +119,7 @@ class ShardedDenseSearch:
         qf, qc = ops.quantize_queries(queries)
         candidate_k = int(top_k * rescore_multiplier) if use_rescoring else top_k
         candidate_k = max(1, min(candidate_k, _lib.RR_MAX_K))
-        d_loc, i_loc = ops.hamming_topk(qc, candidate_k, tag_mask, tag_value)
+        d_loc, i_loc = ops.hamming_topk(qc, candidate_k, tag_mask, tag_value, check_overflow=check_overflow)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world > 1:
             d_all = _gather_lists(d_loc, self.group)

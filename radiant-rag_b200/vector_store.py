@@ -184,8 +184,6 @@ class B200VectorStore(BaseVectorStore):
                         idx.int8[row].copy_(idx.int8[last])
                     if idx.f32 is not None:
                         idx.f32[row].copy_(idx.f32[last])
-                    if idx.pm1 is not None:
-                        idx.pm1[row].copy_(idx.pm1[last])
                     moved = self._id_of[last]
                     self._id_of[row] = moved
                     self._row_of[moved] = row

@@ -19,7 +19,7 @@ class CpuShardOps:
         q = np.asarray(queries, dtype=np.float32)
         return torch.from_numpy(q), torch.from_numpy(oracle.quantize_ubinary(q))
 
-    def hamming_topk(self, qcodes, k, tag_mask=0, tag_value=0):
+    def hamming_topk(self, qcodes, k, tag_mask=0, tag_value=0, check_overflow=True):
         d, i = oracle.hamming_topk(self.codes, qcodes.numpy(), k)
         i = np.where(i >= 0, i + self.row_base, -1)
         return torch.from_numpy(d), torch.from_numpy(i)

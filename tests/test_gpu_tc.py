@@ -41,17 +41,17 @@ def test_tc_gemm_scores_exact(n, dim, q):
 def test_unpack_pm1():
     require_gpu()
     x = synthetic.hash_rows_f32(0, 300, 384, seed=2)
-    idx = DenseIndex(384, device=0, store_int8=False, store_f32=False, store_pm1=True)
-    idx.add(x)
-    want = np.where(x > 0, 1, -1).astype(np.int8)
-    assert np.array_equal(idx.pm1[:300].cpu().numpy(), want)
+    idx = DenseIndex(384, device=0, store_int8=False, store_f32=False)
+    _qf, qc = idx.quantize_queries(x)
+    out = torch.empty((300, 384), dtype=torch.int8, device="cuda")
+    _lib.call("rr_unpack_codes_pm1", qc.data_ptr(), 300, idx.words * 4, 384, out.data_ptr(), _stream())
+    assert np.array_equal(out.cpu().numpy(), np.where(x > 0, 1, -1).astype(np.int8))
 
 
 def _both_paths(corpus, queries, k, tags=None, mask=0, value=0, row_base=0):
     dim = corpus.shape[1]
-    idx = DenseIndex(dim, device=0, store_int8=False, store_f32=False, store_pm1=True, row_base=row_base)
+    idx = DenseIndex(dim, device=0, store_int8=False, store_f32=False, row_base=row_base)
     idx.add(corpus, tags)
-    assert idx.pm1 is not None
     _qf, qc = idx.quantize_queries(queries)
     d_tc, i_tc = idx.hamming_topk(qc, k, mask, value, use_tc=True, check_overflow=False)
     d_pc, i_pc = idx.hamming_topk(qc, k, mask, value, use_tc=False)
@@ -66,6 +66,8 @@ def _both_paths(corpus, queries, k, tags=None, mask=0, value=0, row_base=0):
     (5_000, 128, 17, 10),
     (4_500, 256, 300, 1000),     # k at the limit, 3 query blocks
     (200, 128, 16, 50),          # smaller than one sample
+    (30_000, 100, 40, 17),       # dim not a multiple of 32 (padded to 128 bits)
+    (9_000, 640, 33, 64),        # words = 20 -> 5 K blocks
 ])
 def test_tc_hamming_equals_popc_and_oracle(n, dim, q, k):
     require_gpu()
@@ -103,7 +105,7 @@ def test_tc_overflow_falls_back_to_exact_path():
     n, dim = 200_000, 128
     corpus = np.tile(np.linspace(-1, 1, dim, dtype=np.float32), (n, 1))
     queries = np.tile(np.linspace(-1, 1, dim, dtype=np.float32), (20, 1))
-    idx = DenseIndex(dim, device=0, store_int8=False, store_f32=False, store_pm1=True)
+    idx = DenseIndex(dim, device=0, store_int8=False, store_f32=False)
     idx.add(corpus)
     _qf, qc = idx.quantize_queries(queries)
     idx.hamming_topk(qc, 10, use_tc=True, check_overflow=False)
@@ -136,7 +138,7 @@ def test_tc_config2_full_size():
     """1M x 768, 256 queries, k'=200 on device-generated data: tensor-core == POPC path."""
     require_gpu()
     n, dim, q, k = 1_000_000, 768, 256, 200
-    idx = DenseIndex(dim, device=0, store_int8=False, store_f32=False, store_pm1=True, capacity=n)
+    idx = DenseIndex(dim, device=0, store_int8=False, store_f32=False, capacity=n)
     for lo in range(0, n, 250_000):
         idx.add(synth_rows_device(lo, 250_000, dim, seed=1))
     queries = synth_query_rows_device(0, q, dim, seed=1, n_corpus=n)

@@ -16,7 +16,7 @@ sys.path.insert(0, str(ROOT))
 from radiant_rag_b200.index import DenseIndex, synth_query_rows_device, synth_rows_device  # noqa: E402
 
 
-def build(n, dim, seed=4):
+def build(n, dim, seed=4, pm1=True):
     idx = DenseIndex(dim, device=0, store_int8=False, store_f32=False, capacity=n)
     step = 500_000
     for lo in range(0, n, step):
@@ -49,7 +49,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     shapes = [  # (rows, dim, [(q, k), ...])
         (1_000_000, 768, [(1, 200), (2, 200), (4, 200), (16, 200), (64, 200), (256, 200)]),
-        (12_500_000, 1024, [(1, 40), (2, 40), (4, 40), (8, 40), (64, 40), (256, 40)]),
+        (12_500_000, 1024, [(1, 40), (2, 40), (4, 40), (8, 40), (64, 40), (256, 40), (1024, 40)]),
     ]
     if len(sys.argv) > 1 and sys.argv[1] == "small":
         shapes = shapes[:1]
@@ -60,10 +60,19 @@ def main():
         for q, k in cases:
             queries = synth_query_rows_device(0, q, dim, 4, n)
             _qf, qc = idx.quantize_queries(queries)
-            mean_ms, best_ms = time_call(lambda: idx.hamming_topk(qc, k), flush)
+            mean_ms, best_ms = time_call(lambda: idx.hamming_topk(qc, k, use_tc=False), flush)
             code_bytes = n * idx.words * 4
+            tc = None
+            if q >= 16:
+                tc_ms, tc_best = time_call(lambda: idx.hamming_topk(qc, k, use_tc=True, check_overflow=False), flush)
+                macs = q * n * dim
+                tc = {"ms_mean": round(tc_ms, 4), "ms_best": round(tc_best, 4),
+                      "int8_TOPS": round(2 * macs / (tc_ms * 1e-3) / 1e12, 1),
+                      
+                      "queries_per_s": round(q / (tc_ms * 1e-3), 1), "overflow": idx.tc_overflow_total()}
             out = {
                 "rows": n, "dim": dim, "q": q, "k": k, "ms_mean": round(mean_ms, 4), "ms_best": round(best_ms, 4),
+                "tensor_core": tc,
                 "code_GB": round(code_bytes / 1e9, 3),
                 "hbm_GBs": round(code_bytes / (mean_ms * 1e-3) / 1e9, 1),
                 "hbm_frac_of_measured": round(code_bytes / (mean_ms * 1e-3) / 1e9 / hbm, 4),
