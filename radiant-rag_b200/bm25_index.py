@@ -105,7 +105,9 @@ class Bm25DeviceIndex:
     ) -> "Bm25DeviceIndex":
         """doc_ptr int64 [N+1] / doc_terms int32 [T]: the documents of THIS shard as CSR of
         term ids; idf f64 [n_terms] (0 for unknown terms), avgdl, k1, b: global tables
-        copied from the host index.  doc_len int32 [N] overrides diff(doc_ptr) (the
+        copied from the host index (idf=None: document frequencies are counted on device and
+        idf is evaluated ON THE HOST with the reference's scalar expression,
+        np.log((n - df + 0.5) / (df + 0.5) + 1.0), bm25_index.py:131-135).  doc_len int32 [N] overrides diff(doc_ptr) (the
         reference keeps ``doc_lengths`` separately).  Sorting / counting uses torch on the
         device (index build is not the hot path); impacts come from rr_bm25_impacts."""
         dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
@@ -139,6 +141,12 @@ class Bm25DeviceIndex:
                   + torch.arange(v + 1, dtype=torch.int64, device=dev)[None, :])
         tile_term_ptr = csum[gather].contiguous()
         del gather, csum
+        if idf is None:
+            df = torch.bincount(term, minlength=v).cpu().numpy()
+            idf = np.zeros(v, dtype=np.float64)
+            for t in np.nonzero(df)[0]:
+                d = int(df[t])
+                idf[t] = np.log((n - d + 0.5) / (d + 0.5) + 1.0)
         idf_t = to_device(idf, dev, torch.float64)
         post_idf = idf_t[term].contiguous()
         post_len = dlen[post_row64].contiguous()

@@ -40,7 +40,8 @@ constexpr int TC_BM = 128;          // corpus rows per MMA tile (TMEM lanes)
 constexpr int TC_BN = 128;          // queries per CTA (TMEM columns per accumulator)
 constexpr int TC_BK = 128;          // bytes of K per stage = one 128B swizzle atom row
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_THREADS = 320;  // producer, MMA, 4 epilogue warps, 4 unpack warps
+constexpr int TC_UNPACK_GROUPS = 1;  // groups of 4 unpack warps; group g expands K blocks with it % 3 == g
+constexpr int TC_THREADS = 192 + 128 * TC_UNPACK_GROUPS;  // producer, MMA, 4 epilogue warps, unpack warps
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK;  // 16 KB
 constexpr int TC_MAX_KB = 8;                  // dim <= 1024
 
@@ -82,6 +83,41 @@ __device__ __forceinline__ void tc_mma_i8(u32 d_tmem, u64 adesc, u64 bdesc, u32 
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// Warp-uniform issue helpers: every lane executes the asm with identical (uniform) operands
+// and elect.sync picks the single issuing lane, so the compiler keeps descriptors and
+// addresses in uniform registers instead of broadcasting them out of a divergent branch
+// (the MMA warp's own instruction latency is what paces short MMAs).
+__device__ __forceinline__ void tc_mma_i8_ss_elect(u32 d_tmem, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, pa;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_ts_elect(u32 d_tmem, u32 a_tmem, u64 bdesc, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, pa;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(u32 bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar) : "memory");
+}
+// A operand from tensor memory (lane = row, four int8 K-elements per 32-bit column)
+__device__ __forceinline__ void tc_mma_i8_ts(u32 d_tmem, u32 a_tmem, u64 bdesc, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start address >> 4 | LBO = 1 (unused for swizzled K-major) | SBO = 1024 B (8-row group) |
 // version 1 (Blackwell) | layout type 2 (SWIZZLE_128B).
@@ -114,13 +150,13 @@ struct TcArgs {
 
 // Expand 32 packed sign bits (np.packbits order: dim 8b is the MSB of byte b, bytes in
 // little-endian word order) to 32 int8 values +1 / -1, as eight 32-bit words.
-__device__ __forceinline__ void tc_expand32(u32 w, u32 (&out)[8]) {
+__device__ __forceinline__ void tc_expand32(u32 w, u32* out) {
   const u32 x = __byte_perm(__brev(w), 0, 0x0123);  // bit d = dim d
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
-    const u32 nib = (x >> (4 * g)) & 0xFu;
-    const u32 t = (nib * 0x00204081u) & 0x01010101u;  // bit i of nib -> byte i
-    out[g] = ~(t * 0xFEu);                            // 1 -> 0x01 (+1), 0 -> 0xFF (-1)
+    const u32 nib = (g == 7) ? (x >> 28) : ((x >> (4 * g)) & 0xFu);
+    const u32 t = (nib * 0x00204081u) & 0x01010101u;  // bit i of nib -> byte i (0 / 1)
+    out[g] = t * 0xFFFFFF02u + 0xFFFFFFFFu;           // per byte 0xFF - 0xFE * t: 1 -> +1, 0 -> -1
   }
 }
 
@@ -135,7 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   unsigned char* sb = base;                                   // [kb][16 KB]
   unsigned char* sa = sb + (size_t)a.kb * TC_TILE_BYTES;      // [stages][16 KB]
   const int row_bytes = a.kb * 16;                            // packed bytes per row
-  unsigned char* spk = sa + (size_t)a.stages * TC_TILE_BYTES; // [2][128 * row_bytes] (packed mode)
+  unsigned char* spk = sa + (a.packed ? 0 : (size_t)a.stages * TC_TILE_BYTES);  // [2][128 * row_bytes] (packed mode)
   int* thr = reinterpret_cast<int*>(spk + (a.packed ? 2 * (size_t)TC_BM * row_bytes : 0));  // [128]
   u32* s_cnt = reinterpret_cast<u32*>(thr + TC_BN);                           // [128]
   u64* bars = reinterpret_cast<u64*>(s_cnt + TC_BN);
@@ -164,12 +200,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_mbar_init(tc_smem(tmem_full + s), 1);
       tc_mbar_init(tc_smem(tmem_empty + s), 128);
       tc_mbar_init(tc_smem(pk_full + s), 1);
-      tc_mbar_init(tc_smem(pk_empty + s), 128);
+      tc_mbar_init(tc_smem(pk_empty + s), 128 * TC_UNPACK_GROUPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: 2 accumulators x 128 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(tmem_ptr)), "r"(256u) : "memory");
+  const u32 tmem_cols = a.packed ? 512u : 256u;  // 2 accumulators x 128 columns (+ A ring of 8 x 32 columns)
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(tmem_ptr)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= 2 && warp < 6) {
@@ -191,12 +228,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_tma_load_2d(tc_smem(sb + (size_t)kb * TC_TILE_BYTES), &map_b, kb * TC_BK, q0, tc_smem(b_full));
       if (!a.packed) {
         // int8 rows straight from HBM: one 128-row x 128-byte TMA box per K block
-        u32 it = 0;
+        u32 s = 0, ph = 0;
         for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x) {
           const long long row0 = i * a.tile_stride * TC_BM;
-          for (int kb = 0; kb < a.kb; ++kb, ++it) {
-            const u32 s = it % stages;
-            tc_mbar_wait(tc_smem(empty_a + s), ((it / stages) & 1u) ^ 1u);
+          for (int kb = 0; kb < a.kb; ++kb, s = (s + 1 == stages) ? 0 : s + 1, ph ^= (s == 0)) {
+            tc_mbar_wait(tc_smem(empty_a + s), ph ^ 1u);
             tc_mbar_expect_tx(tc_smem(full_a + s), TC_TILE_BYTES);
             tc_tma_load_2d(tc_smem(sa + (size_t)s * TC_TILE_BYTES), &map_a, kb * TC_BK, (int)row0, tc_smem(full_a + s));
           }
@@ -223,29 +259,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // ===================== MMA issuer =====================
     tc_mbar_wait(tc_smem(b_full), 0);
     tc_fence_after();
-    u32 it = 0, tcount = 0;
+    const u64 bdesc0 = tc_smem_desc(tc_smem(sb));
+    const u64 adesc0 = tc_smem_desc(tc_smem(sa));
+    const u32 full0 = tc_smem(full_a), empty0 = tc_smem(empty_a);
+    u32 stage = 0, phase = 0, tcount = 0;
     for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
       const u32 as = tcount & 1u;
       tc_mbar_wait(tc_smem(tmem_empty + as), ((tcount >> 1) & 1u) ^ 1u);
       tc_fence_after();
       const u32 d_tmem = tmem_base + as * TC_BN;
-      for (int kb = 0; kb < a.kb; ++kb, ++it) {
-        const u32 s = it % stages;
-        tc_mbar_wait(tc_smem(full_a + s), (it / stages) & 1u);
-        tc_fence_after();
-        if (lane == 0) {
-          const u32 a_addr = tc_smem(sa + (size_t)s * TC_TILE_BYTES);
-          const u32 b_addr = tc_smem(sb + (size_t)kb * TC_TILE_BYTES);
-#pragma unroll
-          for (int k4 = 0; k4 < TC_BK / 32; ++k4)
-            tc_mma_i8(d_tmem, tc_smem_desc(a_addr + k4 * 32), tc_smem_desc(b_addr + k4 * 32), TC_IDESC,
-                      (kb | k4) != 0 ? 1u : 0u);
-          tc_commit(tc_smem(empty_a + s));  // frees the A stage when these MMAs have read it
+      if (a.packed) {
+        for (int kb = 0; kb < a.kb; ++kb) {
+          tc_mbar_wait(full0 + stage * 8, phase);
+          tc_fence_after();
+          const u32 a_tmem = tmem_base + 2 * TC_BN + stage * 32;  // A ring in tensor memory
+          const u64 bd = bdesc0 + (u64)(kb * (TC_TILE_BYTES >> 4));
+          tc_mma_i8_ts_elect(d_tmem, a_tmem, bd, TC_IDESC, kb != 0 ? 1u : 0u);
+          tc_mma_i8_ts_elect(d_tmem, a_tmem + 8, bd + 2, TC_IDESC, 1u);
+          tc_mma_i8_ts_elect(d_tmem, a_tmem + 16, bd + 4, TC_IDESC, 1u);
+          tc_mma_i8_ts_elect(d_tmem, a_tmem + 24, bd + 6, TC_IDESC, 1u);
+          tc_commit_elect(empty0 + stage * 8);  // frees the A stage when these MMAs have read it
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
-        __syncwarp();
+      } else {
+        for (int kb = 0; kb < a.kb; ++kb) {
+          tc_mbar_wait(full0 + stage * 8, phase);
+          tc_fence_after();
+          const u64 ad = adesc0 + (u64)(stage * (TC_TILE_BYTES >> 4));
+          const u64 bd = bdesc0 + (u64)(kb * (TC_TILE_BYTES >> 4));
+          tc_mma_i8_ss_elect(d_tmem, ad, bd, TC_IDESC, kb != 0 ? 1u : 0u);
+          tc_mma_i8_ss_elect(d_tmem, ad + 2, bd + 2, TC_IDESC, 1u);
+          tc_mma_i8_ss_elect(d_tmem, ad + 4, bd + 4, TC_IDESC, 1u);
+          tc_mma_i8_ss_elect(d_tmem, ad + 6, bd + 6, TC_IDESC, 1u);
+          tc_commit_elect(empty0 + stage * 8);
+          if (++stage == stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
       }
-      if (lane == 0) tc_commit(tc_smem(tmem_full + as));  // accumulator complete
-      __syncwarp();
+      tc_commit_elect(tc_smem(tmem_full + as));  // accumulator complete
     }
   } else if (warp < 6) {
     // ===================== epilogue (warps 2..5) =====================
@@ -324,29 +380,47 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (q0 + t < a.q) a.cnt[(size_t)(q0 + t) * gridDim.x + blockIdx.x] = s_cnt[t];
     }
   } else if (a.packed) {
-    // ===================== unpackers (warps 6..9): packed bits -> +-1 int8, swizzled =====================
-    const int u = threadIdx.x - 192;  // row of the tile handled by this thread
-    u32 it = 0, tcount = 0;
+    // ===================== unpackers (warps 6..9): packed bits -> +-1 int8 rows in TENSOR MEMORY =====================
+    // The A operand never touches shared memory: each thread expands the 128 dims of ITS row
+    // for one K block into 32 registers and stores them to its TMEM lane (tcgen05.st), so
+    // shared-memory bandwidth is left to the resident B operand.
+    const int lq = warp & 3;          // TMEM lane quarter this warp may access
+    const int u = lq * 32 + lane;     // row of the tile = TMEM lane
+    const u32 group = (u32)(warp - 6) >> 2;  // several warps per quarter take turns on the K blocks,
+                                             // so one warp's expand latency hides behind the others
+    u32 it = 0, tcount = 0, stage = 0, phase = 0;
     for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
       const u32 slot = tcount & 1u;
       tc_mbar_wait(tc_smem(pk_full + slot), (tcount >> 1) & 1u);
       const unsigned char* prow = spk + (size_t)slot * TC_BM * row_bytes + (size_t)u * row_bytes;
       for (int kb = 0; kb < a.kb; ++kb, ++it) {
-        const u32 s = it % stages;
-        const uint4 pw = *reinterpret_cast<const uint4*>(prow + kb * 16);  // 128 dims of this row
-        tc_mbar_wait(tc_smem(empty_a + s), ((it / stages) & 1u) ^ 1u);
-        unsigned char* dst = sa + (size_t)s * TC_TILE_BYTES + (size_t)u * TC_BK;
-        const u32 words[4] = {pw.x, pw.y, pw.z, pw.w};
-#pragma unroll
-        for (int wq = 0; wq < 4; ++wq) {
-          u32 o[8];
-          tc_expand32(words[wq], o);
-          // 16-byte chunks 2*wq and 2*wq+1 of this row, SWIZZLE_128B: chunk c lives at c ^ (row & 7)
-          const int c0 = (2 * wq) ^ (u & 7), c1 = (2 * wq + 1) ^ (u & 7);
-          *reinterpret_cast<uint4*>(dst + c0 * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<uint4*>(dst + c1 * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+        const u32 s = stage;
+        const u32 ph = phase;
+        if (++stage == stages) {
+          stage = 0;
+          phase ^= 1u;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async (UMMA) reads
+        if (TC_UNPACK_GROUPS > 1 && it % TC_UNPACK_GROUPS != group) continue;
+        const uint4 pw = *reinterpret_cast<const uint4*>(prow + kb * 16);  // 128 dims of this row
+        u32 o[32];
+        tc_expand32(pw.x, o);
+        tc_expand32(pw.y, o + 8);
+        tc_expand32(pw.z, o + 16);
+        tc_expand32(pw.w, o + 24);
+        tc_mbar_wait(tc_smem(empty_a + s), ph ^ 1u);
+        tc_fence_after();
+        const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + 2 * TC_BN + s * 32;
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+            ::"r"(taddr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]),
+              "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]),
+              "r"(o[16]), "r"(o[17]), "r"(o[18]), "r"(o[19]), "r"(o[20]), "r"(o[21]), "r"(o[22]), "r"(o[23]),
+              "r"(o[24]), "r"(o[25]), "r"(o[26]), "r"(o[27]), "r"(o[28]), "r"(o[29]), "r"(o[30]), "r"(o[31])
+            : "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
         tc_mbar_arrive(tc_smem(full_a + s));
       }
       tc_mbar_arrive(tc_smem(pk_empty + slot));
@@ -357,29 +431,106 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
-// tau_q = k-th best sample score, or INT_MIN when the sample holds fewer than k valid rows
-__global__ void tc_tau_kernel(const int* sample_scores, const int* sample_count, int q, int k, int* tau) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < q) tau[i] = (sample_count[i] >= k) ? sample_scores[(size_t)i * k + (k - 1)] : (int)0x80000000;
+// tau_q = k-th best sample score (INT_MIN when the sample holds fewer than k valid rows).
+// Keys are ~orderable(score): the k-th SMALLEST key.  One 1024-thread CTA per query: OR/AND
+// pre-pass, then an MSB-first byte radix select over the bytes that vary; no gather, no sort.
+constexpr int TAU_THREADS = 1024;
+__global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const u32* keys, long long n, int k, int* tau) {
+  __shared__ SelectScratch<TAU_THREADS> sc;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint4* kq = reinterpret_cast<const uint4*>(keys + (size_t)q * n);  // n is a multiple of 128
+  const long long n4 = n >> 2;
+  u32 vor = 0, vand = ~0u;
+  int vcnt = 0;
+  for (long long i = tid; i < n4; i += TAU_THREADS) {
+    const uint4 v = kq[i];
+    const u32 e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (e[j] != 0xFFFFFFFFu) {
+        vor |= e[j];
+        vand &= e[j];
+        ++vcnt;
+      }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    vor |= __shfl_xor_sync(0xffffffffu, vor, o);
+    vand &= __shfl_xor_sync(0xffffffffu, vand, o);
+    vcnt += __shfl_xor_sync(0xffffffffu, vcnt, o);
+  }
+  if (lane == 0) {
+    sc.red_or[warp] = vor;
+    sc.red_and[warp] = vand;
+    sc.red_cnt[warp] = vcnt;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    u64 o = 0, a2 = ~0ull;
+    int c = 0;
+    for (int w = 0; w < TAU_THREADS / 32; ++w) {
+      o |= sc.red_or[w];
+      a2 &= sc.red_and[w];
+      c += sc.red_cnt[w];
+    }
+    sc.b_or = o;
+    sc.b_and = a2;
+    sc.b_valid = c;
+  }
+  __syncthreads();
+  if (sc.b_valid < k) {
+    if (tid == 0) tau[q] = (int)0x80000000;
+    return;
+  }
+  const u32 v_or = (u32)sc.b_or;
+  const u32 diff = v_or ^ (u32)sc.b_and;
+  u32 prefix = 0, mask = 0;
+  int need = k;
+  for (int byte = 3; byte >= 0; --byte) {
+    const u32 bm = 0xFFu << (8 * byte);
+    if ((diff & bm) == 0) {
+      prefix |= v_or & bm;
+      mask |= bm;
+      continue;
+    }
+    for (int i = tid; i < 256; i += TAU_THREADS) sc.hist[i] = 0;
+    __syncthreads();
+    for (long long i = tid; i < n4; i += TAU_THREADS) {
+      const uint4 v = kq[i];
+      const u32 e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (e[j] != 0xFFFFFFFFu && (e[j] & mask) == prefix) atomicAdd(&sc.hist[(e[j] >> (8 * byte)) & 0xFF], 1);
+    }
+    __syncthreads();
+    select_find_bucket<TAU_THREADS>(sc, need);
+    __syncthreads();
+    prefix |= ((u32)sc.b_bucket) << (8 * byte);
+    mask |= bm;
+    need = sc.b_need;
+  }
+  if (tid == 0) tau[q] = i32_from_orderable(~prefix);
 }
 
 // exact top-k of each query's filtered list segments, (score desc, row asc)
+constexpr int LIST_THREADS = 1024;
 template <int MODE>  // MERGE_I32_DESC: scores as is; MERGE_HAMMING: dist = (dim - score) / 2
-__global__ void __launch_bounds__(MERGE_THREADS)
+__global__ void __launch_bounds__(LIST_THREADS)
     tc_select_lists_kernel(const u32* cnt, const int* list_score, const u32* list_row, int n_cta, int cap_cta,
                            int k, int kcap, int dim, long long row_base, void* out_a, long long* out_idx,
                            int* out_count, unsigned* overflow) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
   u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
   u32* s_k2 = reinterpret_cast<u32*>(s_k1 + kcap);
-  __shared__ SelectScratch<MERGE_THREADS> sc;
+  __shared__ SelectScratch<LIST_THREADS> sc;
   __shared__ u32 s_seg[256];  // n_cta <= 148
   const int q = blockIdx.x;
-  for (int i = threadIdx.x; i < n_cta; i += MERGE_THREADS) {
+  for (int i = threadIdx.x; i < n_cta; i += LIST_THREADS) {
     const u32 c = cnt[(size_t)q * n_cta + i];
     if (c > (u32)cap_cta) atomicAdd(overflow, 1u);
     s_seg[i] = c < (u32)cap_cta ? c : (u32)cap_cta;
@@ -398,8 +549,8 @@ __global__ void __launch_bounds__(MERGE_THREADS)
       y = K2_INVALID;
     }
   };
-  const int m = block_select_sorted<MERGE_THREADS>(get, (long long)n_cta * cap_cta, k, s_k1, s_k2, kcap, sc);
-  for (int j = threadIdx.x; j < k; j += MERGE_THREADS) {
+  const int m = block_select_sorted<LIST_THREADS>(get, (long long)n_cta * cap_cta, k, s_k1, s_k2, kcap, sc);
+  for (int j = threadIdx.x; j < k; j += LIST_THREADS) {
     const size_t o = (size_t)q * k + j;
     if (j < m) {
       const int s = i32_from_orderable((u32)(~s_k1[j]));
@@ -519,40 +670,20 @@ struct TcSmem {
 // B resident + A ring (+ packed double buffer) + thresholds / counters / barriers, inside 227 KB
 static TcSmem tc_smem_layout(int kb, bool packed) {
   const size_t limit = 232448;  // 227 KB opt-in maximum per block
-  const size_t fixed = 1024 /*alignment slack*/ + (size_t)kb * TC_TILE_BYTES +
-                       (packed ? 2 * (size_t)TC_BM * kb * 16 : 0) + 2 * TC_BN * 4 + 32 * 8 + 64;
-  int stages = (int)((limit - fixed) / TC_TILE_BYTES);
-  const int max_stages = packed ? 4 : TC_MAX_STAGES;  // packed mode only decouples unpack from MMA
-  if (stages > max_stages) stages = max_stages;
   TcSmem r;
+  if (packed) {
+    // A ring lives in tensor memory (8 x 32 columns next to the two 128-column accumulators);
+    // shared memory holds B, the packed double buffer and the small state only
+    r.stages = 8;
+    r.bytes = 1024 + (size_t)kb * TC_TILE_BYTES + 2 * (size_t)TC_BM * kb * 16 + 2 * TC_BN * 4 + 32 * 8 + 64;
+    return r;
+  }
+  const size_t fixed = 1024 /*alignment slack*/ + (size_t)kb * TC_TILE_BYTES + 2 * TC_BN * 4 + 32 * 8 + 64;
+  int stages = (int)((limit - fixed) / TC_TILE_BYTES);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   r.stages = stages;
   r.bytes = fixed + (size_t)stages * TC_TILE_BYTES;
   return r;
-}
-
-// select_keys32_kernel lives in exact.cu; the tensor-core path needs the same selection on
-// its dense sample keys, so a local copy of the launch is kept here.
-template <int MODE>
-__global__ void __launch_bounds__(MERGE_THREADS)
-    tc_select_keys32_kernel(const u32* keys, long long n, int k, int cap, void* out_a, long long* out_idx,
-                            int* out_count) {
-  extern __shared__ __align__(16) unsigned char merge_smem[];
-  u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
-  u32* s_k2 = reinterpret_cast<u32*>(s_k1 + cap);
-  __shared__ SelectScratch<MERGE_THREADS> sc;
-  const int q = blockIdx.x;
-  const u32* kq = keys + (size_t)q * n;
-  auto get = [&](long long i, u64& x, u32& y) {
-    const u32 key = kq[i];
-    x = (key == 0xFFFFFFFFu) ? K1_INVALID : (u64)key;
-    y = (u32)i;
-  };
-  const int m = block_select_sorted<MERGE_THREADS>(get, n, k, s_k1, s_k2, cap, sc);
-  for (int j = threadIdx.x; j < k; j += MERGE_THREADS) {
-    const bool have = j < m;
-    merge_write<MODE>(out_a, out_idx, (size_t)q * k + j, have, have ? s_k1[j] : 0, have ? s_k2[j] : 0, 0);
-  }
-  if (out_count && threadIdx.x == 0) out_count[q] = m;
 }
 
 // mode: 0 = int8 scores (score desc), 1 = Hamming over +-1 rows (dist asc)
@@ -613,12 +744,7 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
     RR_LAUNCH_CHECK();
   }
   const int kcap = merge_cap(k);
-  tc_select_keys32_kernel<MERGE_I32_DESC><<<q, MERGE_THREADS, (size_t)kcap * 12, st>>>(
-      a.dense_keys, p.sample_tiles * TC_BM, k, kcap, w + p.off_sscore, (long long*)(w + p.off_sidx),
-      (int*)(w + p.off_scount));
-  RR_LAUNCH_CHECK();
-  tc_tau_kernel<<<(q + 255) / 256, 256, 0, st>>>((const int*)(w + p.off_sscore), (const int*)(w + p.off_scount), q,
-                                                 k, (int*)(w + p.off_tau));
+  tc_tau_kernel<<<q, TAU_THREADS, 0, st>>>(a.dense_keys, p.sample_tiles * TC_BM, k, (int*)(w + p.off_tau));
   RR_LAUNCH_CHECK();
 
   // ---- pass 1: filter pass over all rows (every CTA of the grid writes its cnt entries)
@@ -633,11 +759,11 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   }
   // ---- pass 2: exact top-k of each query's list segments
   if (hamming)
-    tc_select_lists_kernel<MERGE_HAMMING><<<q, MERGE_THREADS, (size_t)kcap * 12, st>>>(
+    tc_select_lists_kernel<MERGE_HAMMING><<<q, LIST_THREADS, (size_t)kcap * 12, st>>>(
         a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, row_base, out_a, out_idx, nullptr,
         overflow_out);
   else
-    tc_select_lists_kernel<MERGE_I32_DESC><<<q, MERGE_THREADS, (size_t)kcap * 12, st>>>(
+    tc_select_lists_kernel<MERGE_I32_DESC><<<q, LIST_THREADS, (size_t)kcap * 12, st>>>(
         a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, row_base, out_a, out_idx, nullptr,
         overflow_out);
   RR_LAUNCH_CHECK();
