@@ -30,6 +30,7 @@
 // A list that outgrows its capacity raises an overflow counter and the caller falls back
 // to the CUDA-core path (never observed on the synthetic corpora; guards adversarial data).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "merge.cuh"
@@ -146,6 +147,8 @@ struct TcArgs {
   int stages;           // A-operand ring depth (<= TC_MAX_STAGES)
   int packed;           // 1: A is built in shared memory from packed sign bits (packed_codes)
   const uint8_t* packed_codes;  // [n][kb * 16] np.packbits rows (packed mode)
+  int debug;            // timing experiments only (RR_TC_DEBUG bit flags): 1 = unpackers skip expand + store,
+                        // 2 = MMA warp skips the MMAs, 4 = epilogue skips the TMEM reads (results are garbage)
 };
 
 // Expand 32 packed sign bits (np.packbits order: dim 8b is the MSB of byte b, bytes in
@@ -274,10 +277,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tc_fence_after();
           const u32 a_tmem = tmem_base + 2 * TC_BN + stage * 32;  // A ring in tensor memory
           const u64 bd = bdesc0 + (u64)(kb * (TC_TILE_BYTES >> 4));
-          tc_mma_i8_ts_elect(d_tmem, a_tmem, bd, TC_IDESC, kb != 0 ? 1u : 0u);
-          tc_mma_i8_ts_elect(d_tmem, a_tmem + 8, bd + 2, TC_IDESC, 1u);
-          tc_mma_i8_ts_elect(d_tmem, a_tmem + 16, bd + 4, TC_IDESC, 1u);
-          tc_mma_i8_ts_elect(d_tmem, a_tmem + 24, bd + 6, TC_IDESC, 1u);
+          if (!(a.debug & 2)) {
+            tc_mma_i8_ts_elect(d_tmem, a_tmem, bd, TC_IDESC, kb != 0 ? 1u : 0u);
+            tc_mma_i8_ts_elect(d_tmem, a_tmem + 8, bd + 2, TC_IDESC, 1u);
+            tc_mma_i8_ts_elect(d_tmem, a_tmem + 16, bd + 4, TC_IDESC, 1u);
+            tc_mma_i8_ts_elect(d_tmem, a_tmem + 24, bd + 6, TC_IDESC, 1u);
+          }
           tc_commit_elect(empty0 + stage * 8);  // frees the A stage when these MMAs have read it
           if (++stage == stages) {
             stage = 0;
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const long long dense_col = i * TC_BM + lq * 32 + lane;  // position among the launched rows
       const long long dense_ld = a.n_tiles * TC_BM;
 #pragma unroll 1
-      for (int c = 0; c < TC_BN / 32; ++c) {
+      for (int c = 0; c < ((a.debug & 4) ? 0 : TC_BN / 32); ++c) {
         u32 v[32];
         const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + as * TC_BN + c * 32;
         asm volatile(
@@ -401,6 +406,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           phase ^= 1u;
         }
         if (TC_UNPACK_GROUPS > 1 && it % TC_UNPACK_GROUPS != group) continue;
+        if (a.debug & 1) {
+          tc_mbar_wait(tc_smem(empty_a + s), ph ^ 1u);
+          tc_mbar_arrive(tc_smem(full_a + s));
+          continue;
+        }
         const uint4 pw = *reinterpret_cast<const uint4*>(prow + kb * 16);  // 128 dims of this row
         u32 o[32];
         tc_expand32(pw.x, o);
@@ -731,6 +741,10 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   a.stages = lay.stages;
   a.packed = packed ? 1 : 0;
   a.packed_codes = packed_codes;
+  {
+    const char* e = getenv("RR_TC_DEBUG");
+    a.debug = e ? atoi(e) : 0;
+  }
 
   // ---- pass 0: dense scores of a strided sample of row tiles -> tau
   const bool full_sample = p.sample_tiles == p.tiles;
@@ -866,6 +880,7 @@ extern "C" int rr_tc_dense_keys(const int8_t* emb, int64_t n, int32_t dim, const
   a.stages = lay.stages;
   a.packed = 0;
   a.packed_codes = nullptr;
+  a.debug = 0;
   dim3 grid((unsigned)(a.n_tiles < ctas_x ? a.n_tiles : ctas_x), qblocks);
   tc_i8_search_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
   RR_LAUNCH_CHECK();

@@ -17,4 +17,12 @@ qc = idx.quantize_queries(synth_query_rows_device(0, q, dim, 4, n))[1]
 for _ in range(3):
     idx.hamming_topk(qc, k, use_tc=True, check_overflow=False)
 torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(5):
+    idx.hamming_topk(qc, k, use_tc=True, check_overflow=False)
+b.record()
+torch.cuda.synchronize()
+import os
+print("debug", os.environ.get("RR_TC_DEBUG", "0"), "ms_per_call", a.elapsed_time(b) / 5)
 print("overflow", idx.tc_overflow_total())
