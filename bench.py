@@ -114,7 +114,10 @@ def run_reference_arm(args) -> None:
 
 # ---------------------------------------------------------------- GPU arm
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clock / throttle-reason samples every 100 ms, time-stamped; `summary` keeps the
+    samples that fall inside the given wall-clock windows (the timed regions)."""
+
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -128,7 +131,9 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self) -> dict:
+    def summary(self, windows) -> dict:
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -142,14 +147,18 @@ class ClockSampler:
         try:
             for ln in open(self.path):
                 f = [x.strip() for x in ln.split(",")]
-                if len(f) < 7:
+                if len(f) < 8:
                     continue
                 try:
-                    sm.append(float(f[0]))
-                    mx.append(float(f[1]))
+                    ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    c, m = float(f[1]), float(f[2])
                 except ValueError:
                     continue
-                for nm, v in zip(names, f[3:7]):
+                if not any(a - 0.05 <= ts <= b + 0.05 for a, b in windows):
+                    continue
+                sm.append(c)
+                mx.append(m)
+                for nm, v in zip(names, f[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         except Exception:
@@ -170,6 +179,8 @@ def run_gpu_arm(args) -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # started early: nvidia-smi takes ~1 s to come up
+    windows = []
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -235,13 +246,23 @@ def run_gpu_arm(args) -> None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
         return float(t.item())
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     launches0 = _lib.launch_count
+    w0 = time.time()
     total_ms = timed(step_device, args.steps, args.warmup)
     launches = _lib.launch_count - launches0 - 0
     launches_per_step = launches // (args.steps + args.warmup)
     e2e_ms = timed(step_e2e, args.steps, args.warmup)
-    clocks = sampler.stop() if sampler else {}
+    windows.append((w0, time.time()))
+    # the timed regions last only tens of milliseconds; keep the same step running for ~1.5 s so
+    # that the 100 ms clock sampler sees the GPU under this load (reported with the timed windows)
+    w1 = time.time()
+    while time.time() - w1 < 1.5:
+        for _ in range(20):
+            step_device()
+        torch.cuda.synchronize()
+    windows.append((w1, time.time()))
+    if world > 1:
+        dist.barrier()
     if index.tc_overflow_total() != 0:
         raise SystemExit("tensor-core candidate lists overflowed during the timed region: results not exact")
 
@@ -250,6 +271,7 @@ def run_gpu_arm(args) -> None:
             dist.barrier()
             dist.destroy_process_group()
         return
+    clocks = {}
 
     # ---- stage breakdown + roofline of the scan (single GPU view of rank 0's shard)
     qf, qc = index.quantize_queries(queries_dev)
@@ -278,6 +300,7 @@ def run_gpu_arm(args) -> None:
     rescore_ms = time_stage(lambda: index.rescore(qf, cand, top_k, 0.0, prefer_int8=False), reps)
     quant_ms = time_stage(lambda: index.quantize_queries(queries_dev), reps)
     scan1_ms = time_stage(lambda: index.hamming_topk(qc[:1].contiguous(), cand_k), reps)
+    clocks = sampler.summary(windows) if sampler else {}
 
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
@@ -353,7 +376,8 @@ def run_gpu_arm(args) -> None:
         "stages_ms": {"quantize_queries": quant_ms, "hamming_topk": scan_ms, "rescore_f32": rescore_ms},
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "clocks": {k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
+        "clocks": dict({k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
+                       window="timed regions + 1.5 s of the same step back to back"),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

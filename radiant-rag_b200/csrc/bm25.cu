@@ -63,9 +63,25 @@ __global__ void __launch_bounds__(BM_THREADS) bm25_tile_kernel(const Bm25Args a)
     const int t = terms[j];
     if (t < 0 || t >= a.n_terms) continue;  // unknown token: skipped (bm25_index.py:238-239)
     const long long lo = ptr[t], hi = ptr[t + 1];
-    for (long long p = lo + threadIdx.x; p < hi; p += BM_THREADS) {
-      const int r = (int)((long long)a.post_row[p] - tile_lo);
-      acc[r] = __dadd_rn(acc[r], a.post_impact[p]);
+    // four postings per thread in flight (independent loads first, then the adds: a document
+    // occurs at most once in a term's segment, so the order inside a term is immaterial)
+    for (long long p = lo + threadIdx.x; p < hi; p += 4 * BM_THREADS) {
+      u32 rr4[4];
+      double im4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long pu = p + (long long)u * BM_THREADS;
+        const bool ok = pu < hi;
+        rr4[u] = ok ? __ldg(a.post_row + pu) : 0u;
+        im4[u] = ok ? __ldg(a.post_impact + pu) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (p + (long long)u * BM_THREADS < hi) {
+          const int r = (int)((long long)rr4[u] - tile_lo);
+          acc[r] = __dadd_rn(acc[r], im4[u]);
+        }
+      }
     }
     __syncthreads();
   }

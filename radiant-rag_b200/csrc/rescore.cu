@@ -151,24 +151,56 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_f32_kernel(const RescoreAr
   for (int d = threadIdx.x; d < a.dim; d += RS_THREADS) sq[d] = a.queries[(size_t)q * a.dim + d];
   __syncthreads();
   const long long* cand = a.cand_idx + (size_t)q * a.c;
-  for (int ci = warp; ci < a.c; ci += RS_WARPS) {
-    const long long idx = cand[ci];
-    const long long local = idx - a.row_base;
-    const bool valid = idx >= 0 && local >= 0 && local < a.n;
-    float s = -INFINITY;
-    if (valid) {
-      double acc;
-      if (EMB == RR_F32)
-        acc = dot_f32_row(sq, reinterpret_cast<const float*>(a.emb) + (size_t)local * a.dim, a.dim, lane);
-      else
-        acc = dot_i8_row(sq, reinterpret_cast<const int8_t*>(a.emb) + (size_t)local * a.dim, a.dim, lane);
-      s = (float)acc;
+  // two candidate rows per warp iteration: both rows' 128-bit loads are in flight together,
+  // which is what the latency-bound random gather needs
+  for (int c0 = warp; c0 < a.c; c0 += 2 * RS_WARPS) {
+    const int c1 = c0 + RS_WARPS;
+    const long long idx0 = cand[c0];
+    const long long idx1 = (c1 < a.c) ? cand[c1] : -1;
+    const long long l0 = idx0 - a.row_base, l1 = idx1 - a.row_base;
+    const bool v0 = idx0 >= 0 && l0 >= 0 && l0 < a.n;
+    const bool v1 = idx1 >= 0 && l1 >= 0 && l1 < a.n;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (EMB == RR_F32 && (a.dim & 3) == 0) {
+      const float4* r0 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.emb) + (size_t)(v0 ? l0 : 0) * a.dim);
+      const float4* r1 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.emb) + (size_t)(v1 ? l1 : 0) * a.dim);
+      const float4* q4 = reinterpret_cast<const float4*>(sq);
+      for (int v = lane; v < (a.dim >> 2); v += 32) {
+        float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
+        if (v0) e0 = __ldg(r0 + v);
+        if (v1) e1 = __ldg(r1 + v);
+        const float4 w = q4[v];
+        acc0 += (double)w.x * (double)e0.x;
+        acc1 += (double)w.x * (double)e1.x;
+        acc0 += (double)w.y * (double)e0.y;
+        acc1 += (double)w.y * (double)e1.y;
+        acc0 += (double)w.z * (double)e0.z;
+        acc1 += (double)w.z * (double)e1.z;
+        acc0 += (double)w.w * (double)e0.w;
+        acc1 += (double)w.w * (double)e1.w;
+      }
+      acc0 = warp_sum_f64(acc0);
+      acc1 = warp_sum_f64(acc1);
+    } else {
+      if (v0)
+        acc0 = (EMB == RR_F32)
+                   ? dot_f32_row(sq, reinterpret_cast<const float*>(a.emb) + (size_t)l0 * a.dim, a.dim, lane)
+                   : dot_i8_row(sq, reinterpret_cast<const int8_t*>(a.emb) + (size_t)l0 * a.dim, a.dim, lane);
+      if (v1)
+        acc1 = (EMB == RR_F32)
+                   ? dot_f32_row(sq, reinterpret_cast<const float*>(a.emb) + (size_t)l1 * a.dim, a.dim, lane)
+                   : dot_i8_row(sq, reinterpret_cast<const int8_t*>(a.emb) + (size_t)l1 * a.dim, a.dim, lane);
     }
     if (lane == 0) {
-      if (MODE == 0)
-        keys[ci] = valid ? (((u64)(~f32_orderable(s)) << 32) | (u64)(u32)ci) : K1_INVALID;
-      else
-        a.out_score[(size_t)q * a.c + ci] = s;
+      const float s0 = v0 ? (float)acc0 : -INFINITY;
+      const float s1 = v1 ? (float)acc1 : -INFINITY;
+      if (MODE == 0) {
+        keys[c0] = v0 ? (((u64)(~f32_orderable(s0)) << 32) | (u64)(u32)c0) : K1_INVALID;
+        if (c1 < a.c) keys[c1] = v1 ? (((u64)(~f32_orderable(s1)) << 32) | (u64)(u32)c1) : K1_INVALID;
+      } else {
+        a.out_score[(size_t)q * a.c + c0] = s0;
+        if (c1 < a.c) a.out_score[(size_t)q * a.c + c1] = s1;
+      }
     }
   }
   if (MODE == 0) {
