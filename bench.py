@@ -184,6 +184,7 @@ def run_gpu_arm(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     n, dim, nq, cand_k, top_k, seed = (CFG[k] for k in ("n", "dim", "q", "cand_k", "top_k", "seed"))
     mult = cand_k / top_k
@@ -256,10 +257,12 @@ def run_gpu_arm(args) -> None:
     # the timed regions last only tens of milliseconds; keep the same step running for ~1.5 s so
     # that the 100 ms clock sampler sees the GPU under this load (reported with the timed windows)
     w1 = time.time()
-    while time.time() - w1 < 1.5:
-        for _ in range(20):
-            step_device()
-        torch.cuda.synchronize()
+    n_sustain = max(20, min(20000, int(1500.0 / max(total_ms / args.steps, 1e-3))))  # same count on every rank
+    for i in range(n_sustain):
+        step_device()
+        if i % 50 == 49:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
     windows.append((w1, time.time()))
     if world > 1:
         dist.barrier()
