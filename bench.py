@@ -184,8 +184,20 @@ def run_gpu_arm(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout on the first communicator; rank 0 must print ONE
+        # JSON line, so stdout is pointed at stderr (fd level) until the first collective is done
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     n, dim, nq, cand_k, top_k, seed = (CFG[k] for k in ("n", "dim", "q", "cand_k", "top_k", "seed"))
     mult = cand_k / top_k
 

@@ -35,8 +35,18 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)  # NCCL's version banner goes to stderr
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lo, hi = shard_range(n_total, rank, world)
     bound = 131070.0 * 2.0 ** -synthetic.value_shift(dim)  # every synthetic value lies inside
     ranges = np.stack([np.full(dim, -bound, np.float32), np.full(dim, bound, np.float32)])
