@@ -10,12 +10,14 @@ does (radiant/orchestrator.py:994-998).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import threading
 from pathlib import Path
 from typing import Optional
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "librr_b200.so"
+# RR_B200_LIB points at an alternative build of the same library (kernel-variant experiments)
+LIB_PATH = Path(os.environ["RR_B200_LIB"]) if os.environ.get("RR_B200_LIB") else PKG_DIR / "librr_b200.so"
 
 RR_F32 = 0
 RR_I8 = 1

@@ -64,8 +64,9 @@ def _tokenize(text: str) -> List[str]:
 class Bm25DeviceIndex:
     """Tile-sharded inverted CSR + per-posting float64 impacts in HBM (one shard).
 
-    tile t owns rows [t*tile_docs, (t+1)*tile_docs); postings are sorted by
-    (tile, term, row):
+    tile t owns rows [t*tile_docs, (t+1)*tile_docs); postings are grouped by
+    (tile, term); inside a segment they are interleaved over row % 16 (bank-conflict-free
+    accumulation, see _bank_interleave) or ascending by row (bank_interleave=False):
         tile_term_ptr int64 [n_tiles, n_terms+1]
         post_row      int32 [P]   (read as uint32 by the kernel)
         post_impact   f64   [P]   idf_t * (tf*(k1+1)) / (tf + k1*((1-b) + (b*len)/avgdl))
@@ -102,6 +103,7 @@ class Bm25DeviceIndex:
         tile_docs: int = 8192,
         row_base: int = 0,
         doc_len=None,
+        bank_interleave: bool = True,
     ) -> "Bm25DeviceIndex":
         """doc_ptr int64 [N+1] / doc_terms int32 [T]: the documents of THIS shard as CSR of
         term ids; idf f64 [n_terms] (0 for unknown terms), avgdl, k1, b: global tables
@@ -109,7 +111,9 @@ class Bm25DeviceIndex:
         idf is evaluated ON THE HOST with the reference's scalar expression,
         np.log((n - df + 0.5) / (df + 0.5) + 1.0), bm25_index.py:131-135).  doc_len int32 [N] overrides diff(doc_ptr) (the
         reference keeps ``doc_lengths`` separately).  Sorting / counting uses torch on the
-        device (index build is not the hot path); impacts come from rr_bm25_impacts."""
+        device (index build is not the hot path); impacts come from rr_bm25_impacts.
+        bank_interleave: order each (tile, term) segment round-robin over row % 16 (see
+        _bank_interleave); a document occurs once per segment so the order is free."""
         dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         _lib.init(dev.index or 0)
         ptr = to_device(doc_ptr, dev, torch.int64)
@@ -130,6 +134,8 @@ class Bm25DeviceIndex:
         key, _ = torch.sort(key)
         ukey, tf = torch.unique_consecutive(key, return_counts=True)
         del key
+        if bank_interleave and ukey.numel() > 1:
+            ukey, tf = cls._bank_interleave(ukey, tf, tile_docs)
         tt = ukey // tile_docs  # tile * V + term
         post_row64 = (tt // v) * tile_docs + (ukey % tile_docs)
         term = tt % v
@@ -157,6 +163,33 @@ class Bm25DeviceIndex:
         post_row = post_row64.to(torch.int32).contiguous()
         torch.cuda.current_stream().synchronize()  # temporaries die here
         return cls(dev, n, v, tile_docs, tile_term_ptr, post_row, post_impact, row_base)
+
+    SMEM_BANKS64 = 16  # 8-byte accumulators: 16 bank pairs per half-warp
+
+    @classmethod
+    def _bank_interleave(cls, ukey: torch.Tensor, tf: torch.Tensor, tile_docs: int):
+        """Reorder the postings of every (tile, term) segment so that consecutive postings
+        cycle through row % 16: the query kernel's shared-memory read-modify-write of the
+        float64 accumulators (16 lanes of a half-warp = 16 consecutive postings) then hits
+        16 different bank pairs instead of a random multiset (~3-way conflicts).
+        ukey = (tile*V + term) * tile_docs + row_in_tile, sorted."""
+        nb = cls.SMEM_BANKS64
+        dev = ukey.device
+        seg = ukey // tile_docs
+        bank = (ukey % tile_docs) % nb
+        grp, perm1 = torch.sort(seg * nb + bank, stable=True)  # rows stay ascending inside a group
+        del seg, bank
+        _, gcount = torch.unique_consecutive(grp, return_counts=True)
+        gstart = torch.cumsum(gcount, 0) - gcount
+        rank = torch.arange(grp.numel(), dtype=torch.int64, device=dev) - torch.repeat_interleave(gstart, gcount)
+        del gcount, gstart
+        per_bank = (tile_docs + nb - 1) // nb + 1
+        key3 = ((grp // nb) * per_bank + rank) * nb + (grp % nb)  # (segment, rank, bank)
+        del grp, rank
+        _, perm2 = torch.sort(key3)
+        del key3
+        order = perm1[perm2]
+        return ukey[order].contiguous(), tf[order].contiguous()
 
     def search_batch(self, q_terms, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """q_terms int32 [Q, L] term ids in query-token order, -1 = unknown / padding.

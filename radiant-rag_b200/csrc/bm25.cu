@@ -24,7 +24,15 @@
 
 namespace rr {
 
-constexpr int BM_THREADS = 256;
+#ifndef RR_BM_THREADS
+#define RR_BM_THREADS 256
+#endif
+#ifndef RR_BM_UNROLL
+#define RR_BM_UNROLL 4
+#endif
+constexpr int BM_THREADS = RR_BM_THREADS;
+constexpr int BM_UNROLL = RR_BM_UNROLL;
+constexpr int BM_TERMS = 32;  // query tokens whose segment bounds are fetched together
 
 struct Bm25Args {
   const long long* tile_term_ptr;
@@ -41,6 +49,7 @@ struct Bm25Args {
   int cap;
   u64* part_k1;  // [q][n_tiles][k]
   u32* part_k2;
+  u64* qbound;   // [q] best tile-local k-th key seen so far (K1_INVALID = none yet)
 };
 
 __global__ void __launch_bounds__(BM_THREADS) bm25_tile_kernel(const Bm25Args a) {
@@ -59,39 +68,129 @@ __global__ void __launch_bounds__(BM_THREADS) bm25_tile_kernel(const Bm25Args a)
 
   const long long* ptr = a.tile_term_ptr + (size_t)tile * (a.n_terms + 1);
   const int* terms = a.q_terms + (size_t)qi * a.q_len;
-  for (int j = 0; j < a.q_len; ++j) {
-    const int t = terms[j];
-    if (t < 0 || t >= a.n_terms) continue;  // unknown token: skipped (bm25_index.py:238-239)
-    const long long lo = ptr[t], hi = ptr[t + 1];
-    // four postings per thread in flight (independent loads first, then the adds: a document
-    // occurs at most once in a term's segment, so the order inside a term is immaterial)
-    for (long long p = lo + threadIdx.x; p < hi; p += 4 * BM_THREADS) {
-      u32 rr4[4];
-      double im4[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long pu = p + (long long)u * BM_THREADS;
-        const bool ok = pu < hi;
-        rr4[u] = ok ? __ldg(a.post_row + pu) : 0u;
-        im4[u] = ok ? __ldg(a.post_impact + pu) : 0.0;
+  // The walk is a chain of dependent global loads (term id -> segment bounds -> postings ->
+  // accumulate -> barrier), and a (query, tile) CTA has only a handful of short segments, so
+  // the chain latency, not bandwidth, is what a CTA waits on.  Two measures: the segment
+  // bounds of up to BM_TERMS query tokens are fetched by that many threads at once, and the
+  // postings are software-pipelined one batch ahead across segment boundaries (loads of the
+  // next batch are in flight while the current one is added; only the adds are ordered).
+  __shared__ long long s_lo[BM_TERMS], s_hi[BM_TERMS];
+  constexpr int BATCH = BM_UNROLL * BM_THREADS;
+  for (int j0 = 0; j0 < a.q_len; j0 += BM_TERMS) {
+    const int nt = min(BM_TERMS, a.q_len - j0);
+    __syncthreads();  // previous block of terms fully accumulated; s_lo/s_hi reusable
+    if (threadIdx.x < nt) {
+      const int t = terms[j0 + threadIdx.x];
+      long long lo = 0, hi = 0;
+      if (t >= 0 && t < a.n_terms) {  // unknown token: skipped (bm25_index.py:238-239)
+        lo = __ldg(ptr + t);
+        hi = __ldg(ptr + t + 1);
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (p + (long long)u * BM_THREADS < hi) {
-          const int r = (int)((long long)rr4[u] - tile_lo);
-          acc[r] = __dadd_rn(acc[r], im4[u]);
-        }
-      }
+      s_lo[threadIdx.x] = lo;
+      s_hi[threadIdx.x] = hi;
     }
     __syncthreads();
+    // cursor = (term j, first posting of the batch); CTA-uniform
+    int j = 0;
+    long long base = s_lo[0];
+    while (j < nt && base >= s_hi[j]) {
+      ++j;
+      if (j < nt) base = s_lo[j];
+    }
+    u32 row_c[BM_UNROLL], row_n[BM_UNROLL];
+    double imp_c[BM_UNROLL], imp_n[BM_UNROLL];
+    auto load = [&](int jj, long long bb, u32* r, double* im) {
+      const long long hi = s_hi[jj];
+#pragma unroll
+      for (int u = 0; u < BM_UNROLL; ++u) {
+        const long long pu = bb + threadIdx.x + (long long)u * BM_THREADS;
+        const bool ok = pu < hi;
+        r[u] = ok ? __ldg(a.post_row + pu) : 0xFFFFFFFFu;
+        im[u] = ok ? __ldg(a.post_impact + pu) : 0.0;
+      }
+    };
+    if (j < nt) load(j, base, row_c, imp_c);
+    while (j < nt) {
+      int jn = j;
+      long long bn = base + BATCH;
+      while (jn < nt && bn >= s_hi[jn]) {
+        ++jn;
+        if (jn < nt) bn = s_lo[jn];
+      }
+      if (jn < nt) load(jn, bn, row_n, imp_n);
+      // a document occurs at most once in a term's segment: adds inside a term never collide
+#pragma unroll
+      for (int u = 0; u < BM_UNROLL; ++u) {
+        if (row_c[u] != 0xFFFFFFFFu) {
+          const int r = (int)((long long)row_c[u] - tile_lo);
+          acc[r] = __dadd_rn(acc[r], imp_c[u]);
+        }
+      }
+      if (jn != j) __syncthreads();  // next batch belongs to a later query token
+#pragma unroll
+      for (int u = 0; u < BM_UNROLL; ++u) {
+        row_c[u] = row_n[u];
+        imp_c[u] = imp_n[u];
+      }
+      j = jn;
+      base = bn;
+    }
   }
+  __syncthreads();
 
   auto get = [&](long long i, u64& x, u32& y) {
     const double s = acc[i];
     x = (s > 0.0) ? ~f64_orderable(s) : K1_INVALID;  // score <= 0 dropped (bm25_index.py:267)
     y = (u32)(tile_lo + i);
   };
-  const int m = block_select_sorted<BM_THREADS>(get, rows_here, a.k, s_k1, s_k2, a.cap, sc);
+  // Cross-tile bound: once any tile of this query has k positive scores, its k-th key is
+  // an upper bound on the query's final k-th key, and a document whose key is strictly
+  // larger can never reach the merged top-k.  Tiles are scheduled query-fastest, so for
+  // batches wider than one wave of CTAs every tile but the first sees a bound, keeps
+  // ~k candidates and finishes with one pass and a small sort instead of a radix select.
+  __shared__ u64 s_bound;
+  if (threadIdx.x == 0) s_bound = *reinterpret_cast<volatile u64*>(a.qbound + qi);
+  __syncthreads();
+  const u64 bound = s_bound;
+  int m = -1;
+  bool sorted = true;
+  if (bound != K1_INVALID) {
+    if (threadIdx.x == 0) sc.count = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows_here; i += BM_THREADS) {
+      u64 x;
+      u32 y;
+      get(i, x, y);
+      if (x <= bound) {
+        const int slot = atomicAdd(&sc.count, 1);
+        if (slot < a.cap) {
+          s_k1[slot] = x;
+          s_k2[slot] = y;
+        }
+      }
+    }
+    __syncthreads();
+    const int cnt = sc.count;
+    if (cnt <= a.k) {
+      // all of them go to the merge, which does not need its input sorted
+      m = cnt;
+      sorted = false;
+    } else if (cnt <= a.cap) {
+      int p = 1;
+      while (p < cnt) p <<= 1;
+      for (int i = cnt + threadIdx.x; i < p; i += BM_THREADS) {
+        s_k1[i] = K1_INVALID;
+        s_k2[i] = K2_INVALID;
+      }
+      __syncthreads();
+      block_bitonic_sort_pairs<BM_THREADS>(s_k1, s_k2, p);
+      m = a.k;
+    }
+    __syncthreads();
+  }
+  if (m < 0) m = block_select_sorted<BM_THREADS, true>(get, rows_here, a.k, s_k1, s_k2, a.cap, sc);
+  if (sorted && m == a.k && threadIdx.x == 0)
+    atomicMin(reinterpret_cast<unsigned long long*>(a.qbound + qi), (unsigned long long)s_k1[a.k - 1]);
   const size_t o = ((size_t)qi * a.n_tiles + tile) * a.k;
   for (int j = threadIdx.x; j < a.k; j += BM_THREADS) {
     a.part_k1[o + j] = (j < m) ? s_k1[j] : K1_INVALID;
@@ -120,7 +219,7 @@ using namespace rr;
 extern "C" size_t rr_bm25_topk_workspace_bytes(int32_t n_tiles, int32_t q, int32_t k) {
   if (n_tiles <= 0 || q <= 0 || k <= 0) return 256;
   const size_t e = (size_t)n_tiles * q * k;
-  return align_up(e * 8, 256) + align_up(e * 4, 256) + 256;
+  return align_up(e * 8, 256) + align_up(e * 4, 256) + align_up((size_t)q * 8, 256) + 256;
 }
 
 extern "C" int rr_bm25_impacts(const int32_t* post_tf, const int32_t* post_len,
@@ -194,6 +293,8 @@ extern "C" int rr_bm25_topk(const int64_t* tile_term_ptr, const uint32_t* post_r
   const size_t e = (size_t)n_tiles * q * k;
   a.part_k1 = (u64*)workspace;
   a.part_k2 = (u32*)((char*)workspace + align_up(e * 8, 256));
+  a.qbound = (u64*)((char*)workspace + align_up(e * 8, 256) + align_up(e * 4, 256));
+  RR_CUDA(cudaMemsetAsync(a.qbound, 0xFF, (size_t)q * 8, st));
   const size_t smem = (size_t)tile_docs * 8 + (size_t)a.cap * 12;
   RR_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)smem));

@@ -7,12 +7,17 @@
 // rr_int8_search_topk is the exact int8 x int8 -> int32 search of config 4 with the
 // same ordering.
 //
-// First-correct design (round 1): a warp streams one row with 128-bit loads and keeps
-// EX_QT query accumulators in registers, so every row is read from HBM once per tile
-// of EX_QT queries; scores are written as 32-bit order-preserving keys [q, n] and the
-// per-query top-k is taken by block_select_sorted.  float32 rows accumulate in
-// float64 (correctly rounded cosine); int8 rows use DP4A (exact).
-// Algorithmic bytes per launch: n * dim * sizeof(elem) + 4 * n * EX_QT written.
+// Score kernels: a warp streams R rows at a time with 128-bit loads (R independent loads
+// in flight per lane) against QT queries held in shared memory as float64, so a row is
+// read from HBM once per QT queries and the query operands are read from shared memory
+// once per R rows.  float32 rows accumulate in float64 (correctly rounded cosine, no
+// f32->f64 conversion of the query in the loop); int8 rows use DP4A (exact).  Scores go
+// out as 32-bit order-preserving keys [q, n].
+// Selection is two-level: (chunk, query) CTAs take the top-k of <= SEL_CHUNK_MAX keys each
+// (block_select_sorted with the per-thread-minimum bound shortcut), then one CTA per
+// query merges the chunk winners.  Single-query latency is therefore one pass over the
+// rows at HBM speed plus two short launches.
+// Algorithmic bytes per launch: n * dim * sizeof(elem) per QT queries + 8 * n * q (keys).
 #include <math.h>
 
 #include "common.cuh"
@@ -37,6 +42,130 @@ struct ExactArgs {
   u32* keys;  // [q][n]
 };
 
+// dim % 4 == 0 and 16-byte aligned rows.  Shared memory: the queries as float64, split
+// into the (x,y) and (z,w) halves of each float4 column group so that consecutive lanes
+// read consecutive 16-byte words (conflict-free LDS.128).
+template <int QT, int R>
+__global__ void __launch_bounds__(EX_THREADS) exact_f32_scores_vec_kernel(const ExactArgs a) {
+  extern __shared__ __align__(16) unsigned char ex_smem[];
+  const int dim4 = a.dim >> 2;
+  double2* sq_lo = reinterpret_cast<double2*>(ex_smem);  // [QT][dim4]
+  double2* sq_hi = sq_lo + (size_t)QT * dim4;             // [QT][dim4]
+  __shared__ double s_qnorm[QT];
+  const int q0 = blockIdx.y * QT;
+  const int nq = min(QT, a.q - q0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float4* queries = reinterpret_cast<const float4*>(a.queries);
+  for (int i = threadIdx.x; i < QT * dim4; i += EX_THREADS) {
+    const int qi = i / dim4, v = i - qi * dim4;
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qi < nq) w = queries[(size_t)(q0 + qi) * dim4 + v];
+    sq_lo[i] = make_double2((double)w.x, (double)w.y);
+    sq_hi[i] = make_double2((double)w.z, (double)w.w);
+  }
+  __syncthreads();
+  for (int j = warp; j < QT; j += EX_WARPS) {
+    double s = 0.0;
+    for (int v = lane; v < dim4; v += 32) {
+      const double2 lo = sq_lo[j * dim4 + v], hi = sq_hi[j * dim4 + v];
+      s += lo.x * lo.x;
+      s += lo.y * lo.y;
+      s += hi.x * hi.x;
+      s += hi.y * hi.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_qnorm[j] = sqrt(s);
+  }
+  __syncthreads();
+  const float4* emb = reinterpret_cast<const float4*>(a.emb);
+  const long long groups = (a.n + R - 1) / R;
+  const long long warps_total = (long long)gridDim.x * EX_WARPS;
+  for (long long g = (long long)blockIdx.x * EX_WARPS + warp; g < groups; g += warps_total) {
+    const long long row0 = g * R;
+    bool valid[R];
+    const float4* rp[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long row = row0 + r;
+      valid[r] = row < a.n;
+      if (valid[r] && a.tags) valid[r] = ((unsigned)a.tags[row] & a.tag_mask) == a.tag_value;
+      rp[r] = emb + (size_t)(valid[r] ? row : 0) * dim4;
+    }
+    double acc[QT][R];
+    double nn[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      nn[r] = 0.0;
+#pragma unroll
+      for (int j = 0; j < QT; ++j) acc[j][r] = 0.0;
+    }
+    for (int v = lane; v < dim4; v += 32) {
+      float4 e[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) e[r] = valid[r] ? __ldg(rp[r] + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+      double ex[R], ey[R], ez[R], ew[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        ex[r] = (double)e[r].x;
+        ey[r] = (double)e[r].y;
+        ez[r] = (double)e[r].z;
+        ew[r] = (double)e[r].w;
+        nn[r] += ex[r] * ex[r];
+        nn[r] += ey[r] * ey[r];
+        nn[r] += ez[r] * ez[r];
+        nn[r] += ew[r] * ew[r];
+      }
+#pragma unroll
+      for (int j = 0; j < QT; ++j) {
+        const double2 lo = sq_lo[j * dim4 + v], hi = sq_hi[j * dim4 + v];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          acc[j][r] += lo.x * ex[r];
+          acc[j][r] += lo.y * ey[r];
+          acc[j][r] += hi.x * ez[r];
+          acc[j][r] += hi.y * ew[r];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        nn[r] += __shfl_xor_sync(0xffffffffu, nn[r], o);
+#pragma unroll
+        for (int j = 0; j < QT; ++j) acc[j][r] += __shfl_xor_sync(0xffffffffu, acc[j][r], o);
+      }
+    }
+    // lane = r * QT + j writes the key of (query j, row r)
+    if (lane < QT * R) {
+      const int r_me = lane / QT, j_me = lane % QT;
+      double dotv = 0.0, nnv = 0.0;
+      bool ok = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (r == r_me) {
+          nnv = nn[r];
+          ok = valid[r];
+#pragma unroll
+          for (int j = 0; j < QT; ++j)
+            if (j == j_me) dotv = acc[j][r];
+        }
+      const long long row = row0 + r_me;
+      if (j_me < nq && row < a.n) {
+        const double qn = s_qnorm[j_me];
+        u32 key = KEY32_INVALID;
+        if (ok && nnv > 0.0 && qn > 0.0) {
+          const float s = (float)(dotv / (sqrt(nnv) * qn));
+          if ((double)s >= a.min_similarity) key = ~f32_orderable(s);
+        }
+        a.keys[(size_t)(q0 + j_me) * a.n + row] = key;
+      }
+    }
+  }
+}
+
+// any dim / alignment (scalar loads)
 __global__ void __launch_bounds__(EX_THREADS) exact_f32_scores_kernel(const ExactArgs a) {
   extern __shared__ __align__(16) unsigned char ex_smem[];
   float* sq = reinterpret_cast<float*>(ex_smem);  // [EX_QT][dim]
@@ -176,29 +305,81 @@ __global__ void __launch_bounds__(EX_THREADS) exact_i8_scores_kernel(const Exact
   }
 }
 
-// per-query top-k over the 32-bit key array
-template <int MODE>
+// level 1 of the per-query top-k over the 32-bit key array: CTA (chunk, query) leaves its
+// chunk's k best as (key, row) pairs in part_k1/part_k2 [q][n_chunks][k]
 __global__ void __launch_bounds__(MERGE_THREADS)
-    select_keys32_kernel(const u32* keys, long long n, int k, int cap, long long row_base, void* out_a,
-                         long long* out_idx, int* out_count) {
+    select_keys32_chunk_kernel(const u32* keys, long long n, long long chunk, int n_chunks, int k, int cap,
+                               u64* part_k1, u32* part_k2) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
   u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
   u32* s_k2 = reinterpret_cast<u32*>(s_k1 + cap);
   __shared__ SelectScratch<MERGE_THREADS> sc;
-  const int q = blockIdx.x;
-  const u32* kq = keys + (size_t)q * n;
+  const int q = blockIdx.y;
+  const long long lo = (long long)blockIdx.x * chunk;
+  const long long len = min(chunk, n - lo);
+  const u32* kq = keys + (size_t)q * n + lo;
   auto get = [&](long long i, u64& x, u32& y) {
     const u32 key = kq[i];
     x = (key == KEY32_INVALID) ? K1_INVALID : (u64)key;
-    y = (u32)i;
+    y = (u32)(lo + i);
   };
-  const int m = block_select_sorted<MERGE_THREADS>(get, n, k, s_k1, s_k2, cap, sc);
+  const int m = block_select_sorted<MERGE_THREADS, true>(get, len, k, s_k1, s_k2, cap, sc);
+  const size_t o = ((size_t)q * n_chunks + blockIdx.x) * k;
   for (int j = threadIdx.x; j < k; j += MERGE_THREADS) {
-    const bool have = j < m;
-    merge_write<MODE>(out_a, out_idx, (size_t)q * k + j, have, have ? s_k1[j] : 0, have ? s_k2[j] : 0,
-                      row_base);
+    part_k1[o + j] = (j < m) ? s_k1[j] : K1_INVALID;
+    part_k2[o + j] = (j < m) ? s_k2[j] : K2_INVALID;
   }
-  if (out_count && threadIdx.x == 0) out_count[q] = m;
+}
+
+constexpr long long SEL_CHUNK_MIN = 4096;
+constexpr int SEL_CHUNKS_MAX = 1024;
+
+static long long select_chunk_rows(long long n) {
+  long long c = (n + SEL_CHUNKS_MAX - 1) / SEL_CHUNKS_MAX;
+  if (c < SEL_CHUNK_MIN) c = SEL_CHUNK_MIN;
+  return (c + 255) / 256 * 256;
+}
+static int select_n_chunks(long long n) {
+  const long long c = select_chunk_rows(n);
+  return (int)((n + c - 1) / c);
+}
+
+// keys [q][n] -> out (score, idx, count); `part` holds [q][n_chunks][k] pairs
+template <int MODE>
+static int select_keys32(const u32* keys, long long n, int q, int k, long long row_base, void* part,
+                         void* out_a, long long* out_idx, int* out_count, cudaStream_t st) {
+  const int n_chunks = select_n_chunks(n);
+  const long long chunk = select_chunk_rows(n);
+  const size_t e = (size_t)q * n_chunks * k;
+  u64* part_k1 = (u64*)part;
+  u32* part_k2 = (u32*)((char*)part + align_up(e * 8, 256));
+  const int cap = merge_cap(k);
+  dim3 grid(n_chunks, q);
+  select_keys32_chunk_kernel<<<grid, MERGE_THREADS, (size_t)cap * 12, st>>>(keys, n, chunk, n_chunks, k, cap,
+                                                                          part_k1, part_k2);
+  RR_LAUNCH_CHECK();
+  MergeArgs m;
+  m.k1 = part_k1;
+  m.k2 = part_k2;
+  m.n_in = (long long)n_chunks * k;
+  m.k = k;
+  m.cap = 0;
+  m.row_base = row_base;
+  m.out_a = out_a;
+  m.out_idx = out_idx;
+  m.out_count = out_count;
+  return launch_merge_pairs<MODE>(m, q, st);
+}
+
+template <int QT, int R>
+static int launch_exact_f32_vec(const ExactArgs& a, int grid_x, cudaStream_t st) {
+  const size_t smem = (size_t)QT * a.dim * 8;
+  RR_CUDA(cudaFuncSetAttribute(exact_f32_scores_vec_kernel<QT, R>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(grid_x, (a.q + QT - 1) / QT);
+  exact_f32_scores_vec_kernel<QT, R><<<grid, EX_THREADS, smem, st>>>(a);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
 }
 
 static int exact_grid_x(long long n) {
@@ -215,9 +396,9 @@ static int exact_grid_x(long long n) {
 using namespace rr;
 
 extern "C" size_t rr_exact_search_f32_workspace_bytes(int64_t n, int32_t q, int32_t k) {
-  (void)k;
-  if (n <= 0 || q <= 0) return 256;
-  return align_up((size_t)n * (size_t)q * 4, 256) + 256;
+  if (n <= 0 || q <= 0 || k <= 0) return 256;
+  const size_t e = (size_t)q * select_n_chunks(n) * k;
+  return align_up((size_t)n * (size_t)q * 4, 256) + align_up(e * 8, 256) + align_up(e * 4, 256) + 256;
 }
 
 extern "C" size_t rr_int8_search_topk_workspace_bytes(int64_t n, int32_t q, int32_t k) {
@@ -253,6 +434,7 @@ extern "C" int rr_exact_search_f32(const float* emb, int64_t n, int32_t dim, con
   RR_CHECK_ARG(top_k >= 1 && top_k <= RR_MAX_K, "top_k out of range");
   RR_CHECK_ARG(dim <= 4096, "dim > 4096 unsupported");
   RR_CHECK_ARG(n < (1LL << 32), "shard larger than 2^32 rows");
+  RR_CHECK_ARG(q <= 65535, "more than 65535 queries per call");
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
     const long long total = (long long)q * top_k;
@@ -268,17 +450,35 @@ extern "C" int rr_exact_search_f32(const float* emb, int64_t n, int32_t dim, con
     return RR_ERR_WORKSPACE;
   }
   ExactArgs a{emb, n, dim, tags, tag_mask, tag_value, queries, q, min_similarity, (u32*)workspace};
-  const size_t smem = (size_t)EX_QT * dim * 4;
-  RR_CUDA(cudaFuncSetAttribute(exact_f32_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                               (int)smem));
-  dim3 grid(exact_grid_x(n), (q + EX_QT - 1) / EX_QT);
-  exact_f32_scores_kernel<<<grid, EX_THREADS, smem, st>>>(a);
-  RR_LAUNCH_CHECK();
-  const int cap = merge_cap(top_k);
-  select_keys32_kernel<MERGE_F32_DESC><<<q, MERGE_THREADS, (size_t)cap * 12, st>>>(
-      (const u32*)workspace, n, top_k, cap, row_base, out_score, (long long*)out_idx, out_count);
-  RR_LAUNCH_CHECK();
-  return RR_OK;
+  const bool vec = (dim & 3) == 0 && (((uintptr_t)emb | (uintptr_t)queries) & 15) == 0;
+  // queries per pass: as many as the batch needs, while the float64 copy fits 96 KB
+  int qt = q >= 8 ? 8 : q >= 4 ? 4 : q >= 2 ? 2 : 1;
+  while (qt > 1 && (size_t)qt * dim * 8 > 96 * 1024) qt >>= 1;
+  if (vec && (size_t)qt * dim * 8 <= 96 * 1024) {
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int rc;
+    if (qt == 8) {
+      long long gx = (n / 2 + EX_WARPS - 1) / EX_WARPS;
+      rc = launch_exact_f32_vec<8, 2>(a, (int)max(1LL, min(gx, (long long)sms * 4)), st);
+    } else {
+      long long gx = (n / 4 + EX_WARPS - 1) / EX_WARPS;
+      const int g = (int)max(1LL, min(gx, (long long)sms * 4));
+      rc = qt == 4 ? launch_exact_f32_vec<4, 4>(a, g, st)
+           : qt == 2 ? launch_exact_f32_vec<2, 4>(a, g, st)
+                     : launch_exact_f32_vec<1, 4>(a, g, st);
+    }
+    if (rc != RR_OK) return rc;
+  } else {
+    const size_t smem = (size_t)EX_QT * dim * 4;
+    RR_CUDA(cudaFuncSetAttribute(exact_f32_scores_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    dim3 grid(exact_grid_x(n), (q + EX_QT - 1) / EX_QT);
+    exact_f32_scores_kernel<<<grid, EX_THREADS, smem, st>>>(a);
+    RR_LAUNCH_CHECK();
+  }
+  void* part = (char*)workspace + align_up((size_t)n * (size_t)q * 4, 256);
+  return select_keys32<MERGE_F32_DESC>((const u32*)workspace, n, q, top_k, row_base, part, out_score,
+                                       (long long*)out_idx, out_count, st);
 }
 
 extern "C" int rr_int8_search_topk(const int8_t* emb, int64_t n, int32_t dim, const uint8_t* tags,
@@ -293,6 +493,7 @@ extern "C" int rr_int8_search_topk(const int8_t* emb, int64_t n, int32_t dim, co
   RR_CHECK_ARG(top_k >= 1 && top_k <= RR_MAX_K, "top_k out of range");
   RR_CHECK_ARG(dim <= 16384, "dim > 16384 unsupported");
   RR_CHECK_ARG(n < (1LL << 32), "shard larger than 2^32 rows");
+  RR_CHECK_ARG(q <= 65535, "more than 65535 queries per call");
   cudaStream_t st = (cudaStream_t)stream;
   if (n == 0) {
     const long long total = (long long)q * top_k;
@@ -313,9 +514,7 @@ extern "C" int rr_int8_search_topk(const int8_t* emb, int64_t n, int32_t dim, co
   dim3 grid(exact_grid_x(n), (q + EX_QT - 1) / EX_QT);
   exact_i8_scores_kernel<<<grid, EX_THREADS, smem, st>>>(a);
   RR_LAUNCH_CHECK();
-  const int cap = merge_cap(top_k);
-  select_keys32_kernel<MERGE_I32_DESC><<<q, MERGE_THREADS, (size_t)cap * 12, st>>>(
-      (const u32*)workspace, n, top_k, cap, row_base, out_score, (long long*)out_idx, nullptr);
-  RR_LAUNCH_CHECK();
-  return RR_OK;
+  void* part = (char*)workspace + align_up((size_t)n * (size_t)q * 4, 256);
+  return select_keys32<MERGE_I32_DESC>((const u32*)workspace, n, q, top_k, row_base, part, out_score,
+                                       (long long*)out_idx, nullptr, st);
 }

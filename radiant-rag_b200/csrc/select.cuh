@@ -27,6 +27,8 @@ struct SelectScratch {
   int b_need;
   int b_ceq;
   int count;
+  u64 tmin[THREADS];  // per-thread minimum key1 (bound shortcut)
+  u32 tidx[THREADS];
 };
 
 // One radix pass worth of bucket search: warp 0 scans hist[256] for the bucket that
@@ -96,7 +98,13 @@ __device__ __forceinline__ void block_bitonic_sort_pairs(u64* s_k1, u32* s_k2, i
 // get(i, k1, k2) (k1 == K1_INVALID marks a hole) and leave them SORTED at
 // s_k1[0..ret), s_k2[0..ret).  `cap` is the capacity of s_k1/s_k2, a power of two
 // >= k.  All threads of the block must call this; returns the same value to all.
-template <int THREADS, class Get>
+//
+// TRY_BOUND (for keys with few ties and n >> k, e.g. float scores): the k-th smallest of
+// the per-thread minimum keys is the key of an element that has >= k elements at or
+// below it, so one compare-and-gather pass against it keeps ~k candidates and the radix
+// passes (whose shared-memory histogram serialises when keys share their high bytes)
+// are skipped.  If ties push the candidate count past `cap` the radix path runs as usual.
+template <int THREADS, bool TRY_BOUND = false, class Get>
 __device__ int block_select_sorted(Get get, long long n, int k, u64* s_k1, u32* s_k2, int cap,
                                    SelectScratch<THREADS>& sc) {
   const int tid = threadIdx.x;
@@ -105,6 +113,7 @@ __device__ int block_select_sorted(Get get, long long n, int k, u64* s_k1, u32* 
 
   // ---- pass 0: count valid, OR / AND of valid keys
   u64 vor = 0, vand = ~0ull;
+  u64 tmin = K1_INVALID;
   int vcnt = 0;
   for (long long i = tid; i < n; i += THREADS) {
     u64 a;
@@ -114,6 +123,7 @@ __device__ int block_select_sorted(Get get, long long n, int k, u64* s_k1, u32* 
       vor |= a;
       vand &= a;
       ++vcnt;
+      if (TRY_BOUND) tmin = a < tmin ? a : tmin;
     }
   }
 #pragma unroll
@@ -148,6 +158,44 @@ __device__ int block_select_sorted(Get get, long long n, int k, u64* s_k1, u32* 
   if (kk == 0) return 0;
   const u64 v_or = sc.b_or;
   const u64 diff = v_or ^ sc.b_and;
+
+  if (TRY_BOUND && valid > cap && k <= THREADS / 2) {
+    sc.tmin[tid] = tmin;
+    sc.tidx[tid] = (u32)tid;
+    __syncthreads();
+    block_bitonic_sort_pairs<THREADS>(sc.tmin, sc.tidx, THREADS);
+    const u64 bound = sc.tmin[kk - 1];
+    if (bound != K1_INVALID) {
+      for (long long i = tid; i < n; i += THREADS) {
+        u64 a;
+        u32 b;
+        get(i, a, b);
+        if (a <= bound) {
+          const int slot = atomicAdd(&sc.count, 1);
+          if (slot < cap) {
+            s_k1[slot] = a;
+            s_k2[slot] = b;
+          }
+        }
+      }
+      __syncthreads();
+      const int cnt = sc.count;
+      if (cnt <= cap) {
+        int p = 1;
+        while (p < cnt) p <<= 1;
+        for (int i = cnt + tid; i < p; i += THREADS) {
+          s_k1[i] = K1_INVALID;
+          s_k2[i] = K2_INVALID;
+        }
+        __syncthreads();
+        block_bitonic_sort_pairs<THREADS>(s_k1, s_k2, p);
+        return cnt < kk ? cnt : kk;
+      }
+      __syncthreads();
+      if (tid == 0) sc.count = 0;
+      __syncthreads();
+    }
+  }
 
   // ---- radix select on key1
   u64 prefix = 0, mask = 0;

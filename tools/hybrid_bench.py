@@ -6,6 +6,7 @@ Prints one JSON line with per-stage CUDA-event times and the hybrid queries/s, p
 float64 bit-exactness check of a sample of BM25 results against the NumPy oracle restricted
 to the documents returned (impacts recomputed on the host)."""
 import json
+import os
 import sys
 import time
 from pathlib import Path
@@ -54,7 +55,7 @@ def main():
     toks = torch.empty(total, dtype=torch.int32, device=dev)
     _lib.call("rr_synth_zipf_tokens", toks.data_ptr(), 0, total, seed, cdf_d.data_ptr(), v, _stream())
     avgdl = total / n_docs
-    bm = Bm25DeviceIndex.build(ptr, toks, v, None, avgdl, 1.5, 0.75, device=0, tile_docs=8192)
+    bm = Bm25DeviceIndex.build(ptr, toks, v, None, avgdl, 1.5, 0.75, device=0, tile_docs=int(os.environ.get('RR_BM25_TILE', '8192')))
     del toks
     build_s = time.time() - t0
     qt = torch.from_numpy(synthetic.zipf_queries(nq, qlen, v, seed)).to(dev)
@@ -105,9 +106,9 @@ def main():
             for j, r in enumerate(rows):
                 tile = r // bm.tile_docs
                 lo, hi = ttp[tile, t], ttp[tile, t + 1]
-                p = lo + np.searchsorted(post_rows[lo:hi], r)
-                if p < hi and post_rows[p] == r:
-                    want[j] += post_imp[p]
+                hit = np.nonzero(post_rows[lo:hi] == r)[0]  # segment order is bank-interleaved
+                if hit.size:
+                    want[j] += post_imp[lo + hit[0]]
         assert np.array_equal(want, b_score[qi, :m].cpu().numpy()), qi
         checked += m
     f_idx, f_score, f_count = out["fused"]
