@@ -452,8 +452,8 @@ extern "C" int rr_exact_search_f32(const float* emb, int64_t n, int32_t dim, con
   ExactArgs a{emb, n, dim, tags, tag_mask, tag_value, queries, q, min_similarity, (u32*)workspace};
   const bool vec = (dim & 3) == 0 && (((uintptr_t)emb | (uintptr_t)queries) & 15) == 0;
   // queries per pass: as many as the batch needs, while the float64 copy fits 96 KB
-  int qt = q >= 8 ? 8 : q >= 4 ? 4 : q >= 2 ? 2 : 1;
-  while (qt > 1 && (size_t)qt * dim * 8 > 96 * 1024) qt >>= 1;
+  int qt = q >= 8 ? 8 : q >= 2 ? 4 : 1;  // (a QT=2 build measured slower than QT=4 on B200)
+  while (qt > 1 && (size_t)qt * dim * 8 > 96 * 1024) qt = qt == 8 ? 4 : 1;
   if (vec && (size_t)qt * dim * 8 <= 96 * 1024) {
     const int sms = sm_count() > 0 ? sm_count() : 148;
     int rc;
@@ -463,9 +463,7 @@ extern "C" int rr_exact_search_f32(const float* emb, int64_t n, int32_t dim, con
     } else {
       long long gx = (n / 4 + EX_WARPS - 1) / EX_WARPS;
       const int g = (int)max(1LL, min(gx, (long long)sms * 4));
-      rc = qt == 4 ? launch_exact_f32_vec<4, 4>(a, g, st)
-           : qt == 2 ? launch_exact_f32_vec<2, 4>(a, g, st)
-                     : launch_exact_f32_vec<1, 4>(a, g, st);
+      rc = qt == 4 ? launch_exact_f32_vec<4, 4>(a, g, st) : launch_exact_f32_vec<1, 4>(a, g, st);
     }
     if (rc != RR_OK) return rc;
   } else {

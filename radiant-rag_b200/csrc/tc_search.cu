@@ -1,9 +1,9 @@
 // Tensor-core exact search: int8 x int8 -> int32 scores on tcgen05 with a fused filter
 // epilogue, for (a) BASELINE config 4 (exact int8 search, "tensor-core rescoring") and
-// (b) the BATCHED Hamming scan, where the packed sign bits are expanded to +-1 int8 operand
-// tiles IN SHARED MEMORY (HBM traffic stays at 1 bit per dimension) and
-// hamming = (D - dot) / 2  exactly (above ~3 queries per
-// pass the POPC pipe, not HBM, bounds the popcount formulation).
+// (b) the BATCHED Hamming scan, where the packed sign bits of the rows are expanded ON CHIP
+// to a 0 / 255 unsigned-int8 operand (HBM traffic stays at 1 bit per dimension), the
+// queries are +-1 int8, and  hamming = popc(q) - dot / 255  exactly (SURVEY.md section 7
+// H1b: above ~3 queries per pass the POPC pipe, not HBM, bounds the popcount formulation).
 //
 // Kernel (one CTA per SM, 320 threads, warp-specialised):
 //   warp 0      TMA producer: the CTA's 128 queries (B operand, K-major, SWIZZLE_128B) are
@@ -11,9 +11,9 @@
 //               128 rows x 128 bytes of K (A operand) stream through an mbarrier ring of TMA
 //               boxes.  Packed mode: each 128-row tile of packed codes is ONE contiguous
 //               bulk copy into a double buffer.
-//   warps 6-9   (packed mode) expand the tile's sign bits K block by K block into the A ring
-//               in the SWIZZLE_128B layout the UMMA descriptor expects (brev + multiply-spread,
-//               conflict-free 16-byte stores), fence.proxy.async, then signal the MMA warp.
+//   warps 6-9   (packed mode) expand the tile's sign bits K block by K block (multiply + PRMT
+//               sign-replicate, 5 instructions per 8 dims) and store them with tcgen05.st into an
+//               A-operand ring that lives in TENSOR MEMORY, then signal the MMA warp.
 //   warp 1      allocates TMEM and issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128,
 //               K=32 per instruction); two 128x128 int32 accumulators in TMEM are
 //               double-buffered against the epilogue.
@@ -30,6 +30,7 @@
 // A list that outgrows its capacity raises an overflow counter and the caller falls back
 // to the CUDA-core path (never observed on the synthetic corpora; guards adversarial data).
 #include <cuda.h>
+#include <math.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -42,7 +43,10 @@ constexpr int TC_BN = 128;          // queries per CTA (TMEM columns per accumul
 constexpr int TC_BK = 128;          // bytes of K per stage = one 128B swizzle atom row
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_UNPACK_GROUPS = 1;  // groups of 4 unpack warps; group g expands K blocks with it % 3 == g
-constexpr int TC_THREADS = 192 + 128 * TC_UNPACK_GROUPS;  // producer, MMA, 4 epilogue warps, unpack warps
+constexpr int TC_EPI_GROUPS = 2;     // groups of 4 epilogue warps; group h owns column chunks [2h, 2h+2)
+constexpr int TC_EPI_CHUNKS = TC_BN / 32 / TC_EPI_GROUPS;
+constexpr int TC_THREADS = 192 + 128 * TC_UNPACK_GROUPS + 128 * (TC_EPI_GROUPS - 1);  // producer, MMA, 4 epilogue,
+                                                                                   // unpack, 4 more epilogue warps
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK;  // 16 KB
 constexpr int TC_MAX_KB = 8;                  // dim <= 1024
 
@@ -66,6 +70,20 @@ __device__ __forceinline__ void tc_mbar_wait(u32 bar, u32 parity) {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
+}
+// for waiters that are far ahead of their partner (the copy producer): back off between
+// polls so the spin does not take issue slots from the warps sharing the scheduler
+__device__ __forceinline__ void tc_mbar_wait_backoff(u32 bar, u32 parity) {
+  u32 done;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    __nanosleep(200);
+  }
 }
 __device__ __forceinline__ void tc_tma_load_2d(u32 dst, const CUtensorMap* map, int c0, int c1, u32 bar) {
   asm volatile(
@@ -128,6 +146,8 @@ __device__ __forceinline__ u64 tc_smem_desc(u32 saddr) {
 // cute::UMMA::InstrDescriptor for kind::i8: D = S32, A = B = signed int8, both K-major,
 // N = 128 (>>3 at bit 17), M = 128 (>>4 at bit 24).
 constexpr u32 TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((u32)(TC_BN >> 3) << 17) | ((u32)(TC_BM >> 4) << 24);
+// packed mode: A = unsigned int8 (format 0), B = signed int8
+constexpr u32 TC_IDESC_UA = (2u << 4) | (0u << 7) | (1u << 10) | ((u32)(TC_BN >> 3) << 17) | ((u32)(TC_BM >> 4) << 24);
 
 struct TcArgs {
   long long n;          // corpus rows
@@ -151,17 +171,30 @@ struct TcArgs {
                         // 2 = MMA warp skips the MMAs, 4 = epilogue skips the TMEM reads (results are garbage)
 };
 
-// Expand 32 packed sign bits (np.packbits order: dim 8b is the MSB of byte b, bytes in
-// little-endian word order) to 32 int8 values +1 / -1, as eight 32-bit words.
+// Expand 32 packed sign bits (np.packbits order: dim 8b+j is bit 7-j of byte b, bytes in
+// little-endian word order) to 32 bytes 0xFF (bit set) / 0x00, as eight 32-bit words.
+// Per source byte: one multiply parks bits 7,6,5,4 (resp. 3,2,1,0) on the MSBs of the four
+// result bytes (the shifted copies b<<0,9,18,27 resp. b<<4,13,22,31 do not overlap), and PRMT
+// in sign-replicate mode turns each MSB into a whole byte: 5 instructions per 8 dims.
+// The MMA reads A as UNSIGNED int8, so a set bit is 255 and
+//   score = sum_i A_i * q_i = 255 * (#(a=1,q=1) - #(a=1,q=0)) = 255 * (popc(q) - hamming(a, q)).
+__device__ __forceinline__ u32 tc_prmt(u32 a, u32 b, u32 sel) {
+  u32 d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
 __device__ __forceinline__ void tc_expand32(u32 w, u32* out) {
-  const u32 x = __byte_perm(__brev(w), 0, 0x0123);  // bit d = dim d
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const u32 nib = (g == 7) ? (x >> 28) : ((x >> (4 * g)) & 0xFu);
-    const u32 t = (nib * 0x00204081u) & 0x01010101u;  // bit i of nib -> byte i (0 / 1)
-    out[g] = t * 0xFFFFFF02u + 0xFFFFFFFFu;           // per byte 0xFF - 0xFE * t: 1 -> +1, 0 -> -1
+  for (int k = 0; k < 4; ++k) {
+    const u32 b = (k == 3) ? (w >> 24) : tc_prmt(w, 0u, 0x4440u | (u32)k);  // byte k, zero-extended
+    out[2 * k] = tc_prmt(b * 0x08040201u, 0u, 0xBA98u);
+    out[2 * k + 1] = tc_prmt(b * 0x80402010u, 0u, 0xBA98u);
   }
 }
+// thresholds are clamped so that bias + score cannot wrap (|score| <= 127 * 127 * 1024 < 2^25);
+// INT_MIN ("keep everything") therefore becomes -2^30
+__host__ __device__ __forceinline__ int tc_tau_eff(int tau) { return tau < -(1 << 30) ? -(1 << 30) : tau; }
+constexpr int TC_PACKED_SCALE = 255;  // packed-mode score = 255 * (popc(q) - hamming)
 
 // Thread layout: warp 0 producer, warp 1 MMA, warps 2-5 epilogue, warps 6-9 unpackers (only
 // in packed mode, where the A operand is built in shared memory from packed sign bits).
@@ -201,7 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_mbar_init(tc_smem(b_full), 1);
     for (int s = 0; s < 2; ++s) {
       tc_mbar_init(tc_smem(tmem_full + s), 1);
-      tc_mbar_init(tc_smem(tmem_empty + s), 128);
+      tc_mbar_init(tc_smem(tmem_empty + s), 128 * TC_EPI_GROUPS);
       tc_mbar_init(tc_smem(pk_full + s), 1);
       tc_mbar_init(tc_smem(pk_empty + s), 128 * TC_UNPACK_GROUPS);
     }
@@ -215,7 +248,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp >= 2 && warp < 6) {
     const int t = threadIdx.x - 64;  // 0..127
     const int qq = q0 + t;
-    thr[t] = (a.tau != nullptr && qq < a.q) ? a.tau[qq] : (int)0x80000000;
+    // bias = -tau_eff: 0 in dense mode (plain scores), far negative for padding columns
+    thr[t] = a.dense ? 0 : (qq < a.q ? -tc_tau_eff(a.tau[qq]) : -(1 << 30));
     s_cnt[t] = 0;
   }
   tc_fence_before();
@@ -246,7 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
           const long long row0 = i * a.tile_stride * TC_BM;
           const u32 slot = tcount & 1u;
-          tc_mbar_wait(tc_smem(pk_empty + slot), ((tcount >> 1) & 1u) ^ 1u);
+          tc_mbar_wait_backoff(tc_smem(pk_empty + slot), ((tcount >> 1) & 1u) ^ 1u);
           long long rows = a.n - row0;
           if (rows > TC_BM) rows = TC_BM;
           const u32 bytes = (u32)(rows * row_bytes);
@@ -268,7 +302,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     u32 stage = 0, phase = 0, tcount = 0;
     for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
       const u32 as = tcount & 1u;
-      tc_mbar_wait(tc_smem(tmem_empty + as), ((tcount >> 1) & 1u) ^ 1u);
+      tc_mbar_wait(tc_smem(tmem_empty + as), (tcount >> 1) & 1u);  // read by the epilogue and re-biased
       tc_fence_after();
       const u32 d_tmem = tmem_base + as * TC_BN;
       if (a.packed) {
@@ -278,10 +312,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const u32 a_tmem = tmem_base + 2 * TC_BN + stage * 32;  // A ring in tensor memory
           const u64 bd = bdesc0 + (u64)(kb * (TC_TILE_BYTES >> 4));
           if (!(a.debug & 2)) {
-            tc_mma_i8_ts_elect(d_tmem, a_tmem, bd, TC_IDESC, kb != 0 ? 1u : 0u);
-            tc_mma_i8_ts_elect(d_tmem, a_tmem + 8, bd + 2, TC_IDESC, 1u);
-            tc_mma_i8_ts_elect(d_tmem, a_tmem + 16, bd + 4, TC_IDESC, 1u);
-            tc_mma_i8_ts_elect(d_tmem, a_tmem + 24, bd + 6, TC_IDESC, 1u);
+            tc_mma_i8_ts_elect(d_tmem, a_tmem, bd, TC_IDESC_UA, 1u);
+            tc_mma_i8_ts_elect(d_tmem, a_tmem + 8, bd + 2, TC_IDESC_UA, 1u);
+            tc_mma_i8_ts_elect(d_tmem, a_tmem + 16, bd + 4, TC_IDESC_UA, 1u);
+            tc_mma_i8_ts_elect(d_tmem, a_tmem + 24, bd + 6, TC_IDESC_UA, 1u);
           }
           tc_commit_elect(empty0 + stage * 8);  // frees the A stage when these MMAs have read it
           if (++stage == stages) {
@@ -295,7 +329,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tc_fence_after();
           const u64 ad = adesc0 + (u64)(stage * (TC_TILE_BYTES >> 4));
           const u64 bd = bdesc0 + (u64)(kb * (TC_TILE_BYTES >> 4));
-          tc_mma_i8_ss_elect(d_tmem, ad, bd, TC_IDESC, kb != 0 ? 1u : 0u);
+          tc_mma_i8_ss_elect(d_tmem, ad, bd, TC_IDESC, 1u);
           tc_mma_i8_ss_elect(d_tmem, ad + 2, bd + 2, TC_IDESC, 1u);
           tc_mma_i8_ss_elect(d_tmem, ad + 4, bd + 4, TC_IDESC, 1u);
           tc_mma_i8_ss_elect(d_tmem, ad + 6, bd + 6, TC_IDESC, 1u);
@@ -308,9 +342,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       tc_commit_elect(tc_smem(tmem_full + as));  // accumulator complete
     }
-  } else if (warp < 6) {
-    // ===================== epilogue (warps 2..5) =====================
+  } else if (warp < 6 || warp >= 6 + 4 * TC_UNPACK_GROUPS) {
+    // ===================== epilogue (warps 2..5 and the last four) =====================
+    // Two warps share a TMEM lane quarter and split the 128 query columns between them: a
+    // single warp's dependent-issue latency is what paces this role.
+    // Filter mode keeps the compare out of the instruction stream: the accumulator of query
+    // column j starts at -tau_j instead of 0 (the epilogue warps write that bias into tensor
+    // memory with tcgen05.st right after they have read a tile, the MMAs always accumulate),
+    // so "score >= tau" is the sign bit of the accumulator and a funnel shift per column
+    // collects the hit mask.  The 128 biases live in registers for the whole kernel.
     const int lq = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    const int half = warp < 6 ? 0 : 1;
+    const int c0 = half * TC_EPI_CHUNKS;  // first column chunk of this warp
+    u32 bias[TC_EPI_CHUNKS * 32];
+#pragma unroll
+    for (int j4 = 0; j4 < TC_EPI_CHUNKS * 8; ++j4) {
+      const int4 tv = reinterpret_cast<const int4*>(thr + c0 * 32)[j4];  // thr[] holds the biases
+      bias[4 * j4 + 0] = (u32)tv.x;
+      bias[4 * j4 + 1] = (u32)tv.y;
+      bias[4 * j4 + 2] = (u32)tv.z;
+      bias[4 * j4 + 3] = (u32)tv.w;
+    }
+    auto store_bias = [&](u32 as) {
+#pragma unroll
+      for (int cc = 0; cc < TC_EPI_CHUNKS; ++cc) {
+        const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + as * TC_BN + (c0 + cc) * 32;
+        const u32* o = bias + cc * 32;
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+            ::"r"(taddr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]),
+              "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]),
+              "r"(o[16]), "r"(o[17]), "r"(o[18]), "r"(o[19]), "r"(o[20]), "r"(o[21]), "r"(o[22]), "r"(o[23]),
+              "r"(o[24]), "r"(o[25]), "r"(o[26]), "r"(o[27]), "r"(o[28]), "r"(o[29]), "r"(o[30]), "r"(o[31])
+            : "memory");
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    };
+    // both accumulators start biased; each arrival below is "read and re-biased"
+    for (u32 as = 0; as < 2; ++as) {
+      store_bias(as);
+      tc_fence_before();
+      tc_mbar_arrive(tc_smem(tmem_empty + as));
+    }
     u32 tcount = 0;
     for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
       const u32 as = tcount & 1u;
@@ -321,70 +396,77 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (valid && a.tags != nullptr) valid = ((unsigned)a.tags[row] & a.tag_mask) == a.tag_value;
       const long long dense_col = i * TC_BM + lq * 32 + lane;  // position among the launched rows
       const long long dense_ld = a.n_tiles * TC_BM;
-#pragma unroll 1
-      for (int c = 0; c < ((a.debug & 4) ? 0 : TC_BN / 32); ++c) {
-        u32 v[32];
-        const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + as * TC_BN + c * 32;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (a.dense) {
+      if (!(a.debug & 4)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int qq = q0 + c * 32 + j;
-            if (qq < a.q)
-              a.dense_keys[(size_t)qq * dense_ld + dense_col] = valid ? ~i32_orderable((int)v[j]) : 0xFFFFFFFFu;
-          }
-        } else {
-          // thresholds of this chunk to registers first (vector loads), so the compare chain
-          // is not serialised behind the shared-memory counter updates
-          int t[32];
+        for (int cc = 0; cc < TC_EPI_CHUNKS; ++cc) {
+          const int c = c0 + cc;
+          u32 v[32];
+          const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + as * TC_BN + c * 32;
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+              : "r"(taddr) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (a.dense) {
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const int4 tv = reinterpret_cast<const int4*>(thr + c * 32)[j4];
-            t[4 * j4 + 0] = tv.x;
-            t[4 * j4 + 1] = tv.y;
-            t[4 * j4 + 2] = tv.z;
-            t[4 * j4 + 3] = tv.w;
-          }
-          const int qlim = a.q - (q0 + c * 32);  // columns >= qlim are padding
-          u32 hit = 0;
+            for (int j = 0; j < 32; ++j) {
+              const int qq = q0 + c * 32 + j;
+              if (qq < a.q)
+                a.dense_keys[(size_t)qq * dense_ld + dense_col] = valid ? ~i32_orderable((int)v[j]) : 0xFFFFFFFFu;
+            }
+          } else {
+            // four independent funnel-shift chains (one warp runs the epilogue of its lane
+            // quarter alone, so dependent-issue latency, not throughput, is what it pays):
+            // bit 7-i of m[g] = sign of column 8g+i (1 = below the bound)
+            u32 m[4] = {0, 0, 0, 0};
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if ((int)v[j] >= t[j] && j < qlim) hit |= 1u << j;
-          if (!valid) hit = 0;
-          while (hit) {  // rare: about k * 32 rows per query reach the sampled bound
-            const int j = __ffs(hit) - 1;
-            hit &= hit - 1;
-            int s = 0;
+            for (int jj = 0; jj < 8; ++jj) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj)
-              if (jj == j) s = (int)v[jj];
-            const u32 slot = atomicAdd(s_cnt + c * 32 + j, 1u);  // shared-memory counter
-            if (slot < (u32)a.cap_cta) {
-              const size_t o = ((size_t)(q0 + c * 32 + j) * gridDim.x + blockIdx.x) * a.cap_cta + slot;
-              a.list_score[o] = s;
-              a.list_row[o] = (u32)row;
+              for (int g = 0; g < 4; ++g) m[g] = __funnelshift_l(v[8 * g + jj], m[g], 1);
+            }
+            // byte g of `miss` = m[g]; hit bit 8g + (7-i) <-> column 8g + i
+            const u32 miss = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
+            u32 hit = valid ? ~miss : 0u;
+            while (hit) {  // rare: about k * stride rows per query reach the sampled bound
+              const int b = __ffs(hit) - 1;
+              hit &= hit - 1;
+              const int j = (b & 24) | (7 - (b & 7));
+              // 5-level select tree instead of a 32-long dependent chain
+              u32 t16[16], t8[8], t4[4], t2[2];
+#pragma unroll
+              for (int x = 0; x < 16; ++x) t16[x] = (j & 1) ? v[2 * x + 1] : v[2 * x];
+#pragma unroll
+              for (int x = 0; x < 8; ++x) t8[x] = (j & 2) ? t16[2 * x + 1] : t16[2 * x];
+#pragma unroll
+              for (int x = 0; x < 4; ++x) t4[x] = (j & 4) ? t8[2 * x + 1] : t8[2 * x];
+#pragma unroll
+              for (int x = 0; x < 2; ++x) t2[x] = (j & 8) ? t4[2 * x + 1] : t4[2 * x];
+              const int s = (int)((j & 16) ? t2[1] : t2[0]);
+              const u32 slot = atomicAdd(s_cnt + c * 32 + j, 1u);  // shared-memory counter
+              if (slot < (u32)a.cap_cta) {
+                const size_t o = ((size_t)(q0 + c * 32 + j) * gridDim.x + blockIdx.x) * a.cap_cta + slot;
+                a.list_score[o] = s;  // biased: score - tau_eff (tc_select_lists adds it back)
+                a.list_row[o] = (u32)row;
+              }
             }
           }
         }
       }
+      store_bias(as);
       tc_fence_before();
       tc_mbar_arrive(tc_smem(tmem_empty + as));
     }
     if (!a.dense) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");  // the epilogue warps only
       const int t = threadIdx.x - 64;
-      if (q0 + t < a.q) a.cnt[(size_t)(q0 + t) * gridDim.x + blockIdx.x] = s_cnt[t];
+      if (t < TC_BN && q0 + t < a.q) a.cnt[(size_t)(q0 + t) * gridDim.x + blockIdx.x] = s_cnt[t];
     }
-  } else if (a.packed) {
+  } else if (a.packed && warp < 6 + 4 * TC_UNPACK_GROUPS) {
     // ===================== unpackers (warps 6..9): packed bits -> +-1 int8 rows in TENSOR MEMORY =====================
     // The A operand never touches shared memory: each thread expands the 128 dims of ITS row
     // for one K block into 32 registers and stores them to its TMEM lane (tcgen05.st), so
@@ -529,17 +611,26 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const u32* keys, lo
 
 // exact top-k of each query's filtered list segments, (score desc, row asc)
 constexpr int LIST_THREADS = 1024;
-template <int MODE>  // MERGE_I32_DESC: scores as is; MERGE_HAMMING: dist = (dim - score) / 2
+template <int MODE>  // MERGE_I32_DESC: scores as is; MERGE_HAMMING: dist = popc(q) - score / 255
 __global__ void __launch_bounds__(LIST_THREADS)
     tc_select_lists_kernel(const u32* cnt, const int* list_score, const u32* list_row, int n_cta, int cap_cta,
-                           int k, int kcap, int dim, long long row_base, void* out_a, long long* out_idx,
-                           int* out_count, unsigned* overflow) {
+                           int k, int kcap, int dim, const int8_t* q_pm1, const int* tau, long long row_base,
+                           void* out_a, long long* out_idx, int* out_count, unsigned* overflow) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
   u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
   u32* s_k2 = reinterpret_cast<u32*>(s_k1 + kcap);
   __shared__ SelectScratch<LIST_THREADS> sc;
   __shared__ u32 s_seg[256];  // n_cta <= 148
+  __shared__ int s_qpop;
   const int q = blockIdx.x;
+  if (MODE == MERGE_HAMMING) {
+    if (threadIdx.x == 0) s_qpop = 0;
+    __syncthreads();
+    int c = 0;
+    for (int d = threadIdx.x; d < dim; d += LIST_THREADS) c += q_pm1[(size_t)q * dim + d] > 0;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_qpop, c);
+  }
   for (int i = threadIdx.x; i < n_cta; i += LIST_THREADS) {
     const u32 c = cnt[(size_t)q * n_cta + i];
     if (c > (u32)cap_cta) atomicAdd(overflow, 1u);
@@ -563,8 +654,8 @@ __global__ void __launch_bounds__(LIST_THREADS)
   for (int j = threadIdx.x; j < k; j += LIST_THREADS) {
     const size_t o = (size_t)q * k + j;
     if (j < m) {
-      const int s = i32_from_orderable((u32)(~s_k1[j]));
-      reinterpret_cast<int*>(out_a)[o] = (MODE == MERGE_HAMMING) ? (dim - s) / 2 : s;
+      const int s = i32_from_orderable((u32)(~s_k1[j])) + tc_tau_eff(tau[q]);  // lists hold score - tau_eff
+      reinterpret_cast<int*>(out_a)[o] = (MODE == MERGE_HAMMING) ? s_qpop - s / TC_PACKED_SCALE : s;
       out_idx[o] = (long long)s_k2[j] + row_base;
     } else {
       reinterpret_cast<int*>(out_a)[o] = (MODE == MERGE_HAMMING) ? 0x7fffffff : (int)0x80000000;
@@ -632,10 +723,21 @@ static int make_map(CUtensorMap* map, const void* ptr, long long rows, int dim) 
   return RR_OK;
 }
 
-constexpr int TC_SAMPLE_STRIDE = 32;  // pass 0 scores every 32nd row tile
+// Pass 0 scores every `stride`-th row tile.  Sampling costs ~ n / stride, the rows that later
+// reach the sampled bound (list appends + final select) cost ~ stride * k per query, so the
+// optimum grows like sqrt(n / k); the constant is fitted on B200 (profiles/).
+static int tc_sample_stride(long long n, int k) {
+  const char* e = getenv("RR_TC_STRIDE");  // experiments only
+  if (e && atoi(e) > 0) return atoi(e);
+  const double want = 0.2 * sqrt((double)n / (double)k);
+  int s = 4;
+  while (s < 128 && (double)s * 1.4142 < want) s <<= 1;
+  return s;
+}
 
 struct TcPlan {
   long long tiles, sample_tiles;
+  int stride;
   int qblocks, ctas_x, cap_cta;
   size_t off_keys, off_sscore, off_sidx, off_scount, off_tau, off_cnt, off_ls, off_lr, total;
 };
@@ -643,7 +745,8 @@ struct TcPlan {
 static TcPlan tc_plan(long long n, int q, int k) {
   TcPlan p;
   p.tiles = (n + TC_BM - 1) / TC_BM;
-  p.sample_tiles = (p.tiles + TC_SAMPLE_STRIDE - 1) / TC_SAMPLE_STRIDE;
+  p.stride = tc_sample_stride(n, k);
+  p.sample_tiles = (p.tiles + p.stride - 1) / p.stride;
   // the sample must be able to hold k rows; tiny corpora are sampled completely
   if (p.sample_tiles * TC_BM < 4LL * k || p.sample_tiles * TC_BM < 2048) p.sample_tiles = p.tiles;
   p.qblocks = (q + TC_BN - 1) / TC_BN;
@@ -748,7 +851,7 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
 
   // ---- pass 0: dense scores of a strided sample of row tiles -> tau
   const bool full_sample = p.sample_tiles == p.tiles;
-  a.tile_stride = full_sample ? 1 : TC_SAMPLE_STRIDE;
+  a.tile_stride = full_sample ? 1 : p.stride;
   a.n_tiles = p.sample_tiles;
   a.tau = nullptr;
   a.dense = 1;
@@ -774,12 +877,12 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   // ---- pass 2: exact top-k of each query's list segments
   if (hamming)
     tc_select_lists_kernel<MERGE_HAMMING><<<q, LIST_THREADS, (size_t)kcap * 12, st>>>(
-        a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, row_base, out_a, out_idx, nullptr,
-        overflow_out);
+        a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, queries, (const int*)(w + p.off_tau), row_base, out_a,
+        out_idx, nullptr, overflow_out);
   else
     tc_select_lists_kernel<MERGE_I32_DESC><<<q, LIST_THREADS, (size_t)kcap * 12, st>>>(
-        a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, row_base, out_a, out_idx, nullptr,
-        overflow_out);
+        a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, queries, (const int*)(w + p.off_tau), row_base, out_a,
+        out_idx, nullptr, overflow_out);
   RR_LAUNCH_CHECK();
   return RR_OK;
 }
