@@ -42,8 +42,14 @@ constexpr int TC_BM = 128;          // corpus rows per MMA tile (TMEM lanes)
 constexpr int TC_BN = 128;          // queries per CTA (TMEM columns per accumulator)
 constexpr int TC_BK = 128;          // bytes of K per stage = one 128B swizzle atom row
 constexpr int TC_MAX_STAGES = 8;
-constexpr int TC_UNPACK_GROUPS = 1;  // groups of 4 unpack warps; group g expands K blocks with it % 3 == g
-constexpr int TC_EPI_GROUPS = 2;     // groups of 4 epilogue warps; group h owns column chunks [2h, 2h+2)
+#ifndef RR_TC_EPI_GROUPS
+#define RR_TC_EPI_GROUPS 2
+#endif
+#ifndef RR_TC_UNPACK_GROUPS
+#define RR_TC_UNPACK_GROUPS 1
+#endif
+constexpr int TC_UNPACK_GROUPS = RR_TC_UNPACK_GROUPS;  // groups of 4 unpack warps; group g expands the K blocks with it % groups == g
+constexpr int TC_EPI_GROUPS = RR_TC_EPI_GROUPS;     // groups of 4 epilogue warps; group h owns column chunks [2h, 2h+2)
 constexpr int TC_EPI_CHUNKS = TC_BN / 32 / TC_EPI_GROUPS;
 constexpr int TC_THREADS = 192 + 128 * TC_UNPACK_GROUPS + 128 * (TC_EPI_GROUPS - 1);  // producer, MMA, 4 epilogue,
                                                                                    // unpack, 4 more epilogue warps
@@ -350,24 +356,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // column j starts at -tau_j instead of 0 (the epilogue warps write that bias into tensor
     // memory with tcgen05.st right after they have read a tile, the MMAs always accumulate),
     // so "score >= tau" is the sign bit of the accumulator and a funnel shift per column
-    // collects the hit mask.  The 128 biases live in registers for the whole kernel.
+    // collects the hit mask.
     const int lq = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
-    const int half = warp < 6 ? 0 : 1;
+    const int half = warp < 6 ? 0 : 1 + (warp - (6 + 4 * TC_UNPACK_GROUPS)) / 4;
     const int c0 = half * TC_EPI_CHUNKS;  // first column chunk of this warp
-    u32 bias[TC_EPI_CHUNKS * 32];
-#pragma unroll
-    for (int j4 = 0; j4 < TC_EPI_CHUNKS * 8; ++j4) {
-      const int4 tv = reinterpret_cast<const int4*>(thr + c0 * 32)[j4];  // thr[] holds the biases
-      bias[4 * j4 + 0] = (u32)tv.x;
-      bias[4 * j4 + 1] = (u32)tv.y;
-      bias[4 * j4 + 2] = (u32)tv.z;
-      bias[4 * j4 + 3] = (u32)tv.w;
-    }
+    // (the biases are re-read from shared memory for every store: this role has slack, and
+    // keeping them out of registers lets the kernel run more unpack warps)
     auto store_bias = [&](u32 as) {
 #pragma unroll
       for (int cc = 0; cc < TC_EPI_CHUNKS; ++cc) {
         const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + as * TC_BN + (c0 + cc) * 32;
-        const u32* o = bias + cc * 32;
+        u32 o[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int4 tv = reinterpret_cast<const int4*>(thr + (c0 + cc) * 32)[j4];  // thr[] holds the biases
+          o[4 * j4 + 0] = (u32)tv.x;
+          o[4 * j4 + 1] = (u32)tv.y;
+          o[4 * j4 + 2] = (u32)tv.z;
+          o[4 * j4 + 3] = (u32)tv.w;
+        }
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
             "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -475,7 +482,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int u = lq * 32 + lane;     // row of the tile = TMEM lane
     const u32 group = (u32)(warp - 6) >> 2;  // several warps per quarter take turns on the K blocks,
                                              // so one warp's expand latency hides behind the others
+    // The hand-off of K block i (wait for the store, signal the MMA warp) is issued after K
+    // block i+1 has been expanded, so the tensor-memory store is in flight during the
+    // expansion instead of stalling the warp.
     u32 it = 0, tcount = 0, stage = 0, phase = 0;
+    bool pending = false;
+    u32 pending_bar = 0;
     for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
       const u32 slot = tcount & 1u;
       tc_mbar_wait(tc_smem(pk_full + slot), (tcount >> 1) & 1u);
@@ -499,6 +511,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_expand32(pw.y, o + 8);
         tc_expand32(pw.z, o + 16);
         tc_expand32(pw.w, o + 24);
+        if (pending) {
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          tc_mbar_arrive(pending_bar);
+        }
         tc_mbar_wait(tc_smem(empty_a + s), ph ^ 1u);
         tc_fence_after();
         const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + 2 * TC_BN + s * 32;
@@ -511,11 +528,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               "r"(o[16]), "r"(o[17]), "r"(o[18]), "r"(o[19]), "r"(o[20]), "r"(o[21]), "r"(o[22]), "r"(o[23]),
               "r"(o[24]), "r"(o[25]), "r"(o[26]), "r"(o[27]), "r"(o[28]), "r"(o[29]), "r"(o[30]), "r"(o[31])
             : "memory");
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        tc_mbar_arrive(tc_smem(full_a + s));
+        pending = true;
+        pending_bar = tc_smem(full_a + s);
       }
       tc_mbar_arrive(tc_smem(pk_empty + slot));
+    }
+    if (pending) {
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      tc_mbar_arrive(pending_bar);
     }
   }
 
