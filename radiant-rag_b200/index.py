@@ -287,21 +287,33 @@ class DenseIndex:
         (adversarial data) the call is redone on the POPC path.  check_overflow=False skips
         that host-side check (one device sync) and accumulates the counter in
         ``tc_overflow_total()`` for the caller to verify later."""
+        dist, idx, ovf = self._hamming_topk_auto(qcodes, k, tag_mask, tag_value, use_tc)
+        if ovf is None:
+            return dist, idx
+        if check_overflow:
+            if int(ovf.item()) != 0:
+                return self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
+        else:
+            self._defer_overflow(ovf)
+        return dist, idx
+
+    def _hamming_topk_auto(self, qcodes: torch.Tensor, k: int, tag_mask: int, tag_value: int,
+                           use_tc: Optional[bool] = None):
+        """-> (dist, idx, ovf): ovf is the device overflow counter of a tensor-core call, None
+        when the POPC path ran (always exact)."""
         self._activate()
         q = qcodes.shape[0]
         if use_tc is None:
             use_tc = self.use_tensor_cores and q >= self.tc_min_queries and self.n >= 4096
         if not use_tc or self.n == 0:
-            return self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
-        dist, idx, ovf = self._hamming_topk_tc(qcodes, k, tag_mask, tag_value)
-        if check_overflow:
-            if int(ovf.item()) != 0:
-                return self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
-        else:
-            if self._tc_overflow is None:
-                self._tc_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self._tc_overflow += ovf
-        return dist, idx
+            dist, idx = self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
+            return dist, idx, None
+        return self._hamming_topk_tc(qcodes, k, tag_mask, tag_value)
+
+    def _defer_overflow(self, ovf: torch.Tensor) -> None:
+        if self._tc_overflow is None:
+            self._tc_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._tc_overflow += ovf
 
     def tc_overflow_total(self) -> int:
         """Overflow events of tensor-core calls made with check_overflow=False (0 = all exact)."""
@@ -375,14 +387,29 @@ class DenseIndex:
         qf, qc = self.quantize_queries(queries)
         candidate_k = int(top_k * rescore_multiplier) if use_rescoring else top_k
         candidate_k = max(1, min(candidate_k, _lib.RR_MAX_K))
-        _dist, cand = self.hamming_topk(qc, candidate_k, tag_mask, tag_value, check_overflow=check_overflow)
-        if not use_rescoring:
-            idx = cand[:, :top_k].contiguous()
-            score = torch.ones(idx.shape, dtype=torch.float32, device=self.device)
-            count = (idx >= 0).sum(dim=1).to(torch.int32)
+        # Stage 2 is queued behind stage 1 before the tensor-core overflow counter is read, so
+        # the (single) host sync of a checked call sits at its end and the GPU never idles
+        # between the stages; an overflow (adversarial data) redoes the call on the POPC path.
+        _dist, cand, ovf = self._hamming_topk_auto(qc, candidate_k, tag_mask, tag_value)
+
+        def stage2(cand_rows):
+            if not use_rescoring:
+                idx = cand_rows[:, :top_k].contiguous()
+                score = torch.ones(idx.shape, dtype=torch.float32, device=self.device)
+                count = (idx >= 0).sum(dim=1).to(torch.int32)
+                return idx, score, count
+            score, idx, count = self.rescore(qf, cand_rows, top_k, min_similarity, prefer_int8)
             return idx, score, count
-        score, idx, count = self.rescore(qf, cand, top_k, min_similarity, prefer_int8)
-        return idx, score, count
+
+        out = stage2(cand)
+        if ovf is not None:
+            if check_overflow:
+                if int(ovf.item()) != 0:
+                    _dist, cand = self._hamming_topk_popc(qc, candidate_k, tag_mask, tag_value)
+                    out = stage2(cand)
+            else:
+                self._defer_overflow(ovf)
+        return out
 
     def search_exact(self, queries: ArrayLike, top_k: int, min_similarity: float = 0.0,
                      tag_mask: int = 0, tag_value: int = 0

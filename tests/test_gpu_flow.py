@@ -239,3 +239,22 @@ def test_row_sharded_emulated_on_one_gpu():
         rows, sc = orc.search(qt[qi].tolist(), k)
         m = int(m_count[qi])
         assert m_idx[qi, :m].cpu().tolist() == rows.tolist() and m_score[qi, :m].cpu().tolist() == sc.tolist()
+
+
+def test_graph_replay_equals_eager_search():
+    """A captured search step replays to exactly the eager results, for new queries too."""
+    require_gpu()
+    from radiant_rag_b200.graphed import GraphedSearch
+    n, dim, nq, top_k = 20_000, 768, 32, 10
+    corpus = synthetic.hash_rows_f32(0, n, dim, seed=77)
+    index, _ranges = build_index(corpus, int8=True, f32=False)
+    graph = GraphedSearch(lambda q: index.search_quantized(q, top_k, 4.0, check_overflow=False), nq, dim, "cuda:0")
+    assert graph.kernels_per_replay > 0
+    for seed in (1, 2):
+        queries = synthetic.hash_query_rows_f32(0, nq, dim, seed=seed, n_corpus=n)
+        want = index.search_quantized(queries, top_k, 4.0)
+        got = graph(torch.from_numpy(queries).pin_memory())
+        torch.cuda.synchronize()
+        for g, w in zip(got, want):
+            assert torch.equal(g, w)
+    assert index.tc_overflow_total() == 0
