@@ -229,8 +229,11 @@ def run_gpu_arm(args) -> None:
     # that the host issue time of a step does not bound a sub-millisecond GPU step.
     graphed = None
     if not args.no_graph:
-        from radiant_rag_b200.graphed import GraphedSearch
-        graphed = GraphedSearch(search_step, nq, dim, dev)
+        from radiant_rag_b200.graphed import GraphedSearch, GraphedShardedSearch
+        if world > 1:  # compute segments as graphs, the NCCL exchanges eagerly between them
+            graphed = GraphedShardedSearch(search, nq, dim, top_k, rescore_multiplier=mult, prefer_int8=False)
+        else:
+            graphed = GraphedSearch(search_step, nq, dim, dev)
         graphed.load(queries_dev)
         torch.cuda.synchronize()
 
@@ -402,7 +405,7 @@ def run_gpu_arm(args) -> None:
         "config": {"workload": WORKLOAD, "corpus_rows": n, "dim": dim, "batch_queries": nq, "candidates": cand_k,
                    "top_k": top_k, "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}",
                    "l2": "flushed between timed iterations (256 MB fill)",
-                   "issue": "eager launches" if graphed is None else "CUDA graph replay of the step"},
+                   "issue": "eager launches" if graphed is None else ("CUDA graph replay of the step" if world == 1 else "3 CUDA graphs per step with eager NCCL exchanges between them")},
         "e2e": {"value": nq / (e2e_ms_per_step * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms_per_step,
                 "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * top_k * 12 + nq * 4},
         "gpu_launches": launches_per_step * args.steps,

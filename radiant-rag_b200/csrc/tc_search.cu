@@ -204,6 +204,10 @@ constexpr int TC_PACKED_SCALE = 255;  // packed-mode score = 255 * (popc(q) - ha
 
 // Thread layout: warp 0 producer, warp 1 MMA, warps 2-5 epilogue, warps 6-9 unpackers (only
 // in packed mode, where the A operand is built in shared memory from packed sign bits).
+// EPI: 0 = filter pass (lists), 1 = dense keys of every launched row (tests / debug),
+//      2 = sample pass: per (CTA, row slot) maximum over the CTA's tiles, one key per slot.
+constexpr int EPI_FILTER = 0, EPI_DENSE = 1, EPI_COLMAX = 2;
+template <int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     tc_i8_search_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                         const TcArgs a) {
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const int t = threadIdx.x - 64;  // 0..127
     const int qq = q0 + t;
     // bias = -tau_eff: 0 in dense mode (plain scores), far negative for padding columns
-    thr[t] = a.dense ? 0 : (qq < a.q ? -tc_tau_eff(a.tau[qq]) : -(1 << 30));
+    thr[t] = EPI != EPI_FILTER ? 0 : (qq < a.q ? -tc_tau_eff(a.tau[qq]) : -(1 << 30));
     s_cnt[t] = 0;
   }
   tc_fence_before();
@@ -393,6 +397,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_before();
       tc_mbar_arrive(tc_smem(tmem_empty + as));
     }
+    // sample pass: best score seen by this thread's row slot, per query column (a slot sees one
+    // row of every tile the CTA takes, so the slots partition the sampled rows)
+    int colmax[EPI == EPI_COLMAX ? TC_EPI_CHUNKS * 32 : 1];
+#pragma unroll
+    for (int j = 0; j < (EPI == EPI_COLMAX ? TC_EPI_CHUNKS * 32 : 1); ++j) colmax[j] = (int)0x80000000;
     u32 tcount = 0;
     for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
       const u32 as = tcount & 1u;
@@ -419,12 +428,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
                 "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
               : "r"(taddr) : "memory");
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (a.dense) {
+          if (EPI == EPI_DENSE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int qq = q0 + c * 32 + j;
               if (qq < a.q)
                 a.dense_keys[(size_t)qq * dense_ld + dense_col] = valid ? ~i32_orderable((int)v[j]) : 0xFFFFFFFFu;
+            }
+          } else if (EPI == EPI_COLMAX) {
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) colmax[cc * 32 + j] = max(colmax[cc * 32 + j], (int)v[j]);
             }
           } else {
             // four independent funnel-shift chains (one warp runs the epilogue of its lane
@@ -468,7 +482,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_before();
       tc_mbar_arrive(tc_smem(tmem_empty + as));
     }
-    if (!a.dense) {
+    if (EPI == EPI_COLMAX) {
+      const size_t ld = (size_t)gridDim.x * TC_BM;
+#pragma unroll
+      for (int cc = 0; cc < TC_EPI_CHUNKS; ++cc) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int qq = q0 + (c0 + cc) * 32 + j;
+          const int mx = colmax[cc * 32 + j];
+          if (qq < a.q)
+            a.dense_keys[(size_t)qq * ld + (size_t)blockIdx.x * TC_BM + lq * 32 + lane] =
+                mx == (int)0x80000000 ? 0xFFFFFFFFu : ~i32_orderable(mx);
+        }
+      }
+    }
+    if (EPI == EPI_FILTER) {
       asm volatile("bar.sync 1, %0;" ::"n"(128 * TC_EPI_GROUPS) : "memory");  // the epilogue warps only
       const int t = threadIdx.x - 64;
       if (t < TC_BN && q0 + t < a.q) a.cnt[(size_t)(q0 + t) * gridDim.x + blockIdx.x] = s_cnt[t];
@@ -548,9 +576,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   }
 }
 
-// tau_q = k-th best sample score (INT_MIN when the sample holds fewer than k valid rows).
-// Keys are ~orderable(score): the k-th SMALLEST key.  One 1024-thread CTA per query: OR/AND
-// pre-pass, then an MSB-first byte radix select over the bytes that vary; no gather, no sort.
+// tau_q = a score that at least k sample rows reach (INT_MIN when the sample holds fewer than
+// k valid rows).  Keys are ~orderable(score).  One 1024-thread CTA per query: one pass for the
+// per-thread minima and a sort of those (k <= 256), else the exact k-th smallest key by an
+// MSB-first byte radix select over the bytes that vary.
 constexpr int TAU_THREADS = 1024;
 __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const u32* keys, long long n, int k, int* tau) {
   __shared__ SelectScratch<TAU_THREADS> sc;
@@ -558,7 +587,7 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const u32* keys, lo
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint4* kq = reinterpret_cast<const uint4*>(keys + (size_t)q * n);  // n is a multiple of 128
   const long long n4 = n >> 2;
-  u32 vor = 0, vand = ~0u;
+  u32 vor = 0, vand = ~0u, tmin = 0xFFFFFFFFu;
   int vcnt = 0;
   for (long long i = tid; i < n4; i += TAU_THREADS) {
     const uint4 v = kq[i];
@@ -569,6 +598,7 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const u32* keys, lo
         vor |= e[j];
         vand &= e[j];
         ++vcnt;
+        tmin = min(tmin, e[j]);
       }
   }
 #pragma unroll
@@ -599,6 +629,22 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const u32* keys, lo
   if (sc.b_valid < k) {
     if (tid == 0) tau[q] = (int)0x80000000;
     return;
+  }
+  // Any score that at least k sample rows reach is a valid bound, it need not be the exact
+  // k-th: the k-th smallest of the per-thread minimum keys is one (the k smallest minima
+  // belong to k different rows) and costs one bitonic sort of 1024 keys instead of the radix
+  // passes; it lets ~10% more rows through the filter pass than the exact k-th would.
+  if (k <= TAU_THREADS / 4) {
+    sc.tmin[tid] = tmin == 0xFFFFFFFFu ? K1_INVALID : (u64)tmin;
+    sc.tidx[tid] = (u32)tid;
+    __syncthreads();
+    block_bitonic_sort_pairs<TAU_THREADS>(sc.tmin, sc.tidx, TAU_THREADS);
+    const u64 bound = sc.tmin[k - 1];
+    if (bound != K1_INVALID) {
+      if (tid == 0) tau[q] = i32_from_orderable(~(u32)bound);
+      return;
+    }
+    __syncthreads();
   }
   const u32 v_or = (u32)sc.b_or;
   const u32 diff = v_or ^ (u32)sc.b_and;
@@ -632,6 +678,7 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const u32* keys, lo
 
 // exact top-k of each query's filtered list segments, (score desc, row asc)
 constexpr int LIST_THREADS = 1024;
+constexpr int LIST_STAGE_CAP = 6144;  // list entries of one query staged in shared memory (48 KB)
 template <int MODE>  // MERGE_I32_DESC: scores as is; MERGE_HAMMING: dist = popc(q) - score / 255
 __global__ void __launch_bounds__(LIST_THREADS)
     tc_select_lists_kernel(const u32* cnt, const int* list_score, const u32* list_row, int n_cta, int cap_cta,
@@ -640,8 +687,12 @@ __global__ void __launch_bounds__(LIST_THREADS)
   extern __shared__ __align__(16) unsigned char merge_smem[];
   u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
   u32* s_k2 = reinterpret_cast<u32*>(s_k1 + kcap);
+  u32* st_key = s_k2 + kcap;               // [LIST_STAGE_CAP] compacted list of this query
+  u32* st_row = st_key + LIST_STAGE_CAP;   // [LIST_STAGE_CAP]
   __shared__ SelectScratch<LIST_THREADS> sc;
   __shared__ u32 s_seg[256];  // n_cta <= 148
+  __shared__ u32 s_off[256];
+  __shared__ u32 s_total;
   __shared__ int s_qpop;
   const int q = blockIdx.x;
   if (MODE == MERGE_HAMMING) {
@@ -660,9 +711,12 @@ __global__ void __launch_bounds__(LIST_THREADS)
   __syncthreads();
   const int* ls = list_score + (size_t)q * n_cta * cap_cta;
   const u32* lr = list_row + (size_t)q * n_cta * cap_cta;
+  // i / cap_cta by multiply-high where that is exact (i * cap_cta < 2^32 for every slot)
+  const u32 magic = ((u64)n_cta * cap_cta * cap_cta < 0x100000000ull)
+                        ? (u32)((0x100000000ull + (u32)cap_cta - 1) / (u32)cap_cta) : 0u;
   auto get = [&](long long i, u64& x, u32& y) {
-    const int seg = (int)(i / cap_cta);
-    const int j = (int)(i - (long long)seg * cap_cta);
+    const int seg = magic ? (int)__umulhi((u32)i, magic) : (int)(i / cap_cta);
+    const int j = (int)i - seg * cap_cta;
     if ((u32)j < s_seg[seg]) {
       x = (u64)(~i32_orderable(ls[i]));
       y = lr[i];
@@ -671,7 +725,47 @@ __global__ void __launch_bounds__(LIST_THREADS)
       y = K2_INVALID;
     }
   };
-  const int m = block_select_sorted<LIST_THREADS>(get, (long long)n_cta * cap_cta, k, s_k1, s_k2, kcap, sc);
+  // The segments are sparse (a third full on average) and every pass over them is a chain of
+  // dependent L2 loads, so they are first compacted into shared memory, one warp per segment
+  // with coalesced loads, and the selection runs over the dense copy.
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    u32 run = 0;
+    for (int base = 0; base < n_cta; base += 32) {
+      const u32 c = (base + lane < n_cta) ? s_seg[base + lane] : 0u;
+      u32 incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u32 up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (base + lane < n_cta) s_off[base + lane] = run + incl - c;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) s_total = run;
+  }
+  __syncthreads();
+  const u32 total = s_total;
+  int m;
+  if (total <= (u32)LIST_STAGE_CAP) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int seg = warp; seg < n_cta; seg += LIST_THREADS / 32) {
+      const u32 c = s_seg[seg], o = s_off[seg];
+      const size_t src = (size_t)seg * cap_cta;
+      for (u32 j = lane; j < c; j += 32) {
+        st_key[o + j] = ~i32_orderable(ls[src + j]);
+        st_row[o + j] = lr[src + j];
+      }
+    }
+    __syncthreads();
+    auto get_dense = [&](long long i, u64& x, u32& y) {
+      x = (u64)st_key[i];
+      y = st_row[i];
+    };
+    m = block_select_sorted<LIST_THREADS, true>(get_dense, (long long)total, k, s_k1, s_k2, kcap, sc);
+  } else {
+    m = block_select_sorted<LIST_THREADS, true>(get, (long long)n_cta * cap_cta, k, s_k1, s_k2, kcap, sc);
+  }
   for (int j = threadIdx.x; j < k; j += LIST_THREADS) {
     const size_t o = (size_t)q * k + j;
     if (j < m) {
@@ -757,8 +851,9 @@ static int tc_sample_stride(long long n, int k) {
 }
 
 struct TcPlan {
-  long long tiles, sample_tiles;
-  int stride;
+  long long tiles, sample_tiles, keys_per_q;
+  int stride, sample_ctas;
+  bool colmax;
   int qblocks, ctas_x, cap_cta;
   size_t off_keys, off_sscore, off_sidx, off_scount, off_tau, off_cnt, off_ls, off_lr, total;
 };
@@ -784,7 +879,12 @@ static TcPlan tc_plan(long long n, int q, int k) {
   p.cap_cta = (int)cap;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += align_up(bytes, 256); return r; };
-  p.off_keys = take((size_t)q * p.sample_tiles * TC_BM * 4);
+  // sample pass output: one key per (CTA, row slot) when those are plenty (>= 4k), else the
+  // dense keys of every sampled row
+  p.sample_ctas = (int)(p.sample_tiles < p.ctas_x ? p.sample_tiles : p.ctas_x);
+  p.colmax = (long long)p.sample_ctas * TC_BM >= 4LL * k;
+  p.keys_per_q = p.colmax ? (long long)p.sample_ctas * TC_BM : p.sample_tiles * TC_BM;
+  p.off_keys = take((size_t)q * p.keys_per_q * 4);
   p.off_sscore = take((size_t)q * k * 4);
   p.off_sidx = take((size_t)q * k * 8);
   p.off_scount = take((size_t)q * 4);
@@ -846,7 +946,12 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   const TcSmem lay = tc_smem_layout(kb, packed);
   RR_CHECK_ARG(lay.stages >= 2, "not enough shared memory for the operand ring");
   const size_t smem = lay.bytes;
-  RR_CUDA(cudaFuncSetAttribute(tc_i8_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RR_CUDA(cudaFuncSetAttribute(tc_i8_search_kernel<EPI_COLMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  RR_CUDA(cudaFuncSetAttribute(tc_i8_search_kernel<EPI_FILTER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
+  RR_CUDA(cudaFuncSetAttribute(tc_i8_search_kernel<EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
   const int qblocks = p.qblocks;
   const int ctas_x = p.ctas_x;
 
@@ -877,12 +982,15 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   a.tau = nullptr;
   a.dense = 1;
   {
-    dim3 grid((unsigned)(a.n_tiles < ctas_x ? a.n_tiles : ctas_x), qblocks);
-    tc_i8_search_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
+    dim3 grid((unsigned)p.sample_ctas, qblocks);
+    if (p.colmax)
+      tc_i8_search_kernel<EPI_COLMAX><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
+    else
+      tc_i8_search_kernel<EPI_DENSE><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
     RR_LAUNCH_CHECK();
   }
   const int kcap = merge_cap(k);
-  tc_tau_kernel<<<q, TAU_THREADS, 0, st>>>(a.dense_keys, p.sample_tiles * TC_BM, k, (int*)(w + p.off_tau));
+  tc_tau_kernel<<<q, TAU_THREADS, 0, st>>>(a.dense_keys, p.keys_per_q, k, (int*)(w + p.off_tau));
   RR_LAUNCH_CHECK();
 
   // ---- pass 1: filter pass over all rows (every CTA of the grid writes its cnt entries)
@@ -892,16 +1000,21 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   a.dense = 0;
   {
     dim3 grid((unsigned)ctas_x, qblocks);
-    tc_i8_search_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
+    tc_i8_search_kernel<EPI_FILTER><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
     RR_LAUNCH_CHECK();
   }
   // ---- pass 2: exact top-k of each query's list segments
+  const size_t list_smem = (size_t)kcap * 12 + (size_t)LIST_STAGE_CAP * 8;
+  RR_CUDA(cudaFuncSetAttribute(tc_select_lists_kernel<MERGE_HAMMING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)list_smem));
+  RR_CUDA(cudaFuncSetAttribute(tc_select_lists_kernel<MERGE_I32_DESC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)list_smem));
   if (hamming)
-    tc_select_lists_kernel<MERGE_HAMMING><<<q, LIST_THREADS, (size_t)kcap * 12, st>>>(
+    tc_select_lists_kernel<MERGE_HAMMING><<<q, LIST_THREADS, list_smem, st>>>(
         a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, queries, (const int*)(w + p.off_tau), row_base, out_a,
         out_idx, nullptr, overflow_out);
   else
-    tc_select_lists_kernel<MERGE_I32_DESC><<<q, LIST_THREADS, (size_t)kcap * 12, st>>>(
+    tc_select_lists_kernel<MERGE_I32_DESC><<<q, LIST_THREADS, list_smem, st>>>(
         a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, queries, (const int*)(w + p.off_tau), row_base, out_a,
         out_idx, nullptr, overflow_out);
   RR_LAUNCH_CHECK();
@@ -981,7 +1094,8 @@ extern "C" int rr_tc_dense_keys(const int8_t* emb, int64_t n, int32_t dim, const
   const int kb = dim / TC_BK;
   const TcSmem lay = tc_smem_layout(kb, false);
   const size_t smem = lay.bytes;
-  RR_CUDA(cudaFuncSetAttribute(tc_i8_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RR_CUDA(cudaFuncSetAttribute(tc_i8_search_kernel<EPI_DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)smem));
   const int qblocks = (q + TC_BN - 1) / TC_BN;
   const int sms = sm_count() > 0 ? sm_count() : 148;
   int ctas_x = sms / qblocks;
@@ -1006,7 +1120,7 @@ extern "C" int rr_tc_dense_keys(const int8_t* emb, int64_t n, int32_t dim, const
   a.packed_codes = nullptr;
   a.debug = 0;
   dim3 grid((unsigned)(a.n_tiles < ctas_x ? a.n_tiles : ctas_x), qblocks);
-  tc_i8_search_kernel<<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
+  tc_i8_search_kernel<EPI_DENSE><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
   RR_LAUNCH_CHECK();
   return RR_OK;
 }

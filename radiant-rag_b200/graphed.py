@@ -58,3 +58,92 @@ class GraphedSearch:
     def __call__(self, queries: torch.Tensor) -> Any:
         self.load(queries)
         return self.replay()
+
+
+def _capture(fn: Callable[[], Any], device: torch.device, warmup: int = 3) -> Tuple[torch.cuda.CUDAGraph, Any, int]:
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            fn()
+    torch.cuda.current_stream(device).wait_stream(side)
+    torch.cuda.synchronize(device)
+    graph = torch.cuda.CUDAGraph()
+    launches0 = _lib.launch_count
+    with torch.cuda.graph(graph):
+        out = fn()
+    return graph, out, _lib.launch_count - launches0
+
+
+class GraphedShardedSearch:
+    """The row-sharded two-stage step (sharded.ShardedDenseSearch.search_quantized) with its
+    three compute segments captured as CUDA graphs and the NCCL exchanges issued eagerly
+    between them:
+
+        graph 1  quantise queries, local Hamming top-k'
+        NCCL     all_gather of the (dist, row) lists
+        graph 2  merge to the global top-k', score the candidates this shard owns
+        NCCL     all_reduce(MAX) of the scores
+        graph 3  rank, cut, filter
+
+    Per step the host issues 3 graph launches and 3 collectives instead of ~25 calls, which
+    is what bounds a sharded step whose GPU time is ~100 us.  Results are identical to the
+    eager path (same kernels, same order)."""
+
+    def __init__(self, search: Any, n_queries: int, dim: int, top_k: int, rescore_multiplier: float = 4.0,
+                 min_similarity: float = 0.0, prefer_int8: bool = True, tag_mask: int = 0,
+                 tag_value: int = 0) -> None:
+        import torch.distributed as dist
+
+        ops = search.ops
+        self.group = search.group
+        self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if self.world < 2:
+            raise ValueError("GraphedShardedSearch is for world_size >= 2; use GraphedSearch on one GPU")
+        self.device = torch.device(ops.device)
+        dev = self.device
+        nq = n_queries
+        cand_k = max(1, min(int(top_k * rescore_multiplier), _lib.RR_MAX_K))
+        self.static_in = torch.zeros((nq, dim), dtype=torch.float32, device=dev)
+
+        def seg1():
+            qf, qc = ops.quantize_queries(self.static_in)
+            d, i = ops.hamming_topk(qc, cand_k, tag_mask, tag_value, check_overflow=False)
+            return qf, d.contiguous(), i.contiguous()
+
+        self.g1, (qf, self.d_loc, self.i_loc), k1 = _capture(seg1, dev)
+        self.d_buf = torch.zeros((self.world, nq, cand_k), dtype=self.d_loc.dtype, device=dev)
+        self.i_buf = torch.zeros((self.world, nq, cand_k), dtype=self.i_loc.dtype, device=dev)
+
+        def seg2():
+            d_all = self.d_buf.permute(1, 0, 2).reshape(nq, self.world * cand_k).contiguous()
+            i_all = self.i_buf.permute(1, 0, 2).reshape(nq, self.world * cand_k).contiguous()
+            _d, cand = ops.merge_hamming(d_all, i_all, cand_k)
+            return cand, ops.score_candidates(qf, cand, prefer_int8)
+
+        self.g2, (cand, self.scores), k2 = _capture(seg2, dev)
+
+        def seg3():
+            return ops.rank_scored(self.scores, cand, top_k, min_similarity)
+
+        self.g3, self.static_out, k3 = _capture(seg3, dev)
+        self.kernels_per_replay = k1 + k2 + k3
+
+    def load(self, queries: torch.Tensor) -> None:
+        self.static_in.copy_(queries, non_blocking=True)
+
+    def replay(self) -> Any:
+        import torch.distributed as dist
+
+        self.g1.replay()
+        dist.all_gather_into_tensor(self.d_buf, self.d_loc, group=self.group)
+        dist.all_gather_into_tensor(self.i_buf, self.i_loc, group=self.group)
+        self.g2.replay()
+        dist.all_reduce(self.scores, op=dist.ReduceOp.MAX, group=self.group)
+        self.g3.replay()
+        _lib.launch_count += self.kernels_per_replay
+        return self.static_out
+
+    def __call__(self, queries: torch.Tensor) -> Any:
+        self.load(queries)
+        return self.replay()
