@@ -27,6 +27,7 @@ struct SelectScratch {
   int b_need;
   int b_ceq;
   int count;
+  u64 kth;            // result slot of block_kth_smallest
   u64 tmin[THREADS];  // per-thread minimum key1 (bound shortcut)
   u32 tidx[THREADS];
 };
@@ -92,6 +93,59 @@ __device__ __forceinline__ void block_bitonic_sort_pairs(u64* s_k1, u32* s_k2, i
       __syncthreads();
     }
   }
+}
+
+// k-th smallest value (rank 0-based, with multiplicity) of one u64 key per thread.
+// Each warp sorts its 32 keys in registers (shuffle bitonic network, no block barrier) and
+// parks the sorted run in shared memory; then ONE warp bisects the value range, lane w
+// counting the elements <= mid in run w by binary search.  Two block barriers and a few
+// thousand warp instructions in total, against ~50 barriers for a block-wide bitonic sort.
+// `runs` is [THREADS] u64 scratch, `result` one u64 in shared memory.
+template <int THREADS>
+__device__ __forceinline__ u64 block_kth_smallest(u64 key, int rank_wanted, u64* runs, u64* result) {
+  static_assert(THREADS % 32 == 0 && THREADS <= 1024, "one lane per sorted run");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  u64 x = key;
+#pragma unroll
+  for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      const u64 y = __shfl_xor_sync(0xffffffffu, x, stride);
+      const bool up = (lane & size) == 0;       // this block of the network sorts ascending
+      const bool lower = (lane & stride) == 0;  // this lane keeps the smaller element when ascending
+      x = ((lower == up) == (y < x)) ? y : x;
+    }
+  }
+  runs[tid] = x;
+  __syncthreads();
+  if (warp == 0) {
+    constexpr int RUNS = THREADS / 32;
+    const bool have = lane < RUNS;
+    const u64* r = runs + (have ? lane : 0) * 32;
+    u64 lo = have ? r[0] : ~0ull, hi = have ? r[31] : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const u64 l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+      lo = l2 < lo ? l2 : lo;
+      hi = h2 > hi ? h2 : hi;
+    }
+    while (lo < hi) {  // smallest value v with #(keys <= v) > rank_wanted
+      const u64 mid = lo + ((hi - lo) >> 1);
+      int cnt = 0;
+      if (have) {
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1)
+          if (r[cnt + step - 1] <= mid) cnt += step;
+        if (cnt == 31 && r[31] <= mid) cnt = 32;
+      }
+      cnt = __reduce_add_sync(0xffffffffu, cnt);
+      if (cnt > rank_wanted) hi = mid;
+      else lo = mid + 1;
+    }
+    if (lane == 0) *result = lo;
+  }
+  __syncthreads();
+  return *result;
 }
 
 // Select the min(k, #valid) smallest pairs among elements 0..n-1 produced by
@@ -160,11 +214,7 @@ __device__ int block_select_sorted(Get get, long long n, int k, u64* s_k1, u32* 
   const u64 diff = v_or ^ sc.b_and;
 
   if (TRY_BOUND && valid > cap && k <= THREADS / 2) {
-    sc.tmin[tid] = tmin;
-    sc.tidx[tid] = (u32)tid;
-    __syncthreads();
-    block_bitonic_sort_pairs<THREADS>(sc.tmin, sc.tidx, THREADS);
-    const u64 bound = sc.tmin[kk - 1];
+    const u64 bound = block_kth_smallest<THREADS>(tmin, kk - 1, sc.tmin, &sc.kth);
     if (bound != K1_INVALID) {
       for (long long i = tid; i < n; i += THREADS) {
         u64 a;

@@ -632,14 +632,11 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const u32* keys, lo
   }
   // Any score that at least k sample rows reach is a valid bound, it need not be the exact
   // k-th: the k-th smallest of the per-thread minimum keys is one (the k smallest minima
-  // belong to k different rows) and costs one bitonic sort of 1024 keys instead of the radix
+  // belong to k different rows) and costs one ranking of 1024 keys instead of the radix
   // passes; it lets ~10% more rows through the filter pass than the exact k-th would.
   if (k <= TAU_THREADS / 4) {
-    sc.tmin[tid] = tmin == 0xFFFFFFFFu ? K1_INVALID : (u64)tmin;
-    sc.tidx[tid] = (u32)tid;
-    __syncthreads();
-    block_bitonic_sort_pairs<TAU_THREADS>(sc.tmin, sc.tidx, TAU_THREADS);
-    const u64 bound = sc.tmin[k - 1];
+    const u64 bound = block_kth_smallest<TAU_THREADS>(tmin == 0xFFFFFFFFu ? K1_INVALID : (u64)tmin, k - 1, sc.tmin,
+                                                       &sc.kth);
     if (bound != K1_INVALID) {
       if (tid == 0) tau[q] = i32_from_orderable(~(u32)bound);
       return;
@@ -677,10 +674,10 @@ __global__ void __launch_bounds__(TAU_THREADS) tc_tau_kernel(const u32* keys, lo
 }
 
 // exact top-k of each query's filtered list segments, (score desc, row asc)
-constexpr int LIST_THREADS = 1024;
+constexpr int LIST_THREADS = 512;
 constexpr int LIST_STAGE_CAP = 6144;  // list entries of one query staged in shared memory (48 KB)
 template <int MODE>  // MERGE_I32_DESC: scores as is; MERGE_HAMMING: dist = popc(q) - score / 255
-__global__ void __launch_bounds__(LIST_THREADS)
+__global__ void __launch_bounds__(LIST_THREADS, 2)
     tc_select_lists_kernel(const u32* cnt, const int* list_score, const u32* list_row, int n_cta, int cap_cta,
                            int k, int kcap, int dim, const int8_t* q_pm1, const int* tau, long long row_base,
                            void* out_a, long long* out_idx, int* out_count, unsigned* overflow) {
