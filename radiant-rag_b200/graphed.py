@@ -20,7 +20,38 @@ import torch
 from . import _lib
 
 
-class GraphedSearch:
+class _StagedInput:
+    """Host queries reach the graph's static input through two device staging buffers filled on a
+    copy stream, so the host->device copy of step i+1 overlaps the kernels of step i (the
+    host runs ahead of the GPU once a step is a graph launch)."""
+
+    def _init_staging(self) -> None:
+        dev = self.device
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._staging = [torch.empty_like(self.static_in) for _ in range(2)]
+        self._filled = [torch.cuda.Event() for _ in range(2)]
+        self._consumed = [torch.cuda.Event() for _ in range(2)]
+        self._turn = 0
+
+    def load(self, queries: torch.Tensor) -> None:
+        """Stage this step's queries into the graph's input buffer."""
+        if queries.is_cuda:
+            self.static_in.copy_(queries, non_blocking=True)
+            return
+        b = self._turn
+        self._turn ^= 1
+        main = torch.cuda.current_stream(self.device)
+        cs = self._copy_stream
+        cs.wait_event(self._consumed[b])  # no-op until the buffer has been used once
+        with torch.cuda.stream(cs):
+            self._staging[b].copy_(queries, non_blocking=True)  # async for pinned host memory
+            self._filled[b].record(cs)
+        main.wait_event(self._filled[b])
+        self.static_in.copy_(self._staging[b], non_blocking=True)
+        self._consumed[b].record(main)
+
+
+class GraphedSearch(_StagedInput):
     """graph = GraphedSearch(lambda q: search.search_quantized(q, 10, check_overflow=False),
                              n_queries, dim, device)
     idx, score, count = graph(queries)      # queries: host (pinned) or device f32 [n_queries, dim]
@@ -45,10 +76,7 @@ class GraphedSearch:
         with torch.cuda.graph(self.graph):
             self.static_out = step(self.static_in)
         self.kernels_per_replay = _lib.launch_count - launches0  # our kernels inside the graph
-
-    def load(self, queries: torch.Tensor) -> None:
-        """Stage this step's queries into the graph's input buffer (async for pinned host memory)."""
-        self.static_in.copy_(queries, non_blocking=True)
+        self._init_staging()
 
     def replay(self) -> Any:
         self.graph.replay()
@@ -75,7 +103,7 @@ def _capture(fn: Callable[[], Any], device: torch.device, warmup: int = 3) -> Tu
     return graph, out, _lib.launch_count - launches0
 
 
-class GraphedShardedSearch:
+class GraphedShardedSearch(_StagedInput):
     """The row-sharded two-stage step (sharded.ShardedDenseSearch.search_quantized) with its
     three compute segments captured as CUDA graphs and the NCCL exchanges issued eagerly
     between them:
@@ -128,9 +156,7 @@ class GraphedShardedSearch:
 
         self.g3, self.static_out, k3 = _capture(seg3, dev)
         self.kernels_per_replay = k1 + k2 + k3
-
-    def load(self, queries: torch.Tensor) -> None:
-        self.static_in.copy_(queries, non_blocking=True)
+        self._init_staging()
 
     def replay(self) -> Any:
         import torch.distributed as dist
