@@ -331,6 +331,21 @@ def run_gpu_arm(args) -> None:
 
     reps = max(5, min(args.steps, 20))
     scan_ms = time_stage(lambda: index.hamming_topk(qc, cand_k, check_overflow=False), reps)
+    # dominant kernel alone: rr_tc_timing brackets the four kernels of rr_hamming_topk_tc with CUDA
+    # events on the launching stream; average over the same flushed repetitions
+    import ctypes as C
+    lib = _lib.load()
+    lib.rr_tc_timing(1)
+    parts = [0.0, 0.0, 0.0, 0.0]
+    buf = (C.c_float * 4)()
+    for _ in range(reps):
+        flush.fill_(1)
+        index.hamming_topk(qc, cand_k, check_overflow=False)
+        if lib.rr_tc_last_timing_ms(buf) != 0:
+            raise SystemExit("rr_tc_last_timing_ms: " + _lib.last_error())
+        parts = [p + float(b) for p, b in zip(parts, buf)]
+    lib.rr_tc_timing(0)
+    sample_ms, tau_ms, filter_ms, select_ms = (p / reps for p in parts)
     scan_popc_ms = time_stage(lambda: index.hamming_topk(qc, cand_k, use_tc=False), reps)
     _d, cand = index.hamming_topk(qc, cand_k)
     rescore_ms = time_stage(lambda: index.rescore(qf, cand, top_k, 0.0, prefer_int8=False), reps)
@@ -350,14 +365,25 @@ def run_gpu_arm(args) -> None:
     popc_rate = nq * n_local * index.words / (scan_popc_ms * 1e-3)
     int8_ops = 2.0 * nq * n_local * index.words * 32
     bf16_peak = float(json.loads(peaks_path.read_text()).get("bf16_tflops", 1590.0)) if peaks_path.exists() else 1590.0
+    tensor_peak = 2.0 * bf16_peak
     roofline = {
-        "kernel": "rr_hamming_topk_tc: tc_i8_search_kernel (tcgen05 kind::i8) x2 + select kernels",
-        "bound": "tensor", "achieved": int8_ops / (scan_ms * 1e-3) / 1e12, "peak": 2.0 * bf16_peak,
-        "unit": "TOP/s", "frac": int8_ops / (scan_ms * 1e-3) / 1e12 / (2.0 * bf16_peak), "traffic": None,
+        "kernel": "tc_i8_search_kernel<EPI_FILTER> (tcgen05 kind::i8 filter pass of rr_hamming_topk_tc; ~60% of the "
+                  "step, profiles/r1_launches_bench_final_summary.md)",
+        "bound": "tensor", "achieved": int8_ops / (filter_ms * 1e-3) / 1e12, "peak": tensor_peak,
+        "unit": "TOP/s", "frac": int8_ops / (filter_ms * 1e-3) / 1e12 / tensor_peak,
+        "traffic": 105844480 if (world == 1 and n_local == 1_000_000 and dim == 768 and nq == 256) else None,
+        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, ncu --set full "
+                          "(profiles/r1_ncu_full_summary_final.md)",
+        "launch_ms": filter_ms, "timing": "CUDA events on the launching stream around the kernel (rr_tc_timing), "
+                                         "L2 flushed before every call",
         "peak_source": "2 x measured dense bf16 cuBLAS burst (MEASURED_PEAKS.json); int8 is nominally 2x bf16",
         "algorithmic_ops_per_launch": int8_ops, "algorithmic_bytes_per_launch": code_bytes,
-        "note": "batched stage 1 runs as a +-1 int8 GEMM on tcgen05 with packed codes expanded in shared "
-                "memory; HBM traffic is the packed codes only. hbm / popc views of the same stage below.",
+        "note": "batched stage 1 runs as an exact u8(0/255) x s8(+-1) GEMM on tcgen05: packed codes are expanded on "
+                "chip into a tensor-memory operand ring, HBM traffic is the packed codes only. The other kernels of "
+                "the stage, and hbm / popc views of the same stage, below.",
+        "stage1_kernels_ms": {"sample_pass": sample_ms, "tau": tau_ms, "filter_pass": filter_ms,
+                              "list_select": select_ms, "whole_call": scan_ms},
+        "stage1_call_frac": int8_ops / (scan_ms * 1e-3) / 1e12 / tensor_peak,
         "hbm_view": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "peak_source": peak_src},
         "popc_path": {"ms": scan_popc_ms, "bound": "popc", "achieved": popc_rate / 1e12, "peak": popc_peak / 1e12,
@@ -401,7 +427,7 @@ def run_gpu_arm(args) -> None:
     line = {
         "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u8 codes as +-1 int8 (tcgen05) + f32 rescore", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "u8 sign codes (0/255 u8 x +-1 s8 on tcgen05, int32 accumulate) + f32 rescore", "data": "synthetic",
         "config": {"workload": WORKLOAD, "corpus_rows": n, "dim": dim, "batch_queries": nq, "candidates": cand_k,
                    "top_k": top_k, "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}",
                    "l2": "flushed between timed iterations (256 MB fill)",

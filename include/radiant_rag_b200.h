@@ -111,6 +111,13 @@ int rr_int8_search_topk_tc(const int8_t* emb, int64_t n, int32_t dim, const uint
  * (key = ~(score ^ 0x80000000), 0xFFFFFFFF = padded row). */
 int rr_tc_dense_keys(const int8_t* emb, int64_t n, int32_t dim, const int8_t* queries_i8, int32_t q,
                      uint32_t* out_keys, void* stream);
+/* Measurement aid (bench.py roofline): when enabled, rr_hamming_topk_tc / rr_int8_search_topk_tc
+ * bracket each of their four kernels with CUDA events on the launching stream;
+ * rr_tc_last_timing_ms waits for the last call and returns the durations in ms:
+ * out_ms[0] sample pass, [1] tau, [2] filter pass (the tcgen05 kernel), [3] list select.
+ * Not for use inside stream capture. */
+int rr_tc_timing(int32_t enable);
+int rr_tc_last_timing_ms(float* out_ms);
 
 /* ---- R3: rescore_candidates (radiant/storage/quantization.py:185-222) plus the
  * caller's cut/filter (radiant/storage/redis_store.py:850-854).

@@ -47,6 +47,8 @@ PROTOTYPES = {
     "rr_hamming_topk_tc": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
     "rr_int8_search_topk_tc": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
     "rr_tc_dense_keys": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p]),
+    "rr_tc_timing": (_i32, [_i32]),
+    "rr_tc_last_timing_ms": (_i32, [_p]),
     "rr_rescore_f32": (_i32, [_p, _i32, _i32, _p, _i32, _i64, _i64, _p, _i32, _i32, _f64, _p, _p, _p, _p]),
     "rr_score_candidates_f32": (_i32, [_p, _i32, _i32, _p, _i32, _i64, _i64, _p, _i32, _p, _p]),
     "rr_rank_scored_f32": (_i32, [_p, _p, _i32, _i32, _i32, _f64, _p, _p, _p, _p]),

@@ -893,6 +893,15 @@ static TcPlan tc_plan(long long n, int q, int k) {
   return p;
 }
 
+// optional per-kernel event timing (rr_tc_timing): events 0..4 bracket the four kernels
+static bool g_tc_timing = false;
+static bool g_tc_timed = false;
+static cudaEvent_t g_tc_ev[5];
+static bool g_tc_ev_ready = false;
+static void tc_mark(int i, cudaStream_t st) {
+  if (g_tc_timing && g_tc_ev_ready) cudaEventRecord(g_tc_ev[i], st);
+}
+
 struct TcSmem {
   int stages;
   size_t bytes;
@@ -978,6 +987,7 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   a.n_tiles = p.sample_tiles;
   a.tau = nullptr;
   a.dense = 1;
+  tc_mark(0, st);
   {
     dim3 grid((unsigned)p.sample_ctas, qblocks);
     if (p.colmax)
@@ -987,8 +997,10 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
     RR_LAUNCH_CHECK();
   }
   const int kcap = merge_cap(k);
+  tc_mark(1, st);
   tc_tau_kernel<<<q, TAU_THREADS, 0, st>>>(a.dense_keys, p.keys_per_q, k, (int*)(w + p.off_tau));
   RR_LAUNCH_CHECK();
+  tc_mark(2, st);
 
   // ---- pass 1: filter pass over all rows (every CTA of the grid writes its cnt entries)
   a.tile_stride = 1;
@@ -1000,6 +1012,7 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
     tc_i8_search_kernel<EPI_FILTER><<<grid, TC_THREADS, smem, st>>>(map_a, map_b, a);
     RR_LAUNCH_CHECK();
   }
+  tc_mark(3, st);
   // ---- pass 2: exact top-k of each query's list segments
   const size_t list_smem = (size_t)kcap * 12 + (size_t)LIST_STAGE_CAP * 8;
   RR_CUDA(cudaFuncSetAttribute(tc_select_lists_kernel<MERGE_HAMMING>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1015,6 +1028,8 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
         a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, queries, (const int*)(w + p.off_tau), row_base, out_a,
         out_idx, nullptr, overflow_out);
   RR_LAUNCH_CHECK();
+  tc_mark(4, st);
+  g_tc_timed = g_tc_timing && g_tc_ev_ready;
   return RR_OK;
 }
 
@@ -1032,6 +1047,27 @@ extern "C" int rr_unpack_codes_pm1(const uint8_t* codes, int64_t n, int32_t code
   if (blocks > 148LL * 32) blocks = 148LL * 32;
   unpack_pm1_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(codes, n, code_stride, dim, out);
   RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
+extern "C" int rr_tc_timing(int32_t enable) {
+  if (enable && !g_tc_ev_ready) {
+    for (int i = 0; i < 5; ++i) RR_CUDA(cudaEventCreate(&g_tc_ev[i]));
+    g_tc_ev_ready = true;
+  }
+  g_tc_timing = enable != 0;
+  if (!g_tc_timing) g_tc_timed = false;
+  return RR_OK;
+}
+
+extern "C" int rr_tc_last_timing_ms(float* out_ms) {
+  RR_CHECK_ARG(out_ms != nullptr, "null pointer");
+  if (!g_tc_timed) {
+    set_error("rr_tc_last_timing_ms: no timed tensor-core call (rr_tc_timing(1) first)");
+    return RR_ERR_INVALID;
+  }
+  RR_CUDA(cudaEventSynchronize(g_tc_ev[4]));
+  for (int i = 0; i < 4; ++i) RR_CUDA(cudaEventElapsedTime(&out_ms[i], g_tc_ev[i], g_tc_ev[i + 1]));
   return RR_OK;
 }
 
