@@ -10,6 +10,7 @@ candidate lists cross NVLink:
                                       -> all_reduce(MAX) [Q, k'] -> rank, cut, filter
   BM25     local top-k (global idf/avgdl baked into the shard's impacts)
                                       -> all_gather -> merge (score desc, row asc)
+  int8     (config 4) local exact int8 top-k -> all_gather -> merge (score desc, row asc)
   RRF      runs on the merged, replicated lists on every rank.
 
 Payloads are tiny (Q*k'*12 B per rank), so the collectives are latency-bound; they are
@@ -59,6 +60,9 @@ class GpuShardOps:
 
     def score_candidates(self, queries_f32, cand_idx, prefer_int8=True):
         return self.index.score_candidates(queries_f32, cand_idx, prefer_int8)
+
+    def search_int8_exact(self, queries_i8, top_k, tag_mask=0, tag_value=0):
+        return self.index.search_int8_exact(queries_i8, top_k, tag_mask, tag_value)
 
     def rank_scored(self, scores, cand_idx, top_k, min_similarity):
         q, c = cand_idx.shape
@@ -156,3 +160,24 @@ class ShardedBM25Search:
         s_all = _gather_lists(score, self.group)
         i_all = _gather_lists(idx, self.group)
         return self.ops.merge_scores_f64(s_all, i_all, k)
+
+
+class ShardedInt8Search:
+    """BASELINE config 4: exact int8 x int8 -> int32 search over a row-sharded corpus.
+    Every rank searches its shard (tensor cores for batches), the per-shard top-k
+    (score, global row) lists are all_gathered and merged by (score desc, row asc)."""
+
+    def __init__(self, ops: Any, group: Optional[Any] = None) -> None:
+        self.ops = ops
+        self.group = group
+
+    def search(self, queries_i8, top_k: int, tag_mask: int = 0, tag_value: int = 0
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """queries_i8 int8 [Q, D], identical on every rank -> (idx int64 [Q,k], score int32 [Q,k])."""
+        idx, score = self.ops.search_int8_exact(queries_i8, top_k, tag_mask, tag_value)
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1:
+            return idx, score
+        s_all = _gather_lists(score, self.group)
+        i_all = _gather_lists(idx, self.group)
+        return self.ops.merge_scores_i32(s_all, i_all, top_k)

@@ -62,6 +62,23 @@ class CpuShardOps:
             out_c[r] = order.size
         return torch.from_numpy(out_i), torch.from_numpy(out_s), torch.from_numpy(out_c)
 
+    def search_int8_exact(self, queries_i8, top_k, tag_mask=0, tag_value=0):
+        r, sc = oracle.int8_exact_topk(np.asarray(queries_i8), self.rows, top_k)
+        r = np.where(r >= 0, r + self.row_base, -1)
+        return torch.from_numpy(r), torch.from_numpy(sc)
+
+    def merge_scores_i32(self, score_all, idx_all, k):
+        s, i = score_all.numpy(), idx_all.numpy()
+        q = s.shape[0]
+        out_i = np.full((q, k), -1, np.int64)
+        out_s = np.full((q, k), np.iinfo(np.int32).min, np.int32)
+        for r in range(q):
+            ok = np.nonzero(i[r] >= 0)[0]
+            order = ok[np.lexsort((i[r][ok], -s[r][ok].astype(np.int64)))][:k]
+            out_i[r, : order.size] = i[r][order]
+            out_s[r, : order.size] = s[r][order]
+        return torch.from_numpy(out_i), torch.from_numpy(out_s)
+
     def merge_scores_f64(self, score_all, idx_all, k):
         s, i = score_all.numpy(), idx_all.numpy()
         q = s.shape[0]

@@ -33,7 +33,7 @@ def _worker(rank, world, port, out_dir):
         import oracle
         from oracle.bm25 import BM25Oracle
         from radiant_rag_b200 import synthetic
-        from radiant_rag_b200.sharded import ShardedBM25Search, ShardedDenseSearch, shard_range
+        from radiant_rag_b200.sharded import ShardedBM25Search, ShardedDenseSearch, ShardedInt8Search, shard_range
         from tests.cpu_ops import CpuBm25Shard, CpuShardOps
 
         n, dim, nq, top_k = 3001, 128, 12, 10  # odd n: ragged last shard
@@ -49,6 +49,11 @@ def _worker(rank, world, port, out_dir):
                             "minsim": {"min_similarity": 0.3}}.items():
             idx, score, count = search.search_quantized(queries, top_k, rescore_multiplier=4.0, **kwargs)
             results[tag] = (idx.numpy(), score.numpy(), count.numpy())
+
+        # config 4: exact int8 search, per-shard top-k merged by (score desc, row asc)
+        q8 = oracle.quantize_int8(queries, ranges)
+        iidx, iscore = ShardedInt8Search(ops).search(q8, 7)
+        results["int8"] = (iidx.numpy(), iscore.numpy())
 
         # BM25: shard-local postings, global idf / avgdl
         n_docs, v = 1203, 300
@@ -95,6 +100,9 @@ def test_sharded_equals_single_index():
             assert m == len(w_ids), (tag, qi)
             assert idx[qi, :m].tolist() == w_ids.tolist(), (tag, qi)
             assert np.array_equal(score[qi, :m], w_s), (tag, qi)
+
+    want_r, want_s = oracle.int8_exact_topk(oracle.quantize_int8(queries, ranges), i8, 7)
+    assert np.array_equal(r0["int8_0"], want_r) and np.array_equal(r0["int8_1"], want_s)
 
     n_docs, v = 1203, 300
     ptr, toks = synthetic.zipf_corpus(n_docs, v, seed=4, mean_len=25)
