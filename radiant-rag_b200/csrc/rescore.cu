@@ -21,6 +21,7 @@ namespace rr {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ROWS = 2;  // candidate rows a warp scores per iteration
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -151,55 +152,60 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_f32_kernel(const RescoreAr
   for (int d = threadIdx.x; d < a.dim; d += RS_THREADS) sq[d] = a.queries[(size_t)q * a.dim + d];
   __syncthreads();
   const long long* cand = a.cand_idx + (size_t)q * a.c;
-  // two candidate rows per warp iteration: both rows' 128-bit loads are in flight together,
-  // which is what the latency-bound random gather needs
-  for (int c0 = warp; c0 < a.c; c0 += 2 * RS_WARPS) {
-    const int c1 = c0 + RS_WARPS;
-    const long long idx0 = cand[c0];
-    const long long idx1 = (c1 < a.c) ? cand[c1] : -1;
-    const long long l0 = idx0 - a.row_base, l1 = idx1 - a.row_base;
-    const bool v0 = idx0 >= 0 && l0 >= 0 && l0 < a.n;
-    const bool v1 = idx1 >= 0 && l1 >= 0 && l1 < a.n;
-    double acc0 = 0.0, acc1 = 0.0;
+  // RS_ROWS candidate rows per warp iteration: the 128-bit loads of all of them are in flight
+  // together, which is what the latency-bound random row gather needs
+  for (int cb = warp; cb < a.c; cb += RS_ROWS * RS_WARPS) {
+    int ci[RS_ROWS];
+    long long loc[RS_ROWS];
+    bool ok[RS_ROWS];
+    double acc[RS_ROWS];
+#pragma unroll
+    for (int r = 0; r < RS_ROWS; ++r) {
+      ci[r] = cb + r * RS_WARPS;
+      const long long idx = (ci[r] < a.c) ? cand[ci[r]] : -1;
+      loc[r] = idx - a.row_base;
+      ok[r] = idx >= 0 && loc[r] >= 0 && loc[r] < a.n;
+      acc[r] = 0.0;
+    }
     if (EMB == RR_F32 && (a.dim & 3) == 0) {
-      const float4* r0 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.emb) + (size_t)(v0 ? l0 : 0) * a.dim);
-      const float4* r1 = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.emb) + (size_t)(v1 ? l1 : 0) * a.dim);
+      const float4* rp[RS_ROWS];
+#pragma unroll
+      for (int r = 0; r < RS_ROWS; ++r)
+        rp[r] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.emb) + (size_t)(ok[r] ? loc[r] : 0) * a.dim);
       const float4* q4 = reinterpret_cast<const float4*>(sq);
       for (int v = lane; v < (a.dim >> 2); v += 32) {
-        float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0;
-        if (v0) e0 = __ldg(r0 + v);
-        if (v1) e1 = __ldg(r1 + v);
+        float4 e[RS_ROWS];
+#pragma unroll
+        for (int r = 0; r < RS_ROWS; ++r) e[r] = ok[r] ? __ldg(rp[r] + v) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 w = q4[v];
-        acc0 += (double)w.x * (double)e0.x;
-        acc1 += (double)w.x * (double)e1.x;
-        acc0 += (double)w.y * (double)e0.y;
-        acc1 += (double)w.y * (double)e1.y;
-        acc0 += (double)w.z * (double)e0.z;
-        acc1 += (double)w.z * (double)e1.z;
-        acc0 += (double)w.w * (double)e0.w;
-        acc1 += (double)w.w * (double)e1.w;
+        const double wx = (double)w.x, wy = (double)w.y, wz = (double)w.z, ww = (double)w.w;
+#pragma unroll
+        for (int r = 0; r < RS_ROWS; ++r) {  // same order of additions per row as one row at a time
+          acc[r] += wx * (double)e[r].x;
+          acc[r] += wy * (double)e[r].y;
+          acc[r] += wz * (double)e[r].z;
+          acc[r] += ww * (double)e[r].w;
+        }
       }
-      acc0 = warp_sum_f64(acc0);
-      acc1 = warp_sum_f64(acc1);
+#pragma unroll
+      for (int r = 0; r < RS_ROWS; ++r) acc[r] = warp_sum_f64(acc[r]);
     } else {
-      if (v0)
-        acc0 = (EMB == RR_F32)
-                   ? dot_f32_row(sq, reinterpret_cast<const float*>(a.emb) + (size_t)l0 * a.dim, a.dim, lane)
-                   : dot_i8_row(sq, reinterpret_cast<const int8_t*>(a.emb) + (size_t)l0 * a.dim, a.dim, lane);
-      if (v1)
-        acc1 = (EMB == RR_F32)
-                   ? dot_f32_row(sq, reinterpret_cast<const float*>(a.emb) + (size_t)l1 * a.dim, a.dim, lane)
-                   : dot_i8_row(sq, reinterpret_cast<const int8_t*>(a.emb) + (size_t)l1 * a.dim, a.dim, lane);
+#pragma unroll
+      for (int r = 0; r < RS_ROWS; ++r)
+        if (ok[r])
+          acc[r] = (EMB == RR_F32)
+                       ? dot_f32_row(sq, reinterpret_cast<const float*>(a.emb) + (size_t)loc[r] * a.dim, a.dim, lane)
+                       : dot_i8_row(sq, reinterpret_cast<const int8_t*>(a.emb) + (size_t)loc[r] * a.dim, a.dim, lane);
     }
     if (lane == 0) {
-      const float s0 = v0 ? (float)acc0 : -INFINITY;
-      const float s1 = v1 ? (float)acc1 : -INFINITY;
-      if (MODE == 0) {
-        keys[c0] = v0 ? (((u64)(~f32_orderable(s0)) << 32) | (u64)(u32)c0) : K1_INVALID;
-        if (c1 < a.c) keys[c1] = v1 ? (((u64)(~f32_orderable(s1)) << 32) | (u64)(u32)c1) : K1_INVALID;
-      } else {
-        a.out_score[(size_t)q * a.c + c0] = s0;
-        if (c1 < a.c) a.out_score[(size_t)q * a.c + c1] = s1;
+#pragma unroll
+      for (int r = 0; r < RS_ROWS; ++r) {
+        if (ci[r] >= a.c) continue;
+        const float sc = ok[r] ? (float)acc[r] : -INFINITY;
+        if (MODE == 0)
+          keys[ci[r]] = ok[r] ? (((u64)(~f32_orderable(sc)) << 32) | (u64)(u32)ci[r]) : K1_INVALID;
+        else
+          a.out_score[(size_t)q * a.c + ci[r]] = sc;
       }
     }
   }

@@ -64,6 +64,10 @@ class GpuShardOps:
     def search_int8_exact(self, queries_i8, top_k, tag_mask=0, tag_value=0):
         return self.index.search_int8_exact(queries_i8, top_k, tag_mask, tag_value)
 
+    def rescore(self, queries_f32, cand_idx, top_k, min_similarity, prefer_int8=True):
+        score, idx, count = self.index.rescore(queries_f32, cand_idx, top_k, min_similarity, prefer_int8)
+        return idx, score, count
+
     def rank_scored(self, scores, cand_idx, top_k, min_similarity):
         q, c = cand_idx.shape
         out_s = torch.empty((q, top_k), dtype=torch.float32, device=self.device)
@@ -136,6 +140,8 @@ class ShardedDenseSearch:
             score = torch.ones(idx.shape, dtype=torch.float32, device=idx.device)
             count = (idx >= 0).sum(dim=1).to(torch.int32)
             return idx, score, count
+        if world == 1 and hasattr(ops, "rescore"):
+            return ops.rescore(qf, cand, top_k, min_similarity, prefer_int8)  # score + rank in one kernel
         s = ops.score_candidates(qf, cand, prefer_int8)
         if world > 1:
             dist.all_reduce(s, op=dist.ReduceOp.MAX, group=self.group)
