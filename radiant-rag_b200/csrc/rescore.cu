@@ -154,14 +154,16 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_f32_kernel(const RescoreAr
   const long long* cand = a.cand_idx + (size_t)q * a.c;
   // RS_ROWS candidate rows per warp iteration: the 128-bit loads of all of them are in flight
   // together, which is what the latency-bound random row gather needs
-  for (int cb = warp; cb < a.c; cb += RS_ROWS * RS_WARPS) {
+  // MODE 1 may split a query's candidates over gridDim.y CTAs (more rows in flight per SM)
+  const int gw = blockIdx.y * RS_WARPS + warp, tw = gridDim.y * RS_WARPS;
+  for (int cb = gw; cb < a.c; cb += RS_ROWS * tw) {
     int ci[RS_ROWS];
     long long loc[RS_ROWS];
     bool ok[RS_ROWS];
     double acc[RS_ROWS];
 #pragma unroll
     for (int r = 0; r < RS_ROWS; ++r) {
-      ci[r] = cb + r * RS_WARPS;
+      ci[r] = cb + r * tw;
       const long long idx = (ci[r] < a.c) ? cand[ci[r]] : -1;
       loc[r] = idx - a.row_base;
       ok[r] = idx >= 0 && loc[r] >= 0 && loc[r] < a.n;
@@ -357,10 +359,17 @@ extern "C" int rr_score_candidates_f32(const float* queries, int32_t q, int32_t 
                 0.0, out_score, nullptr, nullptr};
   const size_t smem = align_up((size_t)dim * 4, 16) + 8;
   cudaStream_t st = (cudaStream_t)stream;
+  // enough CTAs for ~4 per SM, at least one warp iteration of work each
+  int split = (4 * 148 + q - 1) / q;
+  const int max_split = (c + RS_ROWS * RS_WARPS - 1) / (RS_ROWS * RS_WARPS);
+  if (split > max_split) split = max_split;
+  if (split > 8) split = 8;
+  if (split < 1) split = 1;
+  dim3 grid(q, split);
   if (emb_dtype == RR_F32)
-    rescore_f32_kernel<RR_F32, 1><<<q, RS_THREADS, smem, st>>>(a, 1);
+    rescore_f32_kernel<RR_F32, 1><<<grid, RS_THREADS, smem, st>>>(a, 1);
   else
-    rescore_f32_kernel<RR_I8, 1><<<q, RS_THREADS, smem, st>>>(a, 1);
+    rescore_f32_kernel<RR_I8, 1><<<grid, RS_THREADS, smem, st>>>(a, 1);
   RR_LAUNCH_CHECK();
   return RR_OK;
 }
