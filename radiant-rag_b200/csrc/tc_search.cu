@@ -200,6 +200,17 @@ __device__ __forceinline__ void tc_expand32(u32 w, u32* out) {
 // thresholds are clamped so that bias + score cannot wrap (|score| <= 127 * 127 * 1024 < 2^25);
 // INT_MIN ("keep everything") therefore becomes -2^30
 __host__ __device__ __forceinline__ int tc_tau_eff(int tau) { return tau < -(1 << 30) ? -(1 << 30) : tau; }
+__device__ __forceinline__ void tc_st32(u32 taddr, const u32* o) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]),
+        "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]),
+        "r"(o[16]), "r"(o[17]), "r"(o[18]), "r"(o[19]), "r"(o[20]), "r"(o[21]), "r"(o[22]), "r"(o[23]),
+        "r"(o[24]), "r"(o[25]), "r"(o[26]), "r"(o[27]), "r"(o[28]), "r"(o[29]), "r"(o[30]), "r"(o[31])
+      : "memory");
+}
 constexpr int TC_PACKED_SCALE = 255;  // packed-mode score = 255 * (popc(q) - hamming)
 
 // Thread layout: warp 0 producer, warp 1 MMA, warps 2-5 epilogue, warps 6-9 unpackers (only
@@ -316,16 +327,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_after();
       const u32 d_tmem = tmem_base + as * TC_BN;
       if (a.packed) {
-        for (int kb = 0; kb < a.kb; ++kb) {
+        // a ring stage holds TWO K blocks (64 TMEM columns): one hand-off per eight MMAs
+        for (int kb = 0; kb < a.kb; kb += 2) {
           tc_mbar_wait(full0 + stage * 8, phase);
           tc_fence_after();
-          const u32 a_tmem = tmem_base + 2 * TC_BN + stage * 32;  // A ring in tensor memory
+          const u32 a_tmem = tmem_base + 2 * TC_BN + stage * 64;  // A ring in tensor memory
           const u64 bd = bdesc0 + (u64)(kb * (TC_TILE_BYTES >> 4));
           if (!(a.debug & 2)) {
             tc_mma_i8_ts_elect(d_tmem, a_tmem, bd, TC_IDESC_UA, 1u);
             tc_mma_i8_ts_elect(d_tmem, a_tmem + 8, bd + 2, TC_IDESC_UA, 1u);
             tc_mma_i8_ts_elect(d_tmem, a_tmem + 16, bd + 4, TC_IDESC_UA, 1u);
             tc_mma_i8_ts_elect(d_tmem, a_tmem + 24, bd + 6, TC_IDESC_UA, 1u);
+            if (kb + 1 < a.kb) {
+              const u64 bd1 = bd + (u64)(TC_TILE_BYTES >> 4);
+              tc_mma_i8_ts_elect(d_tmem, a_tmem + 32, bd1, TC_IDESC_UA, 1u);
+              tc_mma_i8_ts_elect(d_tmem, a_tmem + 40, bd1 + 2, TC_IDESC_UA, 1u);
+              tc_mma_i8_ts_elect(d_tmem, a_tmem + 48, bd1 + 4, TC_IDESC_UA, 1u);
+              tc_mma_i8_ts_elect(d_tmem, a_tmem + 56, bd1 + 6, TC_IDESC_UA, 1u);
+            }
           }
           tc_commit_elect(empty0 + stage * 8);  // frees the A stage when these MMAs have read it
           if (++stage == stages) {
@@ -520,7 +539,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const u32 slot = tcount & 1u;
       tc_mbar_wait(tc_smem(pk_full + slot), (tcount >> 1) & 1u);
       const unsigned char* prow = spk + (size_t)slot * TC_BM * row_bytes + (size_t)u * row_bytes;
-      for (int kb = 0; kb < a.kb; ++kb, ++it) {
+      for (int kb = 0; kb < a.kb; kb += 2, ++it) {  // two K blocks (256 dims) per ring stage
         const u32 s = stage;
         const u32 ph = phase;
         if (++stage == stages) {
@@ -533,7 +552,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tc_mbar_arrive(tc_smem(full_a + s));
           continue;
         }
+        const bool two = kb + 1 < a.kb;
         const uint4 pw = *reinterpret_cast<const uint4*>(prow + kb * 16);  // 128 dims of this row
+        uint4 pw1 = make_uint4(0u, 0u, 0u, 0u);
+        if (two) pw1 = *reinterpret_cast<const uint4*>(prow + kb * 16 + 16);
         u32 o[32];
         tc_expand32(pw.x, o);
         tc_expand32(pw.y, o + 8);
@@ -546,7 +568,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         tc_mbar_wait(tc_smem(empty_a + s), ph ^ 1u);
         tc_fence_after();
-        const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + 2 * TC_BN + s * 32;
+        const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + 2 * TC_BN + s * 64;
+        if (two) {
+          u32 o1[32];
+          tc_expand32(pw1.x, o1);
+          tc_expand32(pw1.y, o1 + 8);
+          tc_expand32(pw1.z, o1 + 16);
+          tc_expand32(pw1.w, o1 + 24);
+          tc_st32(taddr + 32, o1);
+        }
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
             "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -914,7 +944,7 @@ static TcSmem tc_smem_layout(int kb, bool packed) {
   if (packed) {
     // A ring lives in tensor memory (8 x 32 columns next to the two 128-column accumulators);
     // shared memory holds B, the packed double buffer and the small state only
-    r.stages = 8;
+    r.stages = 4;  // x 64 TMEM columns (two K blocks per stage)
     r.bytes = 1024 + (size_t)kb * TC_TILE_BYTES + 2 * (size_t)TC_BM * kb * 16 + 2 * TC_BN * 4 + 32 * 8 + 64;
     return r;
   }

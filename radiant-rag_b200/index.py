@@ -338,6 +338,13 @@ class DenseIndex:
         score = torch.empty((q, top_k), dtype=torch.float32, device=self.device)
         idx = torch.empty((q, top_k), dtype=torch.int64, device=self.device)
         count = torch.empty((q,), dtype=torch.int32, device=self.device)
+        if q >= 8:
+            # batches: the scoring kernel spreads a query's candidates over several CTAs (more
+            # rows in flight per SM), then one small ranking kernel; same arithmetic, same order
+            s = self.score_candidates(queries, cand_idx, prefer_int8)
+            _lib.call("rr_rank_scored_f32", s.data_ptr(), cand_idx.data_ptr(), q, c, top_k,
+                      float(min_similarity), score.data_ptr(), idx.data_ptr(), count.data_ptr(), _stream())
+            return score, idx, count
         _lib.call("rr_rescore_f32", queries.data_ptr(), q, self.dim, rows.data_ptr(), dt, self.n,
                   self.row_base, cand_idx.data_ptr(), c, top_k, float(min_similarity), score.data_ptr(),
                   idx.data_ptr(), count.data_ptr(), _stream())
