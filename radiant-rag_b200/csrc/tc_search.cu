@@ -55,6 +55,10 @@ constexpr int TC_THREADS = 192 + 128 * TC_UNPACK_GROUPS + 128 * (TC_EPI_GROUPS -
                                                                                    // unpack, 4 more epilogue warps
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK;  // 16 KB
 constexpr int TC_MAX_KB = 8;                  // dim <= 1024
+#ifndef RR_TC_KBPS
+#define RR_TC_KBPS 4
+#endif
+constexpr int TC_KBPS = RR_TC_KBPS;           // K blocks per tensor-memory ring stage (1, 2 or 4)
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ u32 tc_smem(const void* p) { return (u32)__cvta_generic_to_shared(p); }
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const u32 tmem_cols = a.packed ? 512u : 256u;  // 2 accumulators x 128 columns (+ A ring of 8 x 32 columns)
+  const u32 tmem_cols = a.packed ? 512u : 256u;  // 2 accumulators x 128 columns (+ 256 columns of A ring)
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(tmem_ptr)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -327,23 +331,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_after();
       const u32 d_tmem = tmem_base + as * TC_BN;
       if (a.packed) {
-        // a ring stage holds TWO K blocks (64 TMEM columns): one hand-off per eight MMAs
-        for (int kb = 0; kb < a.kb; kb += 2) {
+        // a ring stage holds TC_KBPS K blocks (32 TMEM columns each): one hand-off per 4*TC_KBPS MMAs
+        for (int kb = 0; kb < a.kb; kb += TC_KBPS) {
           tc_mbar_wait(full0 + stage * 8, phase);
           tc_fence_after();
-          const u32 a_tmem = tmem_base + 2 * TC_BN + stage * 64;  // A ring in tensor memory
+          const u32 a_tmem = tmem_base + 2 * TC_BN + stage * (32 * TC_KBPS);  // A ring in tensor memory
           const u64 bd = bdesc0 + (u64)(kb * (TC_TILE_BYTES >> 4));
           if (!(a.debug & 2)) {
-            tc_mma_i8_ts_elect(d_tmem, a_tmem, bd, TC_IDESC_UA, 1u);
-            tc_mma_i8_ts_elect(d_tmem, a_tmem + 8, bd + 2, TC_IDESC_UA, 1u);
-            tc_mma_i8_ts_elect(d_tmem, a_tmem + 16, bd + 4, TC_IDESC_UA, 1u);
-            tc_mma_i8_ts_elect(d_tmem, a_tmem + 24, bd + 6, TC_IDESC_UA, 1u);
-            if (kb + 1 < a.kb) {
-              const u64 bd1 = bd + (u64)(TC_TILE_BYTES >> 4);
-              tc_mma_i8_ts_elect(d_tmem, a_tmem + 32, bd1, TC_IDESC_UA, 1u);
-              tc_mma_i8_ts_elect(d_tmem, a_tmem + 40, bd1 + 2, TC_IDESC_UA, 1u);
-              tc_mma_i8_ts_elect(d_tmem, a_tmem + 48, bd1 + 4, TC_IDESC_UA, 1u);
-              tc_mma_i8_ts_elect(d_tmem, a_tmem + 56, bd1 + 6, TC_IDESC_UA, 1u);
+#pragma unroll
+            for (int j = 0; j < TC_KBPS; ++j) {
+              if (kb + j < a.kb) {
+                const u64 bdj = bd + (u64)(j * (TC_TILE_BYTES >> 4));
+                tc_mma_i8_ts_elect(d_tmem, a_tmem + 32 * j, bdj, TC_IDESC_UA, 1u);
+                tc_mma_i8_ts_elect(d_tmem, a_tmem + 32 * j + 8, bdj + 2, TC_IDESC_UA, 1u);
+                tc_mma_i8_ts_elect(d_tmem, a_tmem + 32 * j + 16, bdj + 4, TC_IDESC_UA, 1u);
+                tc_mma_i8_ts_elect(d_tmem, a_tmem + 32 * j + 24, bdj + 6, TC_IDESC_UA, 1u);
+              }
             }
           }
           tc_commit_elect(empty0 + stage * 8);  // frees the A stage when these MMAs have read it
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const u32 slot = tcount & 1u;
       tc_mbar_wait(tc_smem(pk_full + slot), (tcount >> 1) & 1u);
       const unsigned char* prow = spk + (size_t)slot * TC_BM * row_bytes + (size_t)u * row_bytes;
-      for (int kb = 0; kb < a.kb; kb += 2, ++it) {  // two K blocks (256 dims) per ring stage
+      for (int kb = 0; kb < a.kb; kb += TC_KBPS, ++it) {  // TC_KBPS K blocks (128 dims each) per ring stage
         const u32 s = stage;
         const u32 ph = phase;
         if (++stage == stages) {
@@ -552,10 +555,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tc_mbar_arrive(tc_smem(full_a + s));
           continue;
         }
-        const bool two = kb + 1 < a.kb;
         const uint4 pw = *reinterpret_cast<const uint4*>(prow + kb * 16);  // 128 dims of this row
-        uint4 pw1 = make_uint4(0u, 0u, 0u, 0u);
-        if (two) pw1 = *reinterpret_cast<const uint4*>(prow + kb * 16 + 16);
+        uint4 pwx[TC_KBPS];
+#pragma unroll
+        for (int j = 1; j < TC_KBPS; ++j)
+          pwx[j] = (kb + j < a.kb) ? *reinterpret_cast<const uint4*>(prow + (kb + j) * 16) : make_uint4(0u, 0u, 0u, 0u);
         u32 o[32];
         tc_expand32(pw.x, o);
         tc_expand32(pw.y, o + 8);
@@ -568,14 +572,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         tc_mbar_wait(tc_smem(empty_a + s), ph ^ 1u);
         tc_fence_after();
-        const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + 2 * TC_BN + s * 64;
-        if (two) {
-          u32 o1[32];
-          tc_expand32(pw1.x, o1);
-          tc_expand32(pw1.y, o1 + 8);
-          tc_expand32(pw1.z, o1 + 16);
-          tc_expand32(pw1.w, o1 + 24);
-          tc_st32(taddr + 32, o1);
+        const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + 2 * TC_BN + s * (32 * TC_KBPS);
+#pragma unroll
+        for (int j = 1; j < TC_KBPS; ++j) {
+          if (kb + j < a.kb) {
+            u32 o1[32];
+            tc_expand32(pwx[j].x, o1);
+            tc_expand32(pwx[j].y, o1 + 8);
+            tc_expand32(pwx[j].z, o1 + 16);
+            tc_expand32(pwx[j].w, o1 + 24);
+            tc_st32(taddr + 32 * j, o1);
+          }
         }
         asm volatile(
             "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -942,9 +949,9 @@ static TcSmem tc_smem_layout(int kb, bool packed) {
   const size_t limit = 232448;  // 227 KB opt-in maximum per block
   TcSmem r;
   if (packed) {
-    // A ring lives in tensor memory (8 x 32 columns next to the two 128-column accumulators);
+    // A ring lives in tensor memory (256 columns next to the two 128-column accumulators);
     // shared memory holds B, the packed double buffer and the small state only
-    r.stages = 4;  // x 64 TMEM columns (two K blocks per stage)
+    r.stages = 8 / TC_KBPS;  // x 32 * TC_KBPS TMEM columns (256 columns of A ring in all)
     r.bytes = 1024 + (size_t)kb * TC_TILE_BYTES + 2 * (size_t)TC_BM * kb * 16 + 2 * TC_BN * 4 + 32 * 8 + 64;
     return r;
   }
