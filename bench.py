@@ -371,7 +371,7 @@ def run_gpu_arm(args) -> None:
                   "step, profiles/r1_launches_bench_final_summary.md)",
         "bound": "tensor", "achieved": int8_ops / (filter_ms * 1e-3) / 1e12, "peak": tensor_peak,
         "unit": "TOP/s", "frac": int8_ops / (filter_ms * 1e-3) / 1e12 / tensor_peak,
-        "traffic": 105844480 if (world == 1 and n_local == 1_000_000 and dim == 768 and nq == 256) else None,
+        "traffic": 103592704 if (world == 1 and n_local == 1_000_000 and dim == 768 and nq == 256) else None,
         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, ncu --set full "
                           "(profiles/r1_ncu_full_summary_final.md)",
         "launch_ms": filter_ms, "timing": "CUDA events on the launching stream around the kernel (rr_tc_timing), "
