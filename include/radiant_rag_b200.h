@@ -84,7 +84,8 @@ int rr_hamming_topk(const uint32_t* codes, int64_t n, int32_t words, const uint8
 
 /* ---- Tensor-core (tcgen05 kind::i8, TMEM accumulators, TMA-fed) formulation of the BATCHED
  * stage-1 search.  The packed codes are read as they are (1 bit per dimension from HBM) and
- * expanded to +-1 int8 operand tiles in shared memory; hamming = (32*words - dot) / 2 exactly.
+ * expanded on chip to a 0/255 unsigned-int8 operand in tensor memory; with +-1 int8 queries
+ * hamming = popc(q) - dot / 255 exactly.
  * Same arguments and bit-identical results as rr_hamming_topk, except:
  *   q_pm1     i8 [q, 32*words]  the query codes expanded by rr_unpack_codes_pm1(qcodes, q,
  *             4*words, 32*words, ...);

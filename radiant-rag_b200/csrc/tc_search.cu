@@ -5,28 +5,30 @@
 // queries are +-1 int8, and  hamming = popc(q) - dot / 255  exactly (SURVEY.md section 7
 // H1b: above ~3 queries per pass the POPC pipe, not HBM, bounds the popcount formulation).
 //
-// Kernel (one CTA per SM, 320 threads, warp-specialised):
-//   warp 0      TMA producer: the CTA's 128 queries (B operand, K-major, SWIZZLE_128B) are
-//               loaded once and stay resident in shared memory.  int8 mode: corpus tiles of
-//               128 rows x 128 bytes of K (A operand) stream through an mbarrier ring of TMA
-//               boxes.  Packed mode: each 128-row tile of packed codes is ONE contiguous
-//               bulk copy into a double buffer.
-//   warps 6-9   (packed mode) expand the tile's sign bits K block by K block (multiply + PRMT
-//               sign-replicate, 5 instructions per 8 dims) and store them with tcgen05.st into an
-//               A-operand ring that lives in TENSOR MEMORY, then signal the MMA warp.
-//   warp 1      allocates TMEM and issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128,
-//               K=32 per instruction); two 128x128 int32 accumulators in TMEM are
-//               double-buffered against the epilogue.
-//   warps 2-5   epilogue: tcgen05.ld 32x32b.x32 brings a thread's row of 32 query scores to
-//               registers; a score is appended to its query's list only when it reaches the
-//               query's threshold tau_q.
+// Kernel (one CTA per SM, 448 threads, warp-specialised):
+//   warp 0        TMA producer: the CTA's 128 queries (B operand, K-major, SWIZZLE_128B) are
+//                 loaded once and stay resident in shared memory.  int8 mode: corpus tiles of
+//                 128 rows x 128 bytes of K (A operand) stream through an mbarrier ring of TMA
+//                 boxes.  Packed mode: each 128-row tile of packed codes is ONE contiguous
+//                 bulk copy into a double buffer.
+//   warps 6-9     (packed mode) expand the tile's sign bits (multiply + PRMT sign-replicate,
+//                 5 instructions per 8 dims) and store them with tcgen05.st into an A-operand
+//                 ring that lives in TENSOR MEMORY (TC_KBPS K blocks per stage), then signal
+//                 the MMA warp.
+//   warp 1        allocates TMEM and issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128,
+//                 K=32 per instruction); two 128x128 int32 accumulators in TMEM are
+//                 double-buffered against the epilogue.
+//   warps 2-5,    epilogue, two warps per TMEM lane quarter (64 query columns each):
+//   10-13         tcgen05.ld 32x32b.x32 brings a thread's row of 32 query scores to registers.
+//                 Filter mode: the accumulators start at -tau_q (written by these warps), so a
+//                 hit is a clear sign bit; hits are appended to the query's list.
 // Exact top-k without materialising Q x N scores (164 GB in config 4):
-//   pass 0  the same kernel in DENSE mode over a strided sample of row tiles (1/32 of the
-//           rows) -> per-query k-th best sample score tau_q (select_keys32 on the samples).
-//           At least k rows score >= tau_q in the full set, so
-//   pass 1  the FILTER pass over all rows keeps exactly the rows with score >= tau_q
-//           (about 32*k per query) and
-//   pass 2  block_select_sorted takes the exact top-k by (score desc, row asc).
+//   pass 0  (EPI_COLMAX) the same kernel over a strided sample of row tiles keeps the best score
+//           per (CTA, row slot, query); tc_tau_kernel takes a score tau_q that at least k of
+//           those slots reach.  At least k rows score >= tau_q in the full set, so
+//   pass 1  (EPI_FILTER) over all rows keeps exactly the rows with score >= tau_q
+//           (about stride*k per query) and
+//   pass 2  tc_select_lists_kernel takes the exact top-k by (score desc, row asc).
 // A list that outgrows its capacity raises an overflow counter and the caller falls back
 // to the CUDA-core path (never observed on the synthetic corpora; guards adversarial data).
 #include <cuda.h>

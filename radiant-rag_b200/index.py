@@ -105,8 +105,8 @@ class DenseIndex:
         capacity: int = 0,
         store_pm1: bool = False,
     ) -> None:
-        """store_pm1: deprecated no-op (the tensor-core scan now expands the packed codes in
-        shared memory and needs no extra copy in HBM)."""
+        """store_pm1: deprecated no-op (the tensor-core scan expands the packed codes on chip
+        and needs no extra copy in HBM)."""
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         if self.device.type != "cuda":
             raise _lib.RadiantB200Error("DenseIndex needs a CUDA device; there is no CPU fallback")
@@ -281,9 +281,10 @@ class DenseIndex:
                      ) -> Tuple[torch.Tensor, torch.Tensor]:
         """Exact top-k by (dist asc, row asc).  -> (dist int32 [q,k], idx int64 [q,k]).
 
-        Batches of >= tc_min_queries run on the tensor cores (packed codes expanded to +-1
-        int8 operand tiles in shared memory); both paths return identical results.  The tensor-core path keeps, per
-        query, the rows that beat a sampled bound in a bounded list: if a list overflows
+        Batches of >= tc_min_queries run on the tensor cores (packed codes expanded on chip
+        to a 0/255 u8 operand in tensor memory); both paths return identical results.  The
+        tensor-core path keeps, per query, the rows that beat a sampled bound in a bounded list:
+        if a list overflows
         (adversarial data) the call is redone on the POPC path.  check_overflow=False skips
         that host-side check (one device sync) and accumulates the counter in
         ``tc_overflow_total()`` for the caller to verify later."""
