@@ -95,6 +95,34 @@ def test_bm25_zipf_vs_oracle(n_docs, v, tile, k):
         assert (idx[qi, m:].cpu().numpy() == -1).all()
 
 
+@pytest.mark.parametrize("interleave", [True, False])
+def test_bm25_long_queries_many_tiles(interleave):
+    """70-token queries (three blocks of segment bounds), repeats and unknown tokens mixed in,
+    many small tiles so that the cross-tile bound path is the common one, k above and below the
+    number of matching documents; with and without the bank-interleaved segment order."""
+    require_gpu()
+    n_docs, v = 40_000, 3000
+    ptr, toks = synthetic.zipf_corpus(n_docs, v, seed=99, mean_len=40)
+    orc = BM25Oracle(ptr, toks, v)
+    bm = Bm25DeviceIndex.build(ptr, toks, v, orc.idf, orc.avgdl, orc.k1, orc.b, device=0, tile_docs=512,
+                               bank_interleave=interleave)
+    rng = np.random.default_rng(5)
+    qt = synthetic.zipf_queries(24, 70, v, seed=99)
+    qt[:, 5::11] = -1                         # unknown tokens sprinkled in
+    qt[3, 20:50] = qt[3, 0]                   # one token repeated 30 times
+    qt[4, :] = np.int32(v - 1)                # a rare token only
+    qt[5, 1:] = -1                            # single known token
+    for k in (5, 300):
+        idx, score, count = bm.search_batch(qt, k)
+        torch.cuda.synchronize()
+        for qi in range(qt.shape[0]):
+            rows, sc = orc.search(qt[qi].tolist(), k)
+            m = int(count[qi])
+            assert m == rows.size, (k, qi)
+            assert idx[qi, :m].cpu().tolist() == rows.tolist(), (k, qi)
+            assert score[qi, :m].cpu().tolist() == sc.tolist(), (k, qi)
+
+
 def test_bm25_impacts_kernel_bit_exact():
     require_gpu()
     rng = np.random.default_rng(3)

@@ -68,6 +68,8 @@ def _both_paths(corpus, queries, k, tags=None, mask=0, value=0, row_base=0):
     (200, 128, 16, 50),          # smaller than one sample
     (30_000, 100, 40, 17),       # dim not a multiple of 32 (padded to 128 bits)
     (9_000, 640, 33, 64),        # words = 20 -> 5 K blocks
+    (12_000, 896, 20, 30),       # 7 K blocks: a full and a partial tensor-memory ring stage
+    (6_000, 512, 48, 25),        # 4 K blocks: exactly one ring stage per tile
 ])
 def test_tc_hamming_equals_popc_and_oracle(n, dim, q, k):
     require_gpu()
