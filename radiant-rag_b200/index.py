@@ -197,6 +197,76 @@ class DenseIndex:
         self.n = hi
         return lo, hi
 
+    def add_quantized(self, codes: ArrayLike, int8_rows: Optional[ArrayLike] = None,
+                      f32_rows: Optional[ArrayLike] = None, tags: Optional[ArrayLike] = None) -> Tuple[int, int]:
+        """Append rows that are ALREADY quantised, byte for byte as the reference stores them
+        (wire formats): codes u8 [m, ceil(dim/8)] = ``np.packbits`` rows, the payload
+        of the ``...:doc_binary:{id}`` side keys (redis_store.py:329-338); int8_rows i8 [m, dim], the
+        ``...:doc_int8:{id}`` payload (:339-349); f32_rows the float32 embeddings if kept.
+        Nothing is recomputed.  Returns the local row range [lo, hi)."""
+        self._activate()
+        c = to_device(codes, self.device, torch.uint8)
+        if c.ndim == 1:
+            c = c[None, :]
+        nbytes = (self.dim + 7) // 8
+        if c.shape[1] != nbytes:
+            raise ValueError(f"packed code rows must have {nbytes} bytes for dim {self.dim}, got {c.shape[1]}")
+        m = c.shape[0]
+        if self.store_int8 and int8_rows is None:
+            raise ValueError("this index stores int8 rows: int8_rows is required")
+        if self.store_f32 and f32_rows is None:
+            raise ValueError("this index stores float32 rows: f32_rows is required")
+        lo, hi = self.n, self.n + m
+        self._reserve(hi)
+        self.codes[lo:hi].zero_()  # row padding up to 16 bytes must be 0
+        self.codes[lo:hi, :nbytes].copy_(c)
+        if self.store_int8:
+            r = to_device(int8_rows, self.device, torch.int8).reshape(m, self.dim)
+            self.int8[lo:hi].copy_(r)
+        if self.store_f32:
+            self.f32[lo:hi].copy_(to_device(f32_rows, self.device, torch.float32).reshape(m, self.dim))
+        if tags is None:
+            self.tags[lo:hi].fill_(LEVEL_CHILD)
+        else:
+            self.tags[lo:hi].copy_(to_device(tags, self.device, torch.uint8))
+            self.tags_uniform = False
+        self.n = hi
+        return lo, hi
+
+    def save(self, path: str) -> None:
+        """Persist the shard: one uncompressed .npz with the packed codes, the
+        int8 / float32 rows that are kept, tags, calibration ranges and the scalar settings."""
+        self._activate()
+        torch.cuda.current_stream(self.device).synchronize()
+        n = self.n
+        arrays = {
+            "dim": np.int64(self.dim), "row_base": np.int64(self.row_base), "n": np.int64(n),
+            "codes": self.codes[:n, : (self.dim + 7) // 8].cpu().numpy() if n else np.zeros((0, (self.dim + 7) // 8), np.uint8),
+            "tags": self.tags[:n].cpu().numpy() if n else np.zeros((0,), np.uint8),
+        }
+        if self.store_int8:
+            arrays["int8"] = self.int8[:n].cpu().numpy() if n else np.zeros((0, self.dim), np.int8)
+        if self.store_f32:
+            arrays["f32"] = self.f32[:n].cpu().numpy() if n else np.zeros((0, self.dim), np.float32)
+        if self.ranges is not None:
+            arrays["ranges"] = self.ranges.cpu().numpy()
+        with open(path, "wb") as fh:
+            np.savez(fh, **arrays)
+
+    @classmethod
+    def load(cls, path: str, device: Union[int, str, torch.device] = 0) -> "DenseIndex":
+        """Rebuild a shard saved by ``save`` on `device` (rows are copied, not re-quantised)."""
+        with np.load(path) as z:
+            dim, n = int(z["dim"]), int(z["n"])
+            idx = cls(dim, device=device, store_int8="int8" in z.files, store_f32="f32" in z.files,
+                      int8_ranges=z["ranges"] if "ranges" in z.files else None, row_base=int(z["row_base"]),
+                      capacity=n)
+            if n:
+                idx.add_quantized(z["codes"], z["int8"] if "int8" in z.files else None,
+                                  z["f32"] if "f32" in z.files else None, z["tags"])
+                idx.tags_uniform = bool((z["tags"] == LEVEL_CHILD).all())
+        return idx
+
     def set_row(self, row: int, emb: ArrayLike, tag: int) -> None:
         """Overwrite one existing row (upsert of a known doc_id)."""
         self._activate()

@@ -162,6 +162,47 @@ class B200VectorStore(BaseVectorStore):
                 self._index.add(np.stack(new_rows), np.asarray(new_tags, dtype=np.uint8))
             return len(documents)
 
+    def import_quantized_batch(self, documents: List[Dict[str, Any]]) -> int:
+        """Bulk-load documents whose quantised rows already exist in the reference's wire format
+        (SURVEY.md 8f): each dict has ``doc_id``, ``content``, ``meta`` and ``binary`` = the raw
+        bytes of the ``...:doc_binary:{id}`` key (np.packbits of the embedding, D/8 bytes,
+        redis_store.py:329-338), optionally ``int8`` = the raw bytes of ``...:doc_int8:{id}``
+        (D bytes, :339-349) and ``embedding`` (float32, needed when the index keeps float rows).
+        The payloads are stored as they are; new doc_ids only."""
+        if not documents:
+            return 0
+        with self._lock:
+            first = documents[0]
+            dim = self._embedding_dim or (len(first["embedding"]) if first.get("embedding") is not None
+                                          else len(first["binary"]) * 8)
+            self._ensure_index(dim)
+            idx = self._index
+            codes, i8, f32, tags = [], [], [], []
+            for d in documents:
+                doc_id = d["doc_id"]
+                if doc_id in self._row_of:
+                    raise ValueError(f"import_quantized_batch: {doc_id} is already indexed (use upsert)")
+                content, meta, level, lang = self._prep_doc(d["content"], d.get("meta"), "child")
+                codes.append(np.frombuffer(d["binary"], dtype=np.uint8))
+                if idx.store_int8:
+                    if d.get("int8") is None:
+                        raise ValueError(f"{doc_id}: the index keeps int8 rows but no int8 payload was given")
+                    i8.append(np.frombuffer(d["int8"], dtype=np.int8))
+                if idx.store_f32:
+                    if d.get("embedding") is None:
+                        raise ValueError(f"{doc_id}: the index keeps float32 rows but no embedding was given")
+                    f32.append(np.asarray(d["embedding"], dtype=np.float32))
+                if self._inner is not None:
+                    self._inner.upsert_doc_only(doc_id, content, meta)
+                else:
+                    self._store_doc(doc_id, content, meta)
+                tags.append(make_tag(normalize_doc_level(level) or "child", self._langs.id_for(lang, create=True)))
+                self._row_of[doc_id] = idx.n + len(codes) - 1
+                self._id_of.append(doc_id)
+            idx.add_quantized(np.stack(codes), np.stack(i8) if i8 else None, np.stack(f32) if f32 else None,
+                              np.asarray(tags, dtype=np.uint8))
+            return len(documents)
+
     def upsert_doc_only_batch(self, documents: List[Dict[str, Any]]) -> int:
         for d in documents:
             self.upsert_doc_only(d["doc_id"], d["content"], d.get("meta"))

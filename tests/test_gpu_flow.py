@@ -258,3 +258,47 @@ def test_graph_replay_equals_eager_search():
         for g, w in zip(got, want):
             assert torch.equal(g, w)
     assert index.tc_overflow_total() == 0
+
+
+def test_wire_format_import_and_index_persistence(tmp_path):
+    """rows taken byte for byte from the reference's side-key payloads
+    (np.packbits bytes, int8 bytes) give the same index as quantising on device, the shard
+    survives save -> load, and the store's bulk import answers like a store built by upsert."""
+    require_gpu()
+    from radiant_rag_b200.index import DenseIndex
+    n, dim = 5_000, 384
+    corpus = synthetic.normal_unit_rows(n, dim, seed=12)
+    queries = synthetic.normal_unit_rows(24, dim, seed=13)
+    ranges = oracle.calculate_int8_ranges(corpus)
+    codes, i8 = oracle.quantize_ubinary(corpus), oracle.quantize_int8(corpus, ranges)
+    a, _ = build_index(corpus, int8=True, f32=True)
+    b = DenseIndex(dim, device=0, store_int8=True, store_f32=True, int8_ranges=ranges, row_base=0)
+    assert b.add_quantized(codes, i8, corpus) == (0, n)
+    assert torch.equal(a.codes[:n], b.codes[:n]) and torch.equal(a.int8[:n], b.int8[:n])
+    want = a.search_quantized(queries, 10, 4.0)
+    for got in (b.search_quantized(queries, 10, 4.0),):
+        assert all(torch.equal(g, w) for g, w in zip(got, want))
+    path = str(tmp_path / "shard.npz")
+    b.save(path)
+    c = DenseIndex.load(path, device=0)
+    assert (c.n, c.dim, c.row_base, c.store_int8, c.store_f32) == (n, dim, 0, True, True)
+    assert all(torch.equal(g, w) for g, w in zip(c.search_quantized(queries, 10, 4.0), want))
+    assert all(torch.equal(g, w) for g, w in zip(c.search_exact(queries, 7), a.search_exact(queries, 7)))
+    with pytest.raises(ValueError):
+        b.add_quantized(codes[:, :-1], i8, corpus)   # wrong packed width
+
+    qc = QuantizationConfig(enabled=True, precision="both")
+    ref_store = B200VectorStore(embedding_dim=dim, quantization=qc, int8_ranges=ranges)
+    ref_store.upsert_batch([{"doc_id": f"d{r}", "content": f"c{r}", "embedding": corpus[r], "meta": {}}
+                            for r in range(400)])
+    imp_store = B200VectorStore(embedding_dim=dim, quantization=qc, int8_ranges=ranges)
+    assert imp_store.import_quantized_batch(
+        [{"doc_id": f"d{r}", "content": f"c{r}", "meta": {}, "binary": codes[r].tobytes(), "int8": i8[r].tobytes(),
+          "embedding": corpus[r]} for r in range(400)]) == 400
+    for qi in range(4):
+        got = imp_store.retrieve_by_embedding_quantized(queries[qi].tolist(), 5)
+        exp = ref_store.retrieve_by_embedding_quantized(queries[qi].tolist(), 5)
+        assert [(d.doc_id, s) for d, s in got] == [(d.doc_id, s) for d, s in exp]
+    with pytest.raises(ValueError):
+        imp_store.import_quantized_batch([{"doc_id": "d1", "content": "x", "meta": {}, "binary": codes[1].tobytes(),
+                                           "int8": i8[1].tobytes(), "embedding": corpus[1]}])
