@@ -22,6 +22,7 @@ namespace rr {
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ROWS = 2;  // candidate rows a warp scores per iteration
+constexpr int RS_UNROLL = 3;  // column groups (of 32 float4) whose loads are issued together
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
@@ -175,18 +176,32 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_f32_kernel(const RescoreAr
       for (int r = 0; r < RS_ROWS; ++r)
         rp[r] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.emb) + (size_t)(ok[r] ? loc[r] : 0) * a.dim);
       const float4* q4 = reinterpret_cast<const float4*>(sq);
-      for (int v = lane; v < (a.dim >> 2); v += 32) {
-        float4 e[RS_ROWS];
+      // RS_UNROLL column groups per step: all RS_ROWS * RS_UNROLL 128-bit loads are issued before the
+      // first add (the gather is latency-bound); the adds keep their ascending column order per row
+      const int nv = a.dim >> 2;
+      for (int vb = lane; vb < nv; vb += 32 * RS_UNROLL) {
+        float4 e[RS_UNROLL][RS_ROWS];
 #pragma unroll
-        for (int r = 0; r < RS_ROWS; ++r) e[r] = ok[r] ? __ldg(rp[r] + v) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 w = q4[v];
-        const double wx = (double)w.x, wy = (double)w.y, wz = (double)w.z, ww = (double)w.w;
+        for (int u = 0; u < RS_UNROLL; ++u) {
+          const int v = vb + 32 * u;
 #pragma unroll
-        for (int r = 0; r < RS_ROWS; ++r) {  // same order of additions per row as one row at a time
-          acc[r] += wx * (double)e[r].x;
-          acc[r] += wy * (double)e[r].y;
-          acc[r] += wz * (double)e[r].z;
-          acc[r] += ww * (double)e[r].w;
+          for (int r = 0; r < RS_ROWS; ++r)
+            e[u][r] = (ok[r] && v < nv) ? __ldg(rp[r] + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < RS_UNROLL; ++u) {
+          const int v = vb + 32 * u;
+          if (v < nv) {
+            const float4 w = q4[v];
+            const double wx = (double)w.x, wy = (double)w.y, wz = (double)w.z, ww = (double)w.w;
+#pragma unroll
+            for (int r = 0; r < RS_ROWS; ++r) {  // same order of additions per row as one row at a time
+              acc[r] += wx * (double)e[u][r].x;
+              acc[r] += wy * (double)e[u][r].y;
+              acc[r] += wz * (double)e[u][r].z;
+              acc[r] += ww * (double)e[u][r].w;
+            }
+          }
         }
       }
 #pragma unroll
