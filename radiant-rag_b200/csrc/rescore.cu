@@ -21,8 +21,14 @@ namespace rr {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ROWS = 2;  // candidate rows a warp scores per iteration
-constexpr int RS_UNROLL = 3;  // column groups (of 32 float4) whose loads are issued together
+#ifndef RR_RS_ROWS
+#define RR_RS_ROWS 2
+#endif
+#ifndef RR_RS_UNROLL
+#define RR_RS_UNROLL 3
+#endif
+constexpr int RS_ROWS = RR_RS_ROWS;      // candidate rows a warp scores per iteration
+constexpr int RS_UNROLL = RR_RS_UNROLL;  // column groups (of 32 float4) whose loads are issued together
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
 #pragma unroll
