@@ -326,9 +326,11 @@ class DenseIndex:
                   idx.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
         return dist, idx
 
-    def _hamming_topk_tc(self, qcodes: torch.Tensor, k: int, tag_mask: int, tag_value: int
+    def _hamming_topk_tc(self, qcodes: torch.Tensor, k: int, tag_mask: int, tag_value: int,
+                         ovf: Optional[torch.Tensor] = None
                          ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Tensor-core path; also returns the device overflow counter of this call."""
+        """Tensor-core path; also returns the device overflow counter of this call (`ovf`: an
+        existing counter the kernel adds to, instead of a fresh zeroed one)."""
         q = qcodes.shape[0]
         dpad = self.words * 32  # padded width: padding bits are 0 (-1) in rows and queries alike
         q_pm1 = torch.empty((q, dpad), dtype=torch.int8, device=self.device)
@@ -336,7 +338,8 @@ class DenseIndex:
                   _stream())
         dist = torch.empty((q, k), dtype=torch.int32, device=self.device)
         idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
-        ovf = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if ovf is None:
+            ovf = torch.zeros(1, dtype=torch.int32, device=self.device)
         lib = _lib.load()
         ws_bytes = lib.rr_tc_search_workspace_bytes(self.n, q, k)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
@@ -358,20 +361,17 @@ class DenseIndex:
         (adversarial data) the call is redone on the POPC path.  check_overflow=False skips
         that host-side check (one device sync) and accumulates the counter in
         ``tc_overflow_total()`` for the caller to verify later."""
-        dist, idx, ovf = self._hamming_topk_auto(qcodes, k, tag_mask, tag_value, use_tc)
-        if ovf is None:
-            return dist, idx
-        if check_overflow:
-            if int(ovf.item()) != 0:
-                return self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
-        else:
-            self._defer_overflow(ovf)
+        dist, idx, ovf = self._hamming_topk_auto(qcodes, k, tag_mask, tag_value, use_tc,
+                                                 accumulate=not check_overflow)
+        if ovf is not None and check_overflow and int(ovf.item()) != 0:
+            return self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
         return dist, idx
 
     def _hamming_topk_auto(self, qcodes: torch.Tensor, k: int, tag_mask: int, tag_value: int,
-                           use_tc: Optional[bool] = None):
+                           use_tc: Optional[bool] = None, accumulate: bool = False):
         """-> (dist, idx, ovf): ovf is the device overflow counter of a tensor-core call, None
-        when the POPC path ran (always exact)."""
+        when the POPC path ran (always exact).  accumulate: the kernel adds straight into the
+        index's running counter (``tc_overflow_total``) - no per-call counter, no extra launches."""
         self._activate()
         q = qcodes.shape[0]
         if use_tc is None:
@@ -379,12 +379,11 @@ class DenseIndex:
         if not use_tc or self.n == 0:
             dist, idx = self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
             return dist, idx, None
+        if accumulate:
+            if self._tc_overflow is None:
+                self._tc_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+            return self._hamming_topk_tc(qcodes, k, tag_mask, tag_value, ovf=self._tc_overflow)
         return self._hamming_topk_tc(qcodes, k, tag_mask, tag_value)
-
-    def _defer_overflow(self, ovf: torch.Tensor) -> None:
-        if self._tc_overflow is None:
-            self._tc_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
-        self._tc_overflow += ovf
 
     def tc_overflow_total(self) -> int:
         """Overflow events of tensor-core calls made with check_overflow=False (0 = all exact)."""
@@ -468,7 +467,8 @@ class DenseIndex:
         # Stage 2 is queued behind stage 1 before the tensor-core overflow counter is read, so
         # the (single) host sync of a checked call sits at its end and the GPU never idles
         # between the stages; an overflow (adversarial data) redoes the call on the POPC path.
-        _dist, cand, ovf = self._hamming_topk_auto(qc, candidate_k, tag_mask, tag_value)
+        _dist, cand, ovf = self._hamming_topk_auto(qc, candidate_k, tag_mask, tag_value,
+                                                   accumulate=not check_overflow)
 
         def stage2(cand_rows):
             if not use_rescoring:
@@ -480,13 +480,9 @@ class DenseIndex:
             return idx, score, count
 
         out = stage2(cand)
-        if ovf is not None:
-            if check_overflow:
-                if int(ovf.item()) != 0:
-                    _dist, cand = self._hamming_topk_popc(qc, candidate_k, tag_mask, tag_value)
-                    out = stage2(cand)
-            else:
-                self._defer_overflow(ovf)
+        if ovf is not None and check_overflow and int(ovf.item()) != 0:
+            _dist, cand = self._hamming_topk_popc(qc, candidate_k, tag_mask, tag_value)
+            out = stage2(cand)
         return out
 
     def search_exact(self, queries: ArrayLike, top_k: int, min_similarity: float = 0.0,
