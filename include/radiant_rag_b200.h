@@ -212,6 +212,14 @@ int rr_rrf_fuse(const int64_t* run_idx, const int32_t* run_off_host, int32_t n_r
 /* (dist asc, idx asc) */
 int rr_merge_hamming(const int32_t* in_dist, const int64_t* in_idx, int32_t q, int32_t n_in,
                      int32_t k, int32_t* out_dist, int64_t* out_idx, void* stream);
+/* One-collective form of the Hamming exchange: rr_pack_hamming turns a shard's (dist, global row)
+ * lists into int64 keys (dist << 40 | row, -1 = padding) so that ONE all_gather moves them;
+ * rr_merge_hamming_gathered merges the gathered buffer in its native layout
+ * in_keys i64 [n_shards][q][k_in] (no transpose) by (dist asc, row asc) -> [q, k]. */
+int rr_pack_hamming(const int32_t* dist, const int64_t* idx, int64_t n, int64_t* out_keys,
+                    void* stream);
+int rr_merge_hamming_gathered(const int64_t* in_keys, int32_t n_shards, int32_t q, int32_t k_in,
+                              int32_t k, int32_t* out_dist, int64_t* out_idx, void* stream);
 /* (score desc, idx asc), float64 scores (BM25) */
 int rr_merge_scores_f64(const double* in_score, const int64_t* in_idx, int32_t q,
                         int32_t n_in, int32_t k, double* out_score, int64_t* out_idx,

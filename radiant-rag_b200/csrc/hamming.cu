@@ -483,6 +483,43 @@ extern "C" int rr_hamming_topk(const uint32_t* codes, int64_t n, int32_t words, 
 }
 
 // ---- 8(e): merges of the allgathered per-shard lists --------------------------------
+namespace rr {
+// Hamming lists as they come out of ONE all_gather: keys [shards][q][k_in], key = dist << 40 | row,
+// negative = padding.  No transpose copy: the CTA of query q walks its k_in entries of every shard.
+__global__ void __launch_bounds__(MERGE_THREADS)
+    merge_hamming_gathered_kernel(const long long* keys, int n_shards, int q_total, int k_in, int k, int cap,
+                                  int* out_dist, long long* out_idx) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
+  u32* s_k2 = reinterpret_cast<u32*>(s_k1 + cap);
+  __shared__ SelectScratch<MERGE_THREADS> sc;
+  const int q = blockIdx.x;
+  auto get = [&](long long i, u64& x, u32& y) {
+    const int g = (int)(i / k_in);
+    const int j = (int)(i - (long long)g * k_in);
+    const long long key = keys[((size_t)g * q_total + q) * k_in + j];
+    x = key < 0 ? K1_INVALID : (u64)key;
+    y = key < 0 ? K2_INVALID : 0u;
+  };
+  const int m = block_select_sorted<MERGE_THREADS>(get, (long long)n_shards * k_in, k, s_k1, s_k2, cap, sc);
+  for (int j = threadIdx.x; j < k; j += MERGE_THREADS) {
+    const bool have = j < m;
+    merge_write<MERGE_HAMMING_PACKED>(out_dist, out_idx, (size_t)q * k + j, have, have ? s_k1[j] : 0,
+                                      have ? s_k2[j] : 0, 0);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    pack_hamming_kernel(const int* dist, const long long* idx, long long n, long long* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const long long r = idx[i];
+    out[i] = r < 0 ? -1LL : (((long long)dist[i] << 40) | r);
+  }
+}
+
+}  // namespace rr
+
 extern "C" int rr_merge_hamming(const int32_t* in_dist, const int64_t* in_idx, int32_t q,
                                 int32_t n_in, int32_t k, int32_t* out_dist, int64_t* out_idx,
                                 void* stream) {
@@ -492,6 +529,29 @@ extern "C" int rr_merge_hamming(const int32_t* in_dist, const int64_t* in_idx, i
   return launch_merge_typed<MERGE_HAMMING_PACKED>(in_dist, (const long long*)in_idx, q, n_in, k,
                                                   out_dist, (long long*)out_idx, nullptr,
                                                   (cudaStream_t)stream);
+}
+
+extern "C" int rr_pack_hamming(const int32_t* dist, const int64_t* idx, int64_t n, int64_t* out_keys,
+                               void* stream) {
+  RR_CHECK_ARG(n >= 0, "negative size");
+  if (n == 0) return RR_OK;
+  RR_CHECK_ARG(dist && idx && out_keys, "null pointer");
+  pack_hamming_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      dist, (const long long*)idx, n, (long long*)out_keys);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
+extern "C" int rr_merge_hamming_gathered(const int64_t* in_keys, int32_t n_shards, int32_t q, int32_t k_in,
+                                         int32_t k, int32_t* out_dist, int64_t* out_idx, void* stream) {
+  if (q == 0) return RR_OK;
+  RR_CHECK_ARG(in_keys && out_dist && out_idx, "null pointer");
+  RR_CHECK_ARG(q > 0 && n_shards > 0 && k_in > 0 && k >= 1 && k <= RR_MAX_K, "bad size");
+  const int cap = merge_cap(k);
+  merge_hamming_gathered_kernel<<<q, MERGE_THREADS, (size_t)cap * 12, (cudaStream_t)stream>>>(
+      (const long long*)in_keys, n_shards, q, k_in, k, cap, out_dist, (long long*)out_idx);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
 }
 
 extern "C" int rr_merge_scores_f64(const double* in_score, const int64_t* in_idx, int32_t q,

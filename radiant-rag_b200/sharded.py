@@ -5,7 +5,8 @@ cut into contiguous row blocks ``[g*N/G, (g+1)*N/G)``; queries are replicated.  
 candidate lists cross NVLink:
 
   dense, exact single-index semantics in two small steps
-    1. local Hamming top-k'           -> all_gather [G, Q, k'] -> merge (dist asc, row asc)
+    1. local Hamming top-k'           -> ONE all_gather [G, Q, k'] of packed (dist << 40 | row)
+                                         keys -> merge (dist asc, row asc)
     2. each shard scores the global candidates it OWNS (-inf elsewhere)
                                       -> all_reduce(MAX) [Q, k'] -> rank, cut, filter
   BM25     local top-k (global idf/avgdl baked into the shard's impacts)
@@ -58,6 +59,23 @@ class GpuShardOps:
                   out_d.data_ptr(), out_i.data_ptr(), _stream())
         return out_d, out_i
 
+    def pack_hamming(self, dist_loc: torch.Tensor, idx_loc: torch.Tensor) -> torch.Tensor:
+        """(dist int32, global row int64) [Q, k] -> int64 keys dist << 40 | row (-1 = padding):
+        the two lists of a shard travel in ONE collective."""
+        keys = torch.empty(idx_loc.shape, dtype=torch.int64, device=self.device)
+        _lib.call("rr_pack_hamming", dist_loc.data_ptr(), idx_loc.data_ptr(), idx_loc.numel(),
+                  keys.data_ptr(), _stream())
+        return keys
+
+    def merge_hamming_gathered(self, keys_all: torch.Tensor, k: int):
+        """keys_all int64 [G, Q, k'] exactly as all_gather_into_tensor leaves it (no transpose)."""
+        g, q, k_in = keys_all.shape
+        out_d = torch.empty((q, k), dtype=torch.int32, device=self.device)
+        out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        _lib.call("rr_merge_hamming_gathered", keys_all.data_ptr(), g, q, k_in, k, out_d.data_ptr(),
+                  out_i.data_ptr(), _stream())
+        return out_d, out_i
+
     def score_candidates(self, queries_f32, cand_idx, prefer_int8=True):
         return self.index.score_candidates(queries_f32, cand_idx, prefer_int8)
 
@@ -95,6 +113,18 @@ class GpuShardOps:
         return out_i, out_s
 
 
+def _gather_raw(t: torch.Tensor, group: Optional[Any]) -> torch.Tensor:
+    """[Q, k] on every rank -> [G, Q, k] on every rank (the collective's native layout)."""
+    world = dist.get_world_size(group)
+    t = t.contiguous()
+    buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
+    if t.is_cuda:
+        dist.all_gather_into_tensor(buf, t, group=group)
+    else:  # gloo (CPU tests of the host logic)
+        dist.all_gather(list(buf.unbind(0)), t, group=group)
+    return buf
+
+
 def _gather_lists(t: torch.Tensor, group: Optional[Any]) -> torch.Tensor:
     """[Q, k] on every rank -> [Q, G*k] (rank-major within a query) on every rank."""
     world = dist.get_world_size(group)
@@ -129,7 +159,11 @@ class ShardedDenseSearch:
         candidate_k = max(1, min(candidate_k, _lib.RR_MAX_K))
         d_loc, i_loc = ops.hamming_topk(qc, candidate_k, tag_mask, tag_value, check_overflow=check_overflow)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
-        if world > 1:
+        if world > 1 and hasattr(ops, "pack_hamming"):
+            # (dist, row) packed into one int64 key per entry: one collective, merged in place
+            keys_all = _gather_raw(ops.pack_hamming(d_loc, i_loc), self.group)
+            _d, cand = ops.merge_hamming_gathered(keys_all, candidate_k)
+        elif world > 1:
             d_all = _gather_lists(d_loc, self.group)
             i_all = _gather_lists(i_loc, self.group)
             _d, cand = ops.merge_hamming(d_all, i_all, candidate_k)

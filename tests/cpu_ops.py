@@ -62,6 +62,22 @@ class CpuShardOps:
             out_c[r] = order.size
         return torch.from_numpy(out_i), torch.from_numpy(out_s), torch.from_numpy(out_c)
 
+    def pack_hamming(self, dist_loc, idx_loc):
+        d, i = dist_loc.numpy().astype(np.int64), idx_loc.numpy()
+        return torch.from_numpy(np.where(i >= 0, (d << 40) | i, -1))
+
+    def merge_hamming_gathered(self, keys_all, k):
+        keys = keys_all.numpy()                      # [G, Q, k']
+        g, q, k_in = keys.shape
+        out_d = np.full((q, k), 0x7FFFFFFF, np.int32)
+        out_i = np.full((q, k), -1, np.int64)
+        for r in range(q):
+            kk = np.sort(keys[:, r, :].reshape(-1))
+            kk = kk[kk >= 0][:k]                     # key order == (dist asc, row asc)
+            out_d[r, : kk.size] = (kk >> 40).astype(np.int32)
+            out_i[r, : kk.size] = kk & ((1 << 40) - 1)
+        return torch.from_numpy(out_d), torch.from_numpy(out_i)
+
     def search_int8_exact(self, queries_i8, top_k, tag_mask=0, tag_value=0):
         r, sc = oracle.int8_exact_topk(np.asarray(queries_i8), self.rows, top_k)
         r = np.where(r >= 0, r + self.row_base, -1)

@@ -217,6 +217,10 @@ def test_row_sharded_emulated_on_one_gpu():
     _d, cand = shards[0].merge_hamming(d_all, i_all, 40)
     _sd, s_cand = single.hamming_topk(qc, 40)
     assert torch.equal(cand, s_cand)
+    # one-collective form: packed keys in the gathered [G, Q, k'] layout, merged without a transpose
+    keys_all = torch.stack([s.pack_hamming(l[0], l[1]) for s, l in zip(shards, lists)]).contiguous()
+    pd, pc = shards[0].merge_hamming_gathered(keys_all, 40)
+    assert torch.equal(pc, cand) and torch.equal(pd, _d)
     scores = torch.stack([s.score_candidates(qf, cand) for s in shards]).max(dim=0).values  # all_reduce(MAX)
     idx, score, count = shards[0].rank_scored(scores, cand, top_k, 0.0)
     assert torch.equal(idx, s_idx) and torch.equal(score, s_score) and torch.equal(count, s_count)
