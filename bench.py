@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py - hybrid retrieval queries/sec @ top-10 on the hot path (BASELINE.json).
 
-Workload (N GPUs, strong scaling): BASELINE config 2 - 1M x 768-dim corpus, binary Hamming
-scan -> float32 rescore of the top-200 candidates -> top-10, batch of 256 queries, synthetic
-counter-based data generated on device.  With --gpus N the corpus is row-sharded over N
-ranks (torchrun, NCCL): local scan -> all_gather of k' candidates -> merge -> owner-only
-scoring -> all_reduce(MAX) -> rank.
+Workload = BASELINE config 3: BM25 over 1M synthetic documents (50k vocabulary, Zipf terms,
+~200 tokens) fused via RRF (rrf_k 60) with the dense top-100 of a 1M x 768 two-stage quantised
+search (binary Hamming scan -> float32 rescore of 400 candidates), batch of 1024 queries x 8
+tokens, fused top-10.  One step = ONE product call, ``HybridSearch.search_batch``
+(radiant-rag_b200/hybrid.py): dense -> BM25 -> RRF on device.  With --gpus N the documents are
+row-sharded over N ranks (torchrun, NCCL): both halves exchange their per-shard candidates and
+every rank ends with the same fused lists (strong scaling: the corpus is fixed).
 
 One JSON line on rank 0:
-  value     queries/s with the query batch already resident in HBM (device-timed)
-  e2e       the same through the public API with HOST (pinned) queries in and results out
-  roofline  the Hamming scan (dominant kernel): algorithmic bytes / CUDA-event duration
-  cpu_baseline  the oracle (NumPy port of the reference's CPU path) on a bounded sample
+  value         hybrid queries/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e           the same with HOST (pinned) queries + term ids in and host results out
+  roofline      the dominant kernel of the step, timed live with CUDA events on its stream
+  cpu_baseline  the NumPy oracle on a bounded sample of the batch, 1 thread, and the GPU's fused
+                ids checked against it in the same run (at every N)
+  extras        BASELINE config 2 (dense only, batch 256) on the same GPUs; config 4 at N = 2 / 4
+                and config 5 at N = 8 when the run has those GPUs
 
 `--impl reference` times the CPU path only (all host cores, bounded sample per step).
 """
@@ -19,6 +24,7 @@ One JSON line on rank 0:
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -33,31 +39,75 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-CFG = dict(n=1_000_000, dim=768, q=256, cand_k=200, top_k=10, seed=1)
+CFG = dict(n=1_000_000, dim=768, q=1024, v=50_000, mean_len=200, q_len=8, dense_k=100, bm25_k=100,
+           top_k=10, mult=4.0, rrf_k=60, seed=2, k1=1.5, b=0.75)
+CFG2 = dict(n=1_000_000, dim=768, q=256, cand_k=200, top_k=10, seed=1)
 METRIC = "hybrid retrieval queries/sec @ top-10"
-WORKLOAD = "config2: 1M x 768-dim binary Hamming scan + fp32 rescore of top-200 candidates, batch 256 queries, top-10"
+WORKLOAD = ("config3: BM25 over 1M synthetic docs (50k vocab, Zipf, avg 200 tokens) fused via RRF with the dense "
+            "top-100 of a 1M x 768 binary Hamming scan + fp32 rescore, batch 1024 queries x 8 tokens, fused top-10")
+WORKLOAD2 = "config2: 1M x 768-dim binary Hamming scan + fp32 rescore of top-200 candidates, batch 256 queries, top-10"
 
 
-# ---------------------------------------------------------------- CPU arm (oracle port)
-def _cpu_worker_init(codes_path, dim, n, seed):
-    global _W
-    _W = dict(codes=np.load(codes_path, mmap_mode="r"), dim=dim, n=n, seed=seed)
+def _peaks() -> dict:
+    """Measured peaks: MEASURED_PEAKS.json (driver-written HBM copy / cuBLAS bf16) and
+    profiles/r2_peaks.json (tools/peak_probe.py: int8 tensor pipe, POPC, shared memory)."""
+    out = {"hbm_gbs": 6650.0, "hbm_src": "fallback (B200_PROFILING.md)", "bf16_tflops": 1590.0}
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        out.update(hbm_gbs=float(d["hbm_gbs"]), hbm_src="measured copy bandwidth (MEASURED_PEAKS.json)",
+                   bf16_tflops=float(d.get("bf16_tflops", 1590.0)))
+    p2 = ROOT / "profiles" / "r2_peaks.json"
+    if p2.exists():
+        d = json.loads(p2.read_text())
+        out.update(i8_ts_tops=d.get("i8_mma_m128n128_ts_tops"), i8_ss_tops=d.get("i8_mma_m128n256_ss_tops"),
+                   popc_tera=d.get("popc32_tera_per_s"), smem_tbs=d.get("smem_load_tb_per_s"),
+                   probe_src="measured by tools/peak_probe.py (profiles/r2_peaks.json)")
+    return out
 
 
-def _cpu_one_query(qi):
-    """One query through the CPU restatement of the reference path: ubinary-quantise the
-    query, exact Hamming top-k' over all rows, float32 rescore of the candidates, top-10."""
+def _traffic(kernel: str, shape: str):
+    """dram bytes per launch of `kernel` from a tracked ncu --set full capture keyed by shape
+    (profiles/r2_traffic.json), or None when no capture of this shape is tracked."""
+    p = ROOT / "profiles" / "r2_traffic.json"
+    if not p.exists():
+        return None
+    return json.loads(p.read_text()).get(kernel, {}).get(shape)
+
+
+# ---------------------------------------------------------------- CPU side (oracle port)
+def _cpu_dense_one(codes, dim, seed, n, qi, cand_k, top_k):
+    """One dense query through the CPU restatement: ubinary-quantise, exact Hamming top-k' over all
+    rows, float32 rescore of the candidates (rows regenerated from the counter-based generator)."""
     import oracle
     from radiant_rag_b200 import synthetic
 
-    w = _W
-    q = synthetic.hash_query_rows_f32(qi, 1, w["dim"], w["seed"], w["n"])[0]
+    q = synthetic.hash_query_rows_f32(qi, 1, dim, seed, n)[0]
     qc = oracle.quantize_ubinary(q[None, :])
-    _d, cand = oracle.hamming_topk(w["codes"], qc, CFG["cand_k"])
+    _d, cand = oracle.hamming_topk(codes, qc, cand_k)
     ids = cand[0][cand[0] >= 0]
-    rows = np.concatenate([synthetic.hash_rows_f32(int(r), 1, w["dim"], w["seed"]) for r in ids])
-    got, _s = oracle.rescore_f32(q, rows, ids, top_k=CFG["top_k"], min_similarity=0.0)
-    return got.tolist()
+    rows = np.concatenate([synthetic.hash_rows_f32(int(r), 1, dim, seed) for r in ids])
+    got, _s = oracle.rescore_f32(q, rows, ids, top_k=top_k, min_similarity=0.0)
+    return got
+
+
+def _cpu_hybrid_one(w, qi):
+    """dense top-100 + BM25 top-100 -> RRF top-10 for query qi (reference call chain
+    radiant/app.py:1178-1249, one query at a time)."""
+    import oracle
+
+    d_ids = _cpu_dense_one(w["codes"], CFG["dim"], CFG["seed"], CFG["n"], qi, int(CFG["dense_k"] * CFG["mult"]),
+                           CFG["dense_k"])
+    b_rows, _ = w["orc"].search(w["qt"][qi].tolist(), CFG["bm25_k"])
+    ids, _sc = oracle.rrf_fuse([d_ids.tolist(), b_rows.tolist()], CFG["top_k"], CFG["rrf_k"])
+    return ids.tolist()
+
+
+_W = None
+
+
+def _cpu_worker_query(qi):
+    return _cpu_hybrid_one(_W, qi)
 
 
 def _gen_codes_chunk(args):
@@ -68,42 +118,64 @@ def _gen_codes_chunk(args):
     return oracle.quantize_ubinary(synthetic.hash_rows_f32(lo, m, dim, seed))
 
 
+def _gen_tokens_chunk(args):
+    from radiant_rag_b200 import synthetic
+
+    pos, m, seed, v = args
+    return synthetic.zipf_tokens(pos, m, seed, synthetic.zipf_cdf_u32(v))
+
+
 def run_reference_arm(args) -> None:
-    """The reference's CPU implementation of the path (NumPy port under oracle/ - the
-    reference itself is Python and is not present on the GPU box), all host cores."""
+    """The reference's CPU implementation of the path (NumPy port under oracle/ - the reference
+    itself is Python and is not present on the GPU box), all host cores, one query per task."""
+    global _W
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
 
+    from oracle.bm25 import BM25Oracle
+    from radiant_rag_b200 import synthetic
+
     cores = len(os.sched_getaffinity(0))
-    n, dim, seed = CFG["n"], CFG["dim"], CFG["seed"]
+    n, dim, seed, v = CFG["n"], CFG["dim"], CFG["seed"], CFG["v"]
     ctx = mp.get_context("fork")
     t0 = time.time()
-    chunk = 25_000
-    with ctx.Pool(cores) as pool:
-        parts = pool.map(_gen_codes_chunk, [(lo, min(chunk, n - lo), dim, seed) for lo in range(0, n, chunk)])
-    codes = np.concatenate(parts)
-    tmp = tempfile.mkdtemp()
-    codes_path = os.path.join(tmp, "codes.npy")
-    np.save(codes_path, codes)
-    setup_s = time.time() - t0
     per_step = max(cores, 8)
-    with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(codes_path, dim, n, seed)) as pool:
+    total_q = min(CFG["q"], per_step * (args.steps + args.warmup))
+    qt = synthetic.zipf_queries(CFG["q"], CFG["q_len"], v, seed)
+    need = set(int(t) for qi in range(total_q) for t in qt[qi])
+    lens = synthetic.doc_lengths(0, n, seed, CFG["mean_len"])
+    ptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=ptr[1:])
+    total_tok = int(ptr[-1])
+    with ctx.Pool(cores) as pool:
+        parts = pool.map(_gen_codes_chunk, [(lo, min(25_000, n - lo), dim, seed) for lo in range(0, n, 25_000)])
+        tchunk = 4_000_000
+        tparts = pool.map(_gen_tokens_chunk, [(p, min(tchunk, total_tok - p), seed, v) for p in range(0, total_tok, tchunk)])
+    codes = np.concatenate(parts)
+    toks = np.concatenate(tparts)
+    del parts, tparts
+    orc = BM25Oracle(ptr, toks, v, CFG["k1"], CFG["b"], only_terms=need)
+    del toks
+    _W = dict(codes=codes, orc=orc, qt=qt)  # inherited by the forked workers (copy on write)
+    setup_s = time.time() - t0
+    with ctx.Pool(cores) as pool:
         for w in range(args.warmup):
-            pool.map(_cpu_one_query, [(w * per_step + i) % CFG["q"] for i in range(per_step)])
+            pool.map(_cpu_worker_query, [(w * per_step + i) % total_q for i in range(per_step)])
         times = []
         for s in range(args.steps):
             t = time.perf_counter()
-            pool.map(_cpu_one_query, [(s * per_step + i) % CFG["q"] for i in range(per_step)])
+            pool.map(_cpu_worker_query, [((s + args.warmup) * per_step + i) % total_q for i in range(per_step)])
             times.append(time.perf_counter() - t)
     total = sum(times)
     value = per_step * args.steps / total
-    sample = f"{per_step} queries per step against the full 1M x 768 corpus ({args.steps} steps)"
+    sample = (f"{per_step} queries per step (one per worker process) against the full 1M-doc BM25 index and 1M x 768 "
+              f"codes ({args.steps} steps)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8+f32",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8 codes + f32 rescore + f64 BM25/RRF",
         "data": "synthetic", "config": {"workload": WORKLOAD, "queries_per_step": per_step, "setup_s": round(setup_s, 1)},
         "cpu_baseline": {"value": value, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -168,159 +240,77 @@ class ClockSampler:
         return out
 
 
-def run_gpu_arm(args) -> None:
-    import torch
-    import torch.distributed as dist
+class Bench:
+    """Shared plumbing of the GPU arm: process group, timing loops, L2 flush."""
 
-    from radiant_rag_b200 import _lib, synthetic
-    from radiant_rag_b200.index import DenseIndex, synth_query_rows_device, synth_rows_device
-    from radiant_rag_b200.sharded import GpuShardOps, ShardedDenseSearch, shard_range
+    def __init__(self, args) -> None:
+        import torch
+        import torch.distributed as dist
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    sampler = ClockSampler(local_rank) if rank == 0 else None  # started early: nvidia-smi takes ~1 s to come up
-    windows = []
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        # NCCL prints its version banner to stdout on the first communicator; rank 0 must print ONE
-        # JSON line, so stdout is pointed at stderr (fd level) until the first collective is done
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=dev)
-            warm = torch.zeros(1, device=dev)
-            dist.all_reduce(warm)
-            torch.cuda.synchronize()
-        finally:
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.sampler = ClockSampler(self.local_rank) if self.rank == 0 else None
+        self.windows = []
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            # NCCL prints its version banner to stdout on the first communicator; rank 0 must print ONE
+            # JSON line, so stdout is pointed at stderr (fd level) until the first collective is done
             sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
-    n, dim, nq, cand_k, top_k, seed = (CFG[k] for k in ("n", "dim", "q", "cand_k", "top_k", "seed"))
-    mult = cand_k / top_k
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                warm = torch.zeros(1, device=self.dev)
+                dist.all_reduce(warm)
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
 
-    # ---- resident index of this rank's shard, generated on device
-    lo, hi = shard_range(n, rank, world)
-    index = DenseIndex(dim, device=local_rank, store_int8=False, store_f32=True, row_base=lo, capacity=hi - lo)
-    step_rows = 125_000
-    for a in range(lo, hi, step_rows):
-        index.add(synth_rows_device(a, min(step_rows, hi - a), dim, seed, dev))
-    queries_dev = synth_query_rows_device(0, nq, dim, seed, n, dev)
-    queries_host = queries_dev.cpu().pin_memory()
-    torch.cuda.synchronize()
-    search = ShardedDenseSearch(GpuShardOps(index))
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    def barrier(self) -> None:
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    out_host = {
-        "idx": torch.empty((nq, top_k), dtype=torch.int64).pin_memory(),
-        "score": torch.empty((nq, top_k), dtype=torch.float32).pin_memory(),
-        "count": torch.empty((nq,), dtype=torch.int32).pin_memory(),
-    }
-
-    def search_step(q):
-        # tensor-core stage 1: the overflow counter is accumulated on device and verified
-        # once after the timed region (no host sync inside a step)
-        return search.search_quantized(q, top_k, rescore_multiplier=mult, prefer_int8=False,
-                                       check_overflow=False)
-
-    # One step = ~10 short kernels (+ NCCL collectives when sharded): replayed as a CUDA graph so
-    # that the host issue time of a step does not bound a sub-millisecond GPU step.
-    graphed = None
-    if not args.no_graph:
-        from radiant_rag_b200.graphed import GraphedSearch, GraphedShardedSearch
-        if world > 1:  # compute segments as graphs, the NCCL exchanges eagerly between them
-            graphed = GraphedShardedSearch(search, nq, dim, top_k, rescore_multiplier=mult, prefer_int8=False)
-        else:
-            graphed = GraphedSearch(search_step, nq, dim, dev)
-        graphed.load(queries_dev)
-        torch.cuda.synchronize()
-
-    def step_device():
-        if graphed is not None:
-            return graphed.replay()  # static input already holds the resident queries
-        return search_step(queries_dev)
-
-    def step_e2e():
-        # pipelined serving loop: H2D of this step's queries (pinned), the search, D2H of the results.
-        # The tensor-core overflow counter is accumulated on the device; exactness of every timed
-        # step is asserted below.
-        if graphed is not None:
-            idx, score, count = graphed(queries_host)
-        else:
-            idx, score, count = search_step(queries_host.to(dev, non_blocking=True))
-        out_host["idx"].copy_(idx, non_blocking=True)
-        out_host["score"].copy_(score, non_blocking=True)
-        out_host["count"].copy_(count, non_blocking=True)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def timed(fn, steps, warmup):
+    def timed(self, fn, steps: int, warmup: int) -> float:
+        """Total ms of `steps` calls, each bracketed by CUDA events on the current stream, L2 flushed
+        (256 MB fill) before every call outside the event pair; max over ranks."""
+        torch = self.torch
         for _ in range(warmup):
-            flush.fill_(1)
+            self.flush.fill_(1)
             fn()
-        barrier()
+        self.barrier()
         evs = []
         for _ in range(steps):
-            flush.fill_(1)  # L2 flush between timed iterations (outside the event pair)
+            self.flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
             e1.record()
             evs.append((e0, e1))
-        barrier()
+        self.barrier()
         total_ms = sum(a.elapsed_time(b) for a, b in evs)
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        t = torch.tensor([total_ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
-    launches0 = _lib.launch_count
-    w0 = time.time()
-    total_ms = timed(step_device, args.steps, args.warmup)
-    launches = _lib.launch_count - launches0 - 0
-    launches_per_step = launches // (args.steps + args.warmup)
-    e2e_ms = timed(step_e2e, args.steps, args.warmup)
-    windows.append((w0, time.time()))
-    # the timed regions last only tens of milliseconds; keep the same step running for ~1.5 s so
-    # that the 100 ms clock sampler sees the GPU under this load (reported with the timed windows)
-    w1 = time.time()
-    n_sustain = max(20, min(20000, int(1500.0 / max(total_ms / args.steps, 1e-3))))  # same count on every rank
-    for i in range(n_sustain):
-        step_device()
-        if i % 50 == 49:
-            torch.cuda.synchronize()
-    torch.cuda.synchronize()
-    windows.append((w1, time.time()))
-    if world > 1:
-        dist.barrier()
-    if index.tc_overflow_total() != 0:
-        raise SystemExit("tensor-core candidate lists overflowed during the timed region: results not exact")
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-    clocks = {}
-
-    # ---- stage breakdown + roofline of the scan (single GPU view of rank 0's shard)
-    qf, qc = index.quantize_queries(queries_dev)
-    n_local = hi - lo
-
-    def time_stage(fn, reps):
+    def time_stage(self, fn, reps: int) -> float:
+        """Average ms of one call on THIS rank (no collective inside fn), L2 flushed before each."""
+        torch = self.torch
         for _ in range(3):
-            flush.fill_(1)
+            self.flush.fill_(1)
             fn()
         torch.cuda.synchronize()
         evs = []
         for _ in range(reps):
-            flush.fill_(1)
+            self.flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -329,12 +319,28 @@ def run_gpu_arm(args) -> None:
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs) / reps
 
-    reps = max(5, min(args.steps, 20))
-    scan_ms = time_stage(lambda: index.hamming_topk(qc, cand_k, check_overflow=False), reps)
-    # dominant kernel alone: rr_tc_timing brackets the four kernels of rr_hamming_topk_tc with CUDA
-    # events on the launching stream; average over the same flushed repetitions
-    import ctypes as C
-    lib = _lib.load()
+    def sustain(self, fn, ms_per_step: float) -> None:
+        """Keep the step running ~1.5 s so the 100 ms clock sampler sees the GPU under this load."""
+        w1 = time.time()
+        n_sustain = max(20, min(20000, int(1500.0 / max(ms_per_step, 1e-3))))  # same count on every rank
+        for i in range(n_sustain):
+            fn()
+            if i % 50 == 49:
+                self.torch.cuda.synchronize()
+        self.torch.cuda.synchronize()
+        self.windows.append((w1, time.time()))
+
+    def sum_over_ranks(self, value: int) -> int:
+        if self.world == 1:
+            return int(value)
+        t = self.torch.tensor([int(value)], dtype=self.torch.int64, device=self.dev)
+        self.dist.all_reduce(t)
+        return int(t.item())
+
+
+def _tc_parts(lib, _lib, index, qc, cand_k, flush, reps):
+    """Per-kernel ms of the tensor-core stage 1 (rr_tc_timing brackets the four kernels with CUDA
+    events on the launching stream), averaged over flushed repetitions."""
     lib.rr_tc_timing(1)
     parts = [0.0, 0.0, 0.0, 0.0]
     buf = (C.c_float * 4)()
@@ -345,104 +351,322 @@ def run_gpu_arm(args) -> None:
             raise SystemExit("rr_tc_last_timing_ms: " + _lib.last_error())
         parts = [p + float(b) for p, b in zip(parts, buf)]
     lib.rr_tc_timing(0)
-    sample_ms, tau_ms, filter_ms, select_ms = (p / reps for p in parts)
-    scan_popc_ms = time_stage(lambda: index.hamming_topk(qc, cand_k, use_tc=False), reps)
-    _d, cand = index.hamming_topk(qc, cand_k)
-    rescore_ms = time_stage(lambda: index.rescore(qf, cand, top_k, 0.0, prefer_int8=False), reps)
-    quant_ms = time_stage(lambda: index.quantize_queries(queries_dev), reps)
-    scan1_ms = time_stage(lambda: index.hamming_topk(qc[:1].contiguous(), cand_k), reps)
-    clocks = sampler.summary(windows) if sampler else {}
+    return [p / reps for p in parts]
 
-    peaks_path = ROOT / "MEASURED_PEAKS.json"
-    if peaks_path.exists():
-        hbm_peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+
+def run_config2(bx: Bench, steps: int, warmup: int) -> dict:
+    """BASELINE config 2 (round 1's headline, kept as an extra): dense two-stage search only,
+    batch 256, strong-scaled over the ranks."""
+    torch = bx.torch
+    from radiant_rag_b200 import _lib
+    from radiant_rag_b200.graphed import GraphedSearch, GraphedShardedSearch
+    from radiant_rag_b200.index import DenseIndex, synth_query_rows_device, synth_rows_device
+    from radiant_rag_b200.sharded import GpuShardOps, ShardedDenseSearch, shard_range
+
+    n, dim, nq, cand_k, top_k, seed = (CFG2[k] for k in ("n", "dim", "q", "cand_k", "top_k", "seed"))
+    mult = cand_k / top_k
+    lo, hi = shard_range(n, bx.rank, bx.world)
+    index = DenseIndex(dim, device=bx.local_rank, store_int8=False, store_f32=True, row_base=lo, capacity=hi - lo)
+    for a in range(lo, hi, 125_000):
+        index.add(synth_rows_device(a, min(125_000, hi - a), dim, seed, bx.dev))
+    queries_dev = synth_query_rows_device(0, nq, dim, seed, n, bx.dev)
+    queries_host = queries_dev.cpu().pin_memory()
+    search = ShardedDenseSearch(GpuShardOps(index))
+    out_host = {"idx": torch.empty((nq, top_k), dtype=torch.int64).pin_memory(),
+                "score": torch.empty((nq, top_k), dtype=torch.float32).pin_memory(),
+                "count": torch.empty((nq,), dtype=torch.int32).pin_memory()}
+    if bx.world > 1:
+        graphed = GraphedShardedSearch(search, nq, dim, top_k, rescore_multiplier=mult, prefer_int8=False)
     else:
-        hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    code_bytes = n_local * index.words * 4
-    achieved = code_bytes / (scan_ms * 1e-3) / 1e9
-    sm_clock = (clocks.get("sm_max_mhz") or 1965.0) * 1e6
-    popc_peak = 148 * 16 * sm_clock  # 32-bit POPC lanes per second (16 / clk / SM)
-    popc_rate = nq * n_local * index.words / (scan_popc_ms * 1e-3)
-    int8_ops = 2.0 * nq * n_local * index.words * 32
-    bf16_peak = float(json.loads(peaks_path.read_text()).get("bf16_tflops", 1590.0)) if peaks_path.exists() else 1590.0
-    tensor_peak = 2.0 * bf16_peak
-    roofline = {
-        "kernel": "tc_i8_search_kernel<EPI_FILTER> (tcgen05 kind::i8 filter pass of rr_hamming_topk_tc; ~60% of the "
-                  "step, profiles/r1_launches_bench_final_summary.md)",
-        "bound": "tensor", "achieved": int8_ops / (filter_ms * 1e-3) / 1e12, "peak": tensor_peak,
-        "unit": "TOP/s", "frac": int8_ops / (filter_ms * 1e-3) / 1e12 / tensor_peak,
-        "traffic": 103592704 if (world == 1 and n_local == 1_000_000 and dim == 768 and nq == 256) else None,
-        "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape, ncu --set full "
-                          "(profiles/r1_ncu_full_summary_final.md)",
-        "launch_ms": filter_ms, "timing": "CUDA events on the launching stream around the kernel (rr_tc_timing), "
-                                         "L2 flushed before every call",
-        "peak_source": "2 x measured dense bf16 cuBLAS burst (MEASURED_PEAKS.json); int8 is nominally 2x bf16",
-        "algorithmic_ops_per_launch": int8_ops, "algorithmic_bytes_per_launch": code_bytes,
-        "note": "batched stage 1 runs as an exact u8(0/255) x s8(+-1) GEMM on tcgen05: packed codes are expanded on "
-                "chip into a tensor-memory operand ring, HBM traffic is the packed codes only. The other kernels of "
-                "the stage, and hbm / popc views of the same stage, below.",
-        "stage1_kernels_ms": {"sample_pass": sample_ms, "tau": tau_ms, "filter_pass": filter_ms,
-                              "list_select": select_ms, "whole_call": scan_ms},
-        "stage1_call_frac": int8_ops / (scan_ms * 1e-3) / 1e12 / tensor_peak,
-        "hbm_view": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "peak_source": peak_src},
-        "popc_path": {"ms": scan_popc_ms, "bound": "popc", "achieved": popc_rate / 1e12, "peak": popc_peak / 1e12,
-                      "unit": "T popc32/s", "frac": popc_rate / popc_peak},
-        "single_query": {"kernel": "hamming_scan2_kernel (POPC, TMA bulk staged)", "ms": scan1_ms, "bound": "hbm",
-                         "achieved": code_bytes / (scan1_ms * 1e-3) / 1e9,
-                         "frac": code_bytes / (scan1_ms * 1e-3) / 1e9 / hbm_peak, "unit": "GB/s",
-                         "note": "1M x 768 is only 96 MB; on the 12.5M x 1024 shard of the 100M-row config the "
-                                 "same kernel reaches 0.84 of the measured HBM peak (profiles/, tools/scan_bench.py)"},
-    }
+        graphed = GraphedSearch(lambda q: search.search_quantized(q, top_k, rescore_multiplier=mult, prefer_int8=False,
+                                                                  check_overflow=False), nq, dim, bx.dev)
+    graphed.load(queries_dev)
+    torch.cuda.synchronize()
 
-    # ---- CPU baseline: the oracle on a bounded sample of the same workload, 1 thread
-    import oracle
+    def step_e2e():
+        idx, score, count = graphed(queries_host)
+        out_host["idx"].copy_(idx, non_blocking=True)
+        out_host["score"].copy_(score, non_blocking=True)
+        out_host["count"].copy_(count, non_blocking=True)
 
-    t0 = time.perf_counter()
-    codes_host = index.codes[:n_local].cpu().numpy()[:, : dim // 8] if world == 1 else None
+    launches0 = _lib.launch_count
+    total_ms = bx.timed(graphed.replay, steps, warmup)
+    launches = (_lib.launch_count - launches0) // (steps + warmup)
+    e2e_ms = bx.timed(step_e2e, steps, warmup)
+    overflow = search.overflow_total()  # collective: summed over the ranks
+    out = {"workload": WORKLOAD2, "value": nq / (total_ms / steps * 1e-3), "unit": "queries/s",
+           "ms_per_step": total_ms / steps,
+           "e2e": {"value": nq / (e2e_ms / steps * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / steps,
+                   "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * top_k * 12 + nq * 4},
+           "gpu_launches_per_step": launches, "tc_list_overflows": overflow, "rows_per_gpu": hi - lo}
+    if bx.rank == 0:
+        lib = _lib.load()
+        qf, qc = index.quantize_queries(queries_dev)
+        reps = max(5, min(steps, 20))
+        sample_ms, tau_ms, filter_ms, select_ms = _tc_parts(lib, _lib, index, qc, cand_k, bx.flush, reps)
+        _d, cand = index.hamming_topk(qc, cand_k)
+        rescore_ms = bx.time_stage(lambda: index.rescore(qf, cand, top_k, 0.0, prefer_int8=False), reps)
+        pk = _peaks()
+        int8_ops = 2.0 * nq * (hi - lo) * index.words * 32
+        tensor_peak = pk.get("i8_ts_tops") or 2.0 * pk["bf16_tflops"]
+        out["stage1_kernels_ms"] = {"sample_pass": sample_ms, "tau": tau_ms, "filter_pass": filter_ms,
+                                    "list_select": select_ms}
+        out["rescore_ms"] = rescore_ms
+        out["filter_pass_roofline"] = {
+            "bound": "tensor", "achieved": int8_ops / (filter_ms * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TOP/s",
+            "frac": int8_ops / (filter_ms * 1e-3) / 1e12 / tensor_peak,
+            "peak_source": pk.get("probe_src", "2 x measured bf16 (no probe file)")}
+        c_bytes = nq * cand_k * dim * 4 + nq * dim * 4
+        out["rescore_roofline"] = {"bound": "hbm", "achieved": c_bytes / (rescore_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
+                                   "unit": "GB/s", "frac": c_bytes / (rescore_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
+    del graphed, index
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_gpu_arm(args) -> None:
+    bx = Bench(args)
+    torch, dist = bx.torch, bx.dist
+    from radiant_rag_b200 import _lib, synthetic
+    from radiant_rag_b200.bm25_index import Bm25DeviceIndex, synth_zipf_corpus_device
+    from radiant_rag_b200.hybrid import GraphedHybridSearch, HybridSearch
+    from radiant_rag_b200.index import DenseIndex, synth_query_rows_device, synth_rows_device
+    from radiant_rag_b200.sharded import shard_range
+
+    world, rank, dev = bx.world, bx.rank, bx.dev
+    n, dim, nq, v, seed = CFG["n"], CFG["dim"], CFG["q"], CFG["v"], CFG["seed"]
+    top_k, dense_k, bm25_k, mult, rrf_k, q_len = (CFG[k] for k in ("top_k", "dense_k", "bm25_k", "mult", "rrf_k", "q_len"))
+    cand_k = int(dense_k * mult)
+
+    # ---- resident indexes of this rank's shard, generated on device
+    t_build = time.time()
+    lo, hi = shard_range(n, rank, world)
+    index = DenseIndex(dim, device=bx.local_rank, store_int8=False, store_f32=True, row_base=lo, capacity=hi - lo)
+    for a in range(lo, hi, 125_000):
+        index.add(synth_rows_device(a, min(125_000, hi - a), dim, seed, dev))
+    ptr, toks = synth_zipf_corpus_device(hi - lo, v, seed, CFG["mean_len"], device=bx.local_rank, row_start=lo)
+    bm = Bm25DeviceIndex.build(ptr, toks, v, None, None, CFG["k1"], CFG["b"], device=bx.local_rank, row_base=lo,
+                               sharded=True)  # global df / avgdl over the ranks, built by the product from tokens
+    bm.fast_min_docs = 0  # shards of a large corpus keep the batched path
+    del ptr, toks
+    queries_dev = synth_query_rows_device(0, nq, dim, seed, n, dev)
+    qt_np = synthetic.zipf_queries(nq, q_len, v, seed)
+    qt_dev = torch.from_numpy(qt_np).to(dev)
+    queries_host = queries_dev.cpu().pin_memory()
+    qt_host = torch.from_numpy(qt_np).pin_memory()
+    torch.cuda.synchronize()
+    build_s = time.time() - t_build
+    hybrid = HybridSearch(index, bm, rescore_multiplier=mult, prefer_int8=False)
+    kw = dict(top_k=top_k, dense_top_k=dense_k, bm25_top_k=bm25_k, rrf_k=rrf_k)
+
+    out_host = {"idx": torch.empty((nq, top_k), dtype=torch.int64).pin_memory(),
+                "score": torch.empty((nq, top_k), dtype=torch.float64).pin_memory(),
+                "count": torch.empty((nq,), dtype=torch.int32).pin_memory()}
+
+    graphed = None
+    if world == 1 and not args.no_graph:
+        graphed = GraphedHybridSearch(hybrid, nq, dim, q_len, **kw)
+        graphed.load(queries_dev, qt_dev)
+        torch.cuda.synchronize()
+
+    def step_device():
+        if graphed is not None:
+            return graphed.replay()  # static inputs already hold the resident batch
+        return hybrid.search_batch(queries_dev, qt_dev, check=False, **kw)
+
+    def step_e2e():
+        # pipelined serving loop: H2D of this step's queries + term ids (pinned), the step, D2H of
+        # the fused lists.  Exactness counters are accumulated on device and asserted below.
+        if graphed is not None:
+            res = graphed(queries_host, qt_host)
+        else:
+            res = hybrid.search_batch(queries_host.to(dev, non_blocking=True), qt_host.to(dev, non_blocking=True),
+                                      check=False, **kw)
+        out_host["idx"].copy_(res.idx, non_blocking=True)
+        out_host["score"].copy_(res.score, non_blocking=True)
+        out_host["count"].copy_(res.count, non_blocking=True)
+
+    hybrid.reset_unchecked_events()
+    launches0 = _lib.launch_count
+    w0 = time.time()
+    total_ms = bx.timed(step_device, args.steps, args.warmup)
+    launches_per_step = (_lib.launch_count - launches0) // (args.steps + args.warmup)
+    e2e_ms = bx.timed(step_e2e, args.steps, args.warmup)
+    bx.windows.append((w0, time.time()))
+    bx.sustain(step_device, total_ms / args.steps)
+    # every rank learns about inexact events on ANY rank before anyone decides to stop
+    events = bx.sum_over_ranks(hybrid.unchecked_events())
+    if events != 0:
+        # flagged BM25 queries / overflowed candidate lists in an unchecked step: the timed results
+        # were not all proven exact - report it instead of a number
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "error": f"{events} unchecked exactness events in the timed region"}),
+                  flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        raise SystemExit(2)
+    res_dev = step_device()
+    fused_idx = res_dev.idx.clone()
+    dense_idx = res_dev.dense_idx.clone()
+    torch.cuda.synchronize()
+
+    # ---- rank 0 needs the whole corpus for the CPU check at N > 1: regenerate it on its own GPU
     cpu = None
-    if codes_host is not None:
-        sample_q = 128
-        qh = queries_host.numpy()
-        f32_dev = index.f32
-        t0 = time.perf_counter()
-        cpu_ids = []
-        for qi in range(sample_q):
-            qcode = oracle.quantize_ubinary(qh[qi:qi + 1])
-            _dd, cc = oracle.hamming_topk(codes_host, qcode, cand_k)
-            ids = cc[0][cc[0] >= 0]
-            rows = f32_dev[torch.from_numpy(ids).to(dev)].cpu().numpy()  # candidate rows only
-            got, _s = oracle.rescore_f32(qh[qi], rows, ids, top_k=top_k, min_similarity=0.0)
-            cpu_ids.append(got.tolist())
-        cpu_s = time.perf_counter() - t0
-        cpu = {"value": sample_q / cpu_s, "unit": "queries/s", "cores": 1, "kind": "port",
-               "sample": f"{sample_q} of the {nq} queries against the full 1M x 768 corpus, NumPy oracle, 1 thread"}
-        # the timed GPU path and the CPU path agree on the sample
-        gi, _gs, _gc = step_device()
-        agree = sum(1 for qi in range(sample_q) if gi[qi].cpu().tolist()[: len(cpu_ids[qi])] == cpu_ids[qi])
-        cpu["gpu_matches_cpu_on_sample"] = f"{agree}/{sample_q}"
+    lib = _lib.load()
+    if rank == 0:
+        sample_q = 48
+        sample = [int(x) for x in np.linspace(0, nq - 1, sample_q).astype(int)]
+        if world == 1:
+            codes_host = index.codes[: hi - lo].cpu().numpy()[:, : dim // 8]
+        else:
+            parts = []
+            for a in range(0, n, 125_000):
+                rows = synth_rows_device(a, min(125_000, n - a), dim, seed, dev)
+                c = torch.empty((rows.shape[0], index.words * 4), dtype=torch.uint8, device=dev)
+                _lib.call("rr_quantize_ubinary", rows.data_ptr(), rows.shape[0], dim, c.data_ptr(), index.words * 4,
+                          torch.cuda.current_stream().cuda_stream)
+                parts.append(c.cpu().numpy()[:, : dim // 8])
+            codes_host = np.concatenate(parts)
+        ptr_all, toks_all = synth_zipf_corpus_device(n, v, seed, CFG["mean_len"], device=bx.local_rank)
+        ptr_h, toks_h = ptr_all.cpu().numpy(), toks_all.cpu().numpy()
+        del ptr_all, toks_all
+        import oracle
+        from oracle.bm25 import BM25Oracle
 
-    ms_per_step = total_ms / args.steps
-    e2e_ms_per_step = e2e_ms / args.steps
-    line = {
-        "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u8 sign codes (0/255 u8 x +-1 s8 on tcgen05, int32 accumulate) + f32 rescore", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "corpus_rows": n, "dim": dim, "batch_queries": nq, "candidates": cand_k,
-                   "top_k": top_k, "rows_per_gpu": n_local, "parallelism": f"row-sharded x{world}",
-                   "l2": "flushed between timed iterations (256 MB fill)",
-                   "issue": "eager launches" if graphed is None else ("CUDA graph replay of the step" if world == 1 else "3 CUDA graphs per step with eager NCCL exchanges between them")},
-        "e2e": {"value": nq / (e2e_ms_per_step * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms_per_step,
-                "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * top_k * 12 + nq * 4},
-        "gpu_launches": launches_per_step * args.steps,
-        "gpu_launches_per_step": launches_per_step,
-        "stages_ms": {"quantize_queries": quant_ms, "hamming_topk": scan_ms, "rescore_f32": rescore_ms},
-        "roofline": roofline,
-        "cpu_baseline": cpu,
-        "clocks": dict({k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
-                       window="timed regions + 1.5 s of the same step back to back"),
-    }
-    print(json.dumps(line), flush=True)
+        need = set(int(t) for qi in sample for t in qt_np[qi])
+        orc = BM25Oracle(ptr_h, toks_h, v, CFG["k1"], CFG["b"], only_terms=need)
+        del toks_h
+        w = dict(codes=codes_host, orc=orc, qt=qt_np)
+        t0 = time.perf_counter()
+        cpu_ids = [_cpu_hybrid_one(w, qi) for qi in sample]
+        cpu_s = time.perf_counter() - t0
+        gi = fused_idx.cpu().numpy()
+        agree = sum(1 for j, qi in enumerate(sample) if gi[qi][: len(cpu_ids[j])].tolist() == cpu_ids[j]
+                    and (len(cpu_ids[j]) == top_k or gi[qi][len(cpu_ids[j])] == -1))
+        cpu = {"value": sample_q / cpu_s, "unit": "queries/s", "cores": 1, "kind": "port",
+               "sample": f"{sample_q} of the {nq} queries against the full 1M-doc corpus (dense two-stage + BM25 + RRF), "
+                         "NumPy oracle, 1 thread; index build not timed",
+               "gpu_matches_cpu_on_sample": f"{agree}/{sample_q}"}
+
+    # ---- stage breakdown + roofline (rank 0's shard)
+    line = None
+    if rank == 0:
+        reps = max(5, min(args.steps, 20))
+        n_local = hi - lo
+        qf, qc = index.quantize_queries(queries_dev)
+        dense_ms = bx.time_stage(lambda: index.search_quantized(queries_dev, dense_k, rescore_multiplier=mult,
+                                                                prefer_int8=False, check_overflow=False), reps)
+        sample_ms, tau_ms, filter_ms, select_ms = _tc_parts(lib, _lib, index, qc, cand_k, bx.flush, reps)
+        _d, cand = index.hamming_topk(qc, cand_k)
+        rescore_ms = bx.time_stage(lambda: index.rescore(qf, cand, dense_k, 0.0, prefer_int8=False), reps)
+        bm25_ms = bx.time_stage(lambda: bm.search_batch(qt_dev, bm25_k, check=False), reps)
+        lib.rr_bm25_timing(1)
+        bparts = [0.0] * 4
+        buf = (C.c_float * 4)()
+        for _ in range(reps):
+            bx.flush.fill_(1)
+            bm.search_batch(qt_dev, bm25_k, check=False)
+            if lib.rr_bm25_last_timing_ms(buf) != 0:
+                raise SystemExit("rr_bm25_last_timing_ms: " + _lib.last_error())
+            bparts = [p + float(b) for p, b in zip(bparts, buf)]
+        lib.rr_bm25_timing(0)
+        b_sample, b_tau, b_filter, b_refine = (p / reps for p in bparts)
+        from radiant_rag_b200.agents import rrf_fuse_runs_device
+        b_idx = res_dev.bm25_idx
+        rrf_ms = bx.time_stage(lambda: rrf_fuse_runs_device([dense_idx, b_idx], top_k, rrf_k), reps)
+        clocks = bx.sampler.summary(bx.windows) if bx.sampler else {}
+        pk = _peaks()
+        ms_per_step = total_ms / args.steps
+        # dominant kernel = the largest single launch of the step
+        int8_ops = 2.0 * nq * n_local * index.words * 32
+        tensor_peak = pk.get("i8_ts_tops") or 2.0 * pk["bf16_tflops"]
+        qt_flat = qt_np.ravel()
+        # algorithmic bytes of the BM25 filter pass: ONE pass over the shard's index per batch
+        # (postings 12 B + dense head columns 8 B/doc/term + the offsets the batch touches); without
+        # sharing every query would pull sum_t df(t) * 12 B on its own
+        index_bytes = bm.n_postings * 12 + (bm.head_imp.numel() * 8 if bm.n_head else 0)
+        ttp = bm.tile_term_ptr
+        df_local = (ttp[:, 1:] - ttp[:, :-1]).sum(dim=0)
+        unshared_bytes = float(df_local[torch.from_numpy(qt_flat[qt_flat >= 0].astype(np.int64)).to(dev)].sum().item()) * 12.0
+        tc_roof = {
+            "kernel": "tc_i8_search_kernel<EPI_FILTER> (tcgen05 kind::i8 filter pass of the dense stage 1)",
+            "bound": "tensor", "achieved": int8_ops / (filter_ms * 1e-3) / 1e12, "peak": tensor_peak, "unit": "TOP/s",
+            "frac": int8_ops / (filter_ms * 1e-3) / 1e12 / tensor_peak, "launch_ms": filter_ms,
+            "share_of_step": filter_ms / ms_per_step,
+            "traffic": _traffic("tc_i8_search_kernel_filter", f"{n_local}x{dim}x{nq}"),
+            "peak_source": pk.get("probe_src", "2 x measured dense bf16 cuBLAS burst (no probe file)") +
+                           ": back-to-back tcgen05.mma kind::i8 M128 N128, A in tensor memory",
+            "algorithmic_ops_per_launch": int8_ops, "algorithmic_bytes_per_launch": n_local * index.words * 4}
+        bm_roof = {
+            "kernel": "bm25_fast_kernel<FILTER> (batched float32 filter pass: dense head columns in shared memory + "
+                      "tail postings scattered per query)",
+            "bound": "hbm", "achieved": index_bytes / (b_filter * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": index_bytes / (b_filter * 1e-3) / 1e9 / pk["hbm_gbs"], "launch_ms": b_filter,
+            "share_of_step": b_filter / ms_per_step,
+            "traffic": _traffic("bm25_fast_kernel_filter", f"{n_local}x{v}x{nq}"),
+            "peak_source": pk["hbm_src"],
+            "algorithmic_bytes_per_launch": index_bytes,
+            "algorithmic_bytes_without_batch_sharing": unshared_bytes,
+            "achieved_without_batch_sharing_GBs": unshared_bytes / (b_filter * 1e-3) / 1e9,
+            "note": "one pass over the index serves the whole batch (SURVEY.md 8d asks for both accountings); the "
+                    "kernel's own limiter is shared-memory bandwidth: per (query, document) 4 B of tail accumulator "
+                    "zeroed + 4 B read + 4 B per head token",
+            "smem_view": None if not pk.get("smem_tbs") else {
+                "bytes_per_launch": float(nq) * n_local * (8.0 + 4.0 * 2.65),
+                "achieved_TBs": float(nq) * n_local * (8.0 + 4.0 * 2.65) / (b_filter * 1e-3) / 1e12,
+                "peak_TBs": pk["smem_tbs"], "frac": float(nq) * n_local * (8.0 + 4.0 * 2.65) / (b_filter * 1e-3) / 1e12 / pk["smem_tbs"]}}
+        c_bytes = float(nq) * cand_k * dim * 4 + nq * dim * 4
+        rs_roof = {"kernel": "rescore_f32_kernel (candidate row gather)", "bound": "hbm",
+                   "achieved": c_bytes / (rescore_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                   "frac": c_bytes / (rescore_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "launch_ms": rescore_ms,
+                   "share_of_step": rescore_ms / ms_per_step, "algorithmic_bytes_per_launch": c_bytes}
+        dominant = max((tc_roof, bm_roof, rs_roof), key=lambda r: r["launch_ms"])
+        roofline = dict(dominant)
+        roofline["timing"] = ("CUDA events on the launching stream around the kernel (rr_tc_timing / rr_bm25_timing), "
+                              "L2 flushed before every call")
+        roofline["other_kernels"] = [r for r in (tc_roof, bm_roof, rs_roof) if r is not dominant]
+        line = {
+            "metric": METRIC, "value": nq / (ms_per_step * 1e-3), "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8 sign codes (0/255 u8 x +-1 s8 on tcgen05, int32) + f32 rescore + f32-filtered / f64-exact BM25 + f64 RRF",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "docs": n, "dim": dim, "batch_queries": nq, "query_tokens": q_len,
+                       "dense_top_k": dense_k, "dense_candidates": cand_k, "bm25_top_k": bm25_k, "top_k": top_k,
+                       "rrf_k": rrf_k, "docs_per_gpu": n_local, "parallelism": f"row-sharded x{world}",
+                       "postings_per_gpu": bm.n_postings, "index_build_s": round(build_s, 1),
+                       "l2": "flushed between timed iterations (256 MB fill)",
+                       "issue": "CUDA graph replay of the step" if graphed is not None else
+                                "eager launches + NCCL exchanges"},
+            "e2e": {"value": nq / (e2e_ms / args.steps * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": nq * dim * 4 + nq * q_len * 4, "d2h_bytes_per_step": nq * top_k * 16 + nq * 4},
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "stages_ms": {"dense_top100": dense_ms, "bm25_top100": bm25_ms, "rrf_top10": rrf_ms,
+                          "dense_stage1": {"sample_pass": sample_ms, "tau": tau_ms, "filter_pass": filter_ms,
+                                           "list_select": select_ms},
+                          "dense_rescore": rescore_ms,
+                          "bm25": {"sample_pass": b_sample, "tau": b_tau, "filter_pass": b_filter, "refine": b_refine}},
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": dict({k: clocks.get(k) for k in ("sm_mhz", "sm_max_mhz", "reasons", "samples")},
+                           window="timed regions + 1.5 s of the same step back to back"),
+        }
+    del graphed, hybrid, bm, index
+    torch.cuda.empty_cache()
+
+    # ---- extras: the other BASELINE configs on the same GPUs (collective: every rank takes part)
+    extras = {}
+    if not args.no_extras:
+        ex_steps = max(3, min(args.steps, 10))
+        extras["config2"] = run_config2(bx, ex_steps, 3)
+        if world in (2, 4):
+            extras["config4"] = run_config4(bx, ex_steps)
+        if world == 8:
+            extras["config5"] = run_config5(bx)
+    if rank == 0:
+        line["extras"] = extras
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -456,9 +680,11 @@ def main() -> None:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=int, default=0, help="debug only: override the corpus size")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra BASELINE configs")
     args = ap.parse_args()
     if args.rows:
         CFG["n"] = args.rows
+        CFG2["n"] = args.rows
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)

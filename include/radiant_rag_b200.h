@@ -17,7 +17,8 @@
  *     message of the calling thread's last failure.  No C++ exception crosses the ABI;
  *   - re-entrant: the reference calls dense and BM25 retrieval from two threads
  *     (radiant/orchestrator.py:994-998); there is no global mutable state besides the
- *     thread-local error string and per-device attributes set once in rr_init.
+ *     thread-local error string, the thread-local state of the two timing aids and
+ *     per-device attributes set once in rr_init.
  *   - row ids are int64 positions in the index (insertion order); missing result
  *     slots hold row -1.
  */
@@ -187,6 +188,36 @@ int rr_bm25_topk(const int64_t* tile_term_ptr, const uint32_t* post_row,
                  int64_t* out_idx, int32_t* out_count, void* workspace,
                  size_t workspace_bytes, void* stream);
 
+/* ---- R6 for BATCHES: the same results as rr_bm25_topk, bit for bit, by filter-and-refine with
+ * the postings shared across the batch (csrc/bm25_fast.cu): float32 scores of every (query,
+ * document) against a sampled bound keep a few hundred candidates per query, whose float64
+ * scores are then recomputed in the reference's operation order.  Needs, on top of the
+ * rr_bm25_topk index: rows ASCENDING inside every (tile, term) segment, tile_docs a multiple of
+ * 128 and <= 1024, every impact finite and in [2^-100, 2^100], and for the n_head <= 32 terms
+ * chosen as "head" terms
+ *   head_slot i32 [n_terms]                  slot of the term, -1 for all other terms
+ *   head_imp  f64 [n_tiles, n_head, tile_docs] the term's impact per document of the tile,
+ *                                            0.0 where the document lacks the term
+ * (head terms keep their sparse postings too).
+ * inexact_flags u8 [q] or NULL: 1 for a query whose exactness check failed (candidate list
+ * overflow, or the k-th candidate score does not clear the bound) - its output row is NOT
+ * guaranteed and the caller must redo it with rr_bm25_topk; *inexact_counter (device u32 or
+ * NULL) is incremented once per flagged query. */
+size_t rr_bm25_fast_workspace_bytes(int32_t n_tiles, int32_t tile_docs, int64_t n_docs, int32_t q,
+                                    int32_t k);
+int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* post_row,
+                      const double* post_impact, const int32_t* head_slot, const double* head_imp,
+                      int32_t n_head, int32_t n_tiles, int32_t tile_docs, int32_t n_terms,
+                      int64_t n_docs, const int32_t* q_terms, int32_t q, int32_t q_len, int32_t k,
+                      int64_t row_base, double* out_score, int64_t* out_idx, int32_t* out_count,
+                      uint8_t* inexact_flags, uint32_t* inexact_counter, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* Measurement aid, as rr_tc_timing: out_ms[0] sample pass, [1] tau, [2] filter pass, [3] refine.
+ * The timing state of both aids is per host thread.  Not for use inside stream capture. */
+int rr_bm25_timing(int32_t enable);
+int rr_bm25_last_timing_ms(float* out_ms);
+
 /* R7 helper: per-posting impact in the reference's float64 operation order
  * (bm25_index.py:252-255).  post_tf i32, post_len i32 (length of the posting's
  * document), post_idf f64 (idf of the posting's term, copied from the host index). */
@@ -205,6 +236,13 @@ int rr_bm25_impacts(const int32_t* post_tf, const int32_t* post_len, const doubl
 int rr_rrf_fuse(const int64_t* run_idx, const int32_t* run_off_host, int32_t n_runs, int32_t q,
                 double rrf_k, int32_t k, int64_t* out_idx, double* out_score,
                 int32_t* out_count, void* stream);
+/* Same fusion with every run in its own buffer (no concatenation copy): run r of query i is
+ * run_ptrs_host[r] + i * run_len_host[r], i64 [q, run_len_host[r]] on the device; the two arrays
+ * of n_runs entries are HOST arrays.  This is what the batched hybrid step uses: the dense and
+ * BM25 top-k lists are fused where their kernels left them. */
+int rr_rrf_fuse_runs(const int64_t* const* run_ptrs_host, const int32_t* run_len_host,
+                     int32_t n_runs, int32_t q, double rrf_k, int32_t k, int64_t* out_idx,
+                     double* out_score, int32_t* out_count, void* stream);
 
 /* ---- merge of per-shard candidate lists after the NCCL allgather.
  * Inputs are [q, n_in] lists (n_in = shards * k); idx < 0 marks padding; idx < 2^32
@@ -239,6 +277,18 @@ int rr_synth_doc_lengths(int32_t* out, int64_t row_start, int64_t n, uint64_t se
                          int32_t mean_len, void* stream);
 int rr_synth_zipf_tokens(int32_t* out, int64_t pos_start, int64_t n, uint64_t seed,
                          const uint32_t* cdf, int32_t n_terms, void* stream);
+
+/* ---- peak probes (measurement aids for bench.py / tools/peak_probe.py, not on the product path).
+ * Each call times its own kernel with CUDA events on `stream` (best of 5) and synchronises.
+ *   rr_probe_popc    32-bit POPC instructions per second over a full grid;
+ *   rr_probe_smem    bytes per second of 128-bit shared-memory loads over a full grid;
+ *   rr_probe_i8_mma  int8 operations per second (2 per MAC) of back-to-back
+ *                    tcgen05.mma.kind::i8 from resident operands, one CTA per SM:
+ *                    mode 0 = M128 N256 K32, A and B in shared memory; 1 = M128 N128, both in shared
+ *                    memory; 2 = M128 N128, A in tensor memory (the batched Hamming scan's form). */
+int rr_probe_popc(int32_t iters, double* out_popc32_per_s_host, void* stream);
+int rr_probe_smem(int32_t iters, double* out_bytes_per_s_host, void* stream);
+int rr_probe_i8_mma(int32_t mode, int32_t iters, double* out_ops_per_s_host, void* stream);
 
 #ifdef __cplusplus
 }

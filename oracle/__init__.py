@@ -33,7 +33,9 @@ from .quantize import (  # noqa: F401
     quantize_int8_symmetric_query,
 )
 from .hamming import hamming_distances, hamming_topk  # noqa: F401
-from .rescore import rescore_f32, rescore_i8_exact, exact_cosine_topk, int8_exact_topk  # noqa: F401
+from .rescore import (  # noqa: F401
+    rescore_f32, rescore_i8_exact, exact_cosine_topk, int8_exact_topk, int8_exact_topk_blas,
+)
 from .bm25 import tokenize, BM25Oracle  # noqa: F401
 from .rrf import rrf_fuse  # noqa: F401
 from .flow import two_stage_search  # noqa: F401

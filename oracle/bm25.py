@@ -49,7 +49,12 @@ class BM25Oracle:
         b: float = 0.75,
         idf: Optional[np.ndarray] = None,
         avgdl: Optional[float] = None,
+        only_terms: Optional[Iterable[int]] = None,
     ) -> None:
+        """only_terms: index just these term ids (document lengths, avgdl and the document
+        count still come from ALL tokens, and df / idf of an indexed term only depend on its own
+        postings, so scores of queries made of these terms are unchanged) - lets a full-size
+        corpus be checked on a sample of queries without sorting every token."""
         self.k1 = float(k1)
         self.b = float(b)
         doc_ptr = np.asarray(doc_ptr, dtype=np.int64)
@@ -64,16 +69,28 @@ class BM25Oracle:
 
         # inverted CSR: sort (term, row) pairs, collapse repeats into tf
         rows = np.repeat(np.arange(self.n_docs, dtype=np.int64), self.doc_len)
+        if only_terms is not None:
+            keep = np.isin(doc_terms, np.fromiter((int(t) for t in only_terms), dtype=np.int64))
+            rows, doc_terms = rows[keep], doc_terms[keep]
         key = doc_terms * np.int64(max(self.n_docs, 1)) + rows
+        del rows
         key.sort(kind="stable")
-        uniq, tf = np.unique(key, return_counts=True)
+        if key.size:
+            head = np.empty(key.size, dtype=bool)
+            head[0] = True
+            np.not_equal(key[1:], key[:-1], out=head[1:])
+            first = np.flatnonzero(head)
+            uniq = key[first]
+            tf = np.diff(np.append(first, key.size))
+        else:
+            uniq, tf = key, np.zeros(0, dtype=np.int64)
+        del key
         self.post_term = (uniq // max(self.n_docs, 1)).astype(np.int64)
         self.post_row = (uniq % max(self.n_docs, 1)).astype(np.int64)
         self.post_tf = tf.astype(np.int64)
+        self.df = np.bincount(self.post_term, minlength=self.n_terms).astype(np.int64)
         self.term_ptr = np.zeros(self.n_terms + 1, dtype=np.int64)
-        np.add.at(self.term_ptr, self.post_term + 1, 1)
-        np.cumsum(self.term_ptr, out=self.term_ptr)
-        self.df = np.diff(self.term_ptr)
+        np.cumsum(self.df, out=self.term_ptr[1:])
 
         if idf is None:
             # bm25_index.py:131-135, scalar np.log per term exactly as the reference
@@ -143,5 +160,12 @@ class BM25Oracle:
         pos = np.nonzero(s > 0)[0]
         if pos.size == 0:
             return np.empty(0, np.int64), np.empty(0, np.float64)
+        if pos.size > top_k:
+            # everything at or above the k-th largest score, then the canonical order among those
+            # (same result as sorting all positive scores; the reference also partitions first,
+            # bm25_index.py:258-262)
+            sp = s[pos]
+            kth = np.partition(sp, pos.size - top_k)[pos.size - top_k]
+            pos = pos[sp >= kth]
         order = pos[np.lexsort((pos, -s[pos]))][:top_k]
         return order.astype(np.int64), s[order]

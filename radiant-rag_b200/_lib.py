@@ -59,13 +59,22 @@ PROTOTYPES = {
     "rr_int8_search_topk": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _sz, _p]),
     "rr_bm25_topk_workspace_bytes": (_sz, [_i32, _i32, _i32]),
     "rr_bm25_topk": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i64, _p, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
+    "rr_bm25_fast_workspace_bytes": (_sz, [_i32, _i32, _i64, _i32, _i32]),
+    "rr_bm25_topk_fast": (_i32, [_p, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i64, _p, _i32, _i32, _i32, _i64,
+                                 _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "rr_bm25_timing": (_i32, [_i32]),
+    "rr_bm25_last_timing_ms": (_i32, [_p]),
     "rr_bm25_impacts": (_i32, [_p, _p, _p, _i64, _f64, _f64, _f64, _p, _p]),
     "rr_rrf_fuse": (_i32, [_p, C.POINTER(_i32), _i32, _i32, _f64, _i32, _p, _p, _p, _p]),
+    "rr_rrf_fuse_runs": (_i32, [C.POINTER(_p), C.POINTER(_i32), _i32, _i32, _f64, _i32, _p, _p, _p, _p]),
     "rr_merge_hamming": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "rr_pack_hamming": (_i32, [_p, _p, _i64, _p, _p]),
     "rr_merge_hamming_gathered": (_i32, [_p, _i32, _i32, _i32, _i32, _p, _p, _p]),
     "rr_merge_scores_f64": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "rr_merge_scores_i32": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
+    "rr_probe_popc": (_i32, [_i32, C.POINTER(_f64), _p]),
+    "rr_probe_smem": (_i32, [_i32, C.POINTER(_f64), _p]),
+    "rr_probe_i8_mma": (_i32, [_i32, _i32, C.POINTER(_f64), _p]),
     "rr_synth_rows_f32": (_i32, [_p, _i64, _i64, _i32, _u64, _i32, _p]),
     "rr_synth_query_rows_f32": (_i32, [_p, _i64, _i64, _i32, _u64, _i64, _i32, _p]),
     "rr_synth_doc_lengths": (_i32, [_p, _i64, _i64, _u64, _i32, _p]),
@@ -81,8 +90,8 @@ launch_count = 0
 _KERNELS_PER_CALL = {
     "rr_quantize_ubinary": 1, "rr_quantize_int8": 1, "rr_hamming_topk": 2, "rr_rescore_f32": 1,
     "rr_score_candidates_f32": 1, "rr_rank_scored_f32": 1, "rr_rescore_i8": 1,
-    "rr_exact_search_f32": 2, "rr_int8_search_topk": 2, "rr_bm25_topk": 2, "rr_bm25_impacts": 1,
-    "rr_rrf_fuse": 1, "rr_merge_hamming": 1, "rr_merge_scores_f64": 1, "rr_merge_scores_i32": 1,
+    "rr_exact_search_f32": 2, "rr_int8_search_topk": 2, "rr_bm25_topk": 2, "rr_bm25_topk_fast": 4, "rr_bm25_impacts": 1,
+    "rr_rrf_fuse": 1, "rr_rrf_fuse_runs": 1, "rr_merge_hamming": 1, "rr_merge_scores_f64": 1, "rr_merge_scores_i32": 1,
     "rr_pack_hamming": 1, "rr_merge_hamming_gathered": 1,
     "rr_unpack_codes_pm1": 1, "rr_tc_dense_keys": 1, "rr_hamming_topk_tc": 5, "rr_int8_search_topk_tc": 5,
     "rr_synth_rows_f32": 1, "rr_synth_query_rows_f32": 1, "rr_synth_doc_lengths": 1,

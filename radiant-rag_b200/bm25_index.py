@@ -65,16 +65,30 @@ class Bm25DeviceIndex:
     """Tile-sharded inverted CSR + per-posting float64 impacts in HBM (one shard).
 
     tile t owns rows [t*tile_docs, (t+1)*tile_docs); postings are grouped by
-    (tile, term); inside a segment they are interleaved over row % 16 (bank-conflict-free
-    accumulation, see _bank_interleave) or ascending by row (bank_interleave=False):
+    (tile, term); inside a segment rows ascend (or, with bank_interleave=True, cycle over
+    row % 16 - the exact kernel's conflict-free order, which the batched path cannot use):
         tile_term_ptr int64 [n_tiles, n_terms+1]
-        post_row      int32 [P]   (read as uint32 by the kernel)
+        post_row      int32 [P]   (read as uint32 by the kernels)
         post_impact   f64   [P]   idf_t * (tf*(k1+1)) / (tf + k1*((1-b) + (b*len)/avgdl))
+    For the batched filter-and-refine path (csrc/bm25_fast.cu) the <= 32 terms with the largest
+    document frequency ("head" terms: most of the posting mass under Zipf) are ALSO kept as
+    dense float64 columns per tile:
+        head_slot     int32 [n_terms]                 slot of a head term, -1 otherwise
+        head_imp      f64   [n_tiles, n_head, tile_docs]  impact, 0.0 where the term is absent
     """
+
+    FAST_MIN_DOCS = 65_536   # below this the exact kernel alone is as fast (few tiles)
+    FAST_MAX_TILE = 1024
+    MAX_HEAD = 32
+    MAX_TABLE_BYTES = 8 << 30  # [n_tiles, n_terms+1] int64 offset table
 
     def __init__(self, device: torch.device, n_docs: int, n_terms: int, tile_docs: int,
                  tile_term_ptr: torch.Tensor, post_row: torch.Tensor, post_impact: torch.Tensor,
-                 row_base: int = 0) -> None:
+                 row_base: int = 0, head_slot: Optional[torch.Tensor] = None,
+                 head_imp: Optional[torch.Tensor] = None, fast_ok: bool = False) -> None:
+        if row_base + n_docs >= (1 << 32):
+            # the (score, row) merge keys carry rows as 32-bit values (csrc/merge.cuh)
+            raise ValueError(f"global rows up to {row_base + n_docs} do not fit the 32-bit row field of the BM25 merge")
         self.device = device
         self.n_docs = n_docs
         self.n_terms = n_terms
@@ -84,6 +98,13 @@ class Bm25DeviceIndex:
         self.post_row = post_row
         self.post_impact = post_impact
         self.row_base = row_base
+        self.head_slot = head_slot
+        self.head_imp = head_imp
+        self.n_head = int(head_imp.shape[1]) if head_imp is not None else 0
+        self.fast_ok = bool(fast_ok)
+        self.fast_min_docs = self.FAST_MIN_DOCS
+        self._inexact: Optional[torch.Tensor] = None  # device u32: flagged queries of unchecked calls
+        self.last_flagged = 0                          # queries the last checked call had to redo
 
     @property
     def n_postings(self) -> int:
@@ -96,14 +117,17 @@ class Bm25DeviceIndex:
         doc_terms,
         n_terms: int,
         idf,
-        avgdl: float,
+        avgdl: Optional[float],
         k1: float,
         b: float,
         device=0,
-        tile_docs: int = 8192,
+        tile_docs: int = 1024,
         row_base: int = 0,
         doc_len=None,
-        bank_interleave: bool = True,
+        bank_interleave: bool = False,
+        head_terms: int = 32,
+        sharded: bool = False,
+        group: Any = None,
     ) -> "Bm25DeviceIndex":
         """doc_ptr int64 [N+1] / doc_terms int32 [T]: the documents of THIS shard as CSR of
         term ids; idf f64 [n_terms] (0 for unknown terms), avgdl, k1, b: global tables
@@ -113,7 +137,12 @@ class Bm25DeviceIndex:
         reference keeps ``doc_lengths`` separately).  Sorting / counting uses torch on the
         device (index build is not the hot path); impacts come from rr_bm25_impacts.
         bank_interleave: order each (tile, term) segment round-robin over row % 16 (see
-        _bank_interleave); a document occurs once per segment so the order is free."""
+        _bank_interleave) instead of ascending rows; disables the batched path.
+        head_terms: how many of the most frequent terms also get dense per-tile columns.
+        sharded=True (one process per GPU, torch.distributed initialised): these documents are one
+        row block of a larger corpus - with idf=None / avgdl=None the document frequencies, the
+        document count and the token count are summed over the ranks of `group` first, so every
+        shard bakes the GLOBAL idf / avgdl into its impacts."""
         dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         _lib.init(dev.index or 0)
         ptr = to_device(doc_ptr, dev, torch.int64)
@@ -124,9 +153,18 @@ class Bm25DeviceIndex:
             z64 = torch.zeros((1, max(v, 0) + 1), dtype=torch.int64, device=dev)
             return cls(dev, 0, v, tile_docs, z64, torch.zeros(0, dtype=torch.int32, device=dev),
                        torch.zeros(0, dtype=torch.float64, device=dev), row_base)
+        n_tiles = (n + tile_docs - 1) // tile_docs
+        if n_tiles * (v + 1) * 8 > cls.MAX_TABLE_BYTES:
+            # the dense [tile, term] offset table is what limits small tiles on large vocabularies:
+            # widen the tiles (the exact kernel takes up to 16384 documents per tile)
+            while tile_docs < 16384 and ((n + tile_docs - 1) // tile_docs) * (v + 1) * 8 > cls.MAX_TABLE_BYTES:
+                tile_docs *= 2
+            n_tiles = (n + tile_docs - 1) // tile_docs
+            if n_tiles * (v + 1) * 8 > cls.MAX_TABLE_BYTES:
+                raise ValueError(f"BM25 offset table of {n_tiles} tiles x {v} terms exceeds {cls.MAX_TABLE_BYTES >> 30} GiB; "
+                                 "shard the documents over more GPUs or prune the vocabulary")
         lens = ptr[1:] - ptr[:-1]
         dlen = lens.to(torch.int32) if doc_len is None else to_device(doc_len, dev, torch.int32)
-        n_tiles = (n + tile_docs - 1) // tile_docs
         rows = torch.repeat_interleave(torch.arange(n, dtype=torch.int64, device=dev), lens)
         # key = (tile * V + term) * tile_docs + row_in_tile  -> sorted by (tile, term, row)
         key = ((rows // tile_docs) * v + terms) * tile_docs + (rows % tile_docs)
@@ -136,23 +174,37 @@ class Bm25DeviceIndex:
         del key
         if bank_interleave and ukey.numel() > 1:
             ukey, tf = cls._bank_interleave(ukey, tf, tile_docs)
-        tt = ukey // tile_docs  # tile * V + term
+        tt = ukey // tile_docs  # tile * V + term, non-decreasing
         post_row64 = (tt // v) * tile_docs + (ukey % tile_docs)
         term = tt % v
-        counts = torch.bincount(tt, minlength=n_tiles * v)
-        csum = torch.zeros(n_tiles * v + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(counts, 0, out=csum[1:])
-        del counts, tt, ukey
-        gather = (torch.arange(n_tiles, dtype=torch.int64, device=dev)[:, None] * v
-                  + torch.arange(v + 1, dtype=torch.int64, device=dev)[None, :])
-        tile_term_ptr = csum[gather].contiguous()
-        del gather, csum
-        if idf is None:
-            df = torch.bincount(term, minlength=v).cpu().numpy()
-            idf = np.zeros(v, dtype=np.float64)
-            for t in np.nonzero(df)[0]:
-                d = int(df[t])
-                idf[t] = np.log((n - d + 0.5) / (d + 0.5) + 1.0)
+        del ukey
+        # offsets of every (tile, term) segment: ONE searchsorted over the sorted segment ids, laid
+        # out [n_tiles, V+1] by a strided view of the flat [n_tiles*V + 1] result (row t of the
+        # table is flat[t*V : t*V + V + 1]; no dense bincount / cumsum / gather temporaries)
+        flat = torch.searchsorted(tt, torch.arange(n_tiles * v + 1, dtype=torch.int64, device=dev))
+        del tt
+        tile_term_ptr = flat.as_strided((n_tiles, v + 1), (v, 1)).contiguous()
+        del flat
+        df_dev = torch.bincount(term, minlength=v)
+        if idf is None or avgdl is None:
+            df_glob = df_dev.clone()
+            stats = torch.tensor([n, int(lens.sum().item()) if doc_len is None else int(dlen.sum(dtype=torch.int64).item())],
+                                 dtype=torch.int64, device=dev)
+            if sharded:
+                import torch.distributed as dist
+                if dist.is_initialized() and dist.get_world_size(group) > 1:
+                    dist.all_reduce(df_glob, group=group)
+                    dist.all_reduce(stats, group=group)
+            n_glob, tok_glob = (int(x) for x in stats.cpu().tolist())
+            if avgdl is None:
+                avgdl = tok_glob / n_glob  # Python ints -> one double divide (bm25_index.py:117)
+            if idf is None:
+                df = df_glob.cpu().numpy()
+                idf = np.zeros(v, dtype=np.float64)
+                for t in np.nonzero(df)[0]:
+                    d = int(df[t])
+                    idf[t] = np.log((n_glob - d + 0.5) / (d + 0.5) + 1.0)
+            del df_glob
         idf_t = to_device(idf, dev, torch.float64)
         post_idf = idf_t[term].contiguous()
         post_len = dlen[post_row64].contiguous()
@@ -160,16 +212,44 @@ class Bm25DeviceIndex:
         post_impact = torch.empty(post_tf.shape, dtype=torch.float64, device=dev)
         _lib.call("rr_bm25_impacts", post_tf.data_ptr(), post_len.data_ptr(), post_idf.data_ptr(),
                   post_tf.numel(), float(k1), float(b), float(avgdl), post_impact.data_ptr(), _stream())
+        del post_idf, post_len, post_tf
         post_row = post_row64.to(torch.int32).contiguous()
+        # ---- head terms: dense float64 columns per tile for the batched path
+        head_slot = head_imp = None
+        fast_ok = False
+        if (not bank_interleave and tile_docs % 128 == 0 and tile_docs <= cls.FAST_MAX_TILE
+                and n < (1 << 32)):
+            lo, hi = torch.aminmax(post_impact)
+            finite = bool(torch.isfinite(post_impact).all().item())
+            # float32 filter scores need positive impacts well inside the float32 range
+            fast_ok = finite and float(lo) >= 2.0 ** -100 and float(hi) <= 2.0 ** 100
+        if fast_ok:
+            n_head = min(int(head_terms), cls.MAX_HEAD, v)
+            order = torch.argsort(df_dev, descending=True, stable=True)[:n_head]
+            order = order[df_dev[order] * 8 >= n]  # dense enough to pay for a column
+            n_head = int(order.numel())
+            head_slot = torch.full((v,), -1, dtype=torch.int32, device=dev)
+            head_slot[order] = torch.arange(n_head, dtype=torch.int32, device=dev)
+            head_imp = torch.zeros((n_tiles, max(n_head, 1), tile_docs), dtype=torch.float64, device=dev)
+            if n_head:
+                slot = head_slot[term].to(torch.int64)
+                sel = slot >= 0
+                pos = ((post_row64[sel] // tile_docs) * n_head + slot[sel]) * tile_docs + post_row64[sel] % tile_docs
+                head_imp.view(-1)[pos] = post_impact[sel]
+                del slot, sel, pos
+            else:
+                head_imp = head_imp[:, :0, :].contiguous()
+        del post_row64, term, df_dev
         torch.cuda.current_stream().synchronize()  # temporaries die here
-        return cls(dev, n, v, tile_docs, tile_term_ptr, post_row, post_impact, row_base)
+        return cls(dev, n, v, tile_docs, tile_term_ptr, post_row, post_impact, row_base,
+                   head_slot=head_slot, head_imp=head_imp, fast_ok=fast_ok)
 
     SMEM_BANKS64 = 16  # 8-byte accumulators: 16 bank pairs per half-warp
 
     @classmethod
     def _bank_interleave(cls, ukey: torch.Tensor, tf: torch.Tensor, tile_docs: int):
         """Reorder the postings of every (tile, term) segment so that consecutive postings
-        cycle through row % 16: the query kernel's shared-memory read-modify-write of the
+        cycle through row % 16: the exact kernel's shared-memory read-modify-write of the
         float64 accumulators (16 lanes of a half-warp = 16 consecutive postings) then hits
         16 different bank pairs instead of a random multiset (~3-way conflicts).
         ukey = (tile*V + term) * tile_docs + row_in_tile, sorted."""
@@ -191,15 +271,8 @@ class Bm25DeviceIndex:
         order = perm1[perm2]
         return ukey[order].contiguous(), tf[order].contiguous()
 
-    def search_batch(self, q_terms, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """q_terms int32 [Q, L] term ids in query-token order, -1 = unknown / padding.
-        -> (idx int64 [Q,k] (-1 padded), score f64 [Q,k], count int32 [Q]);
-        order (score desc, row asc), score > 0 only."""
-        if torch.cuda.current_device() != (self.device.index or 0):
-            torch.cuda.set_device(self.device)
-        qt = to_device(q_terms, self.device, torch.int32)
-        if qt.ndim == 1:
-            qt = qt[None, :]
+    # ---- search ----------------------------------------------------------------------
+    def _search_exact(self, qt: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         q, ql = qt.shape
         score = torch.empty((q, k), dtype=torch.float64, device=self.device)
         idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
@@ -212,6 +285,100 @@ class Bm25DeviceIndex:
                   qt.data_ptr(), q, ql, k, self.row_base, score.data_ptr(), idx.data_ptr(),
                   count.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
         return idx, score, count
+
+    def _search_fast(self, qt: torch.Tensor, k: int, counter: torch.Tensor
+                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        q, ql = qt.shape
+        score = torch.empty((q, k), dtype=torch.float64, device=self.device)
+        idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        count = torch.empty((q,), dtype=torch.int32, device=self.device)
+        flags = torch.empty((q,), dtype=torch.uint8, device=self.device)
+        lib = _lib.load()
+        ws_bytes = lib.rr_bm25_fast_workspace_bytes(self.n_tiles, self.tile_docs, self.n_docs, q, k)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+        _lib.call("rr_bm25_topk_fast", self.tile_term_ptr.data_ptr(), self.post_row.data_ptr(),
+                  self.post_impact.data_ptr(), self.head_slot.data_ptr(),
+                  self.head_imp.data_ptr() if self.n_head else None, self.n_head, self.n_tiles,
+                  self.tile_docs, self.n_terms, self.n_docs, qt.data_ptr(), q, ql, k, self.row_base,
+                  score.data_ptr(), idx.data_ptr(), count.data_ptr(), flags.data_ptr(), counter.data_ptr(),
+                  ws.data_ptr(), ws_bytes, _stream())
+        return idx, score, count, flags
+
+    def uses_fast_path(self, q: int, k: int) -> bool:
+        return bool(self.fast_ok and self.n_docs >= self.fast_min_docs and q >= 1 and k <= 1000)
+
+    def search_batch(self, q_terms, k: int, check: bool = True, exact: bool = False
+                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """q_terms int32 [Q, L] term ids in query-token order, -1 = unknown / padding.
+        -> (idx int64 [Q,k] (-1 padded), score f64 [Q,k], count int32 [Q]);
+        order (score desc, row asc), score > 0 only; float64 scores equal the reference's bits.
+
+        Large indexes run the batched filter-and-refine path (csrc/bm25_fast.cu), which proves
+        the exactness of every query it answers and flags the ones it cannot (degenerate ties at
+        the bound); a checked call (one device sync at its end) redoes those with the exact
+        kernel.  check=False skips the sync - for CUDA-graph capture - and accumulates the number
+        of flagged queries in ``inexact_total()`` for the caller to verify.  exact=True forces the
+        exact kernel for the whole batch."""
+        if torch.cuda.current_device() != (self.device.index or 0):
+            torch.cuda.set_device(self.device)
+        qt = to_device(q_terms, self.device, torch.int32)
+        if qt.ndim == 1:
+            qt = qt[None, :]
+        q, ql = qt.shape
+        if exact or ql == 0 or self.n_docs == 0 or not self.uses_fast_path(q, k):
+            return self._search_exact(qt, k)
+        if not check:
+            if self._inexact is None:
+                self._inexact = torch.zeros(1, dtype=torch.int32, device=self.device)
+            idx, score, count, _flags = self._search_fast(qt, k, self._inexact)
+            return idx, score, count
+        counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        idx, score, count, flags = self._search_fast(qt, k, counter)
+        self.last_flagged = int(counter.item())
+        if self.last_flagged:
+            bad = torch.nonzero(flags).flatten()
+            r_idx, r_score, r_count = self._search_exact(qt[bad].contiguous(), k)
+            idx[bad] = r_idx
+            score[bad] = r_score
+            count[bad] = r_count
+        return idx, score, count
+
+    def inexact_total(self) -> int:
+        """Queries flagged by ``check=False`` calls since the last reset (0 = all exact)."""
+        return 0 if self._inexact is None else int(self._inexact.item())
+
+    def inexact_reset(self) -> None:
+        if self._inexact is not None:
+            self._inexact.zero_()
+
+
+def synth_zipf_corpus_device(n_docs: int, n_terms: int, seed: int, mean_len: int = 200,
+                             device=0, row_start: int = 0, chunk_docs: int = 4_000_000
+                             ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Synthetic Zipf documents [row_start, row_start + n_docs) generated ON DEVICE, bit-identical
+    to ``synthetic.zipf_corpus`` restricted to those rows (bench / parity only).
+    Document d owns the GLOBAL token positions [P(d), P(d+1)), P = prefix sum of all document
+    lengths from document 0, so a shard's tokens do not depend on how the corpus is sharded.
+    -> (doc_ptr int64 [n_docs+1] local offsets, tokens int32 [total])."""
+    from . import synthetic
+
+    dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+    _lib.init(dev.index or 0)
+    pos0 = 0
+    for lo in range(0, row_start, chunk_docs):  # global position of this shard's first token
+        m = min(chunk_docs, row_start - lo)
+        tmp = torch.empty(m, dtype=torch.int32, device=dev)
+        _lib.call("rr_synth_doc_lengths", tmp.data_ptr(), lo, m, seed, mean_len, _stream())
+        pos0 += int(tmp.sum(dtype=torch.int64).item())
+    lens = torch.empty(n_docs, dtype=torch.int32, device=dev)
+    _lib.call("rr_synth_doc_lengths", lens.data_ptr(), row_start, n_docs, seed, mean_len, _stream())
+    ptr = torch.zeros(n_docs + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens.to(torch.int64), 0, out=ptr[1:])
+    total = int(ptr[-1].item())
+    cdf_d = torch.from_numpy(synthetic.zipf_cdf_u32(n_terms).view(np.int32)).to(dev)
+    toks = torch.empty(total, dtype=torch.int32, device=dev)
+    _lib.call("rr_synth_zipf_tokens", toks.data_ptr(), pos0, total, seed, cdf_d.data_ptr(), n_terms, _stream())
+    return ptr, toks
 
 
 class BM25Index:
@@ -230,7 +397,7 @@ class BM25Index:
         b: float = 0.75,
         needs_rebuild: bool = True,
         device: int = 0,
-        tile_docs: int = 8192,
+        tile_docs: int = 1024,
     ) -> None:
         self.doc_ids: List[str] = list(doc_ids or [])
         self.doc_tokens: List[List[str]] = list(doc_tokens or [])
@@ -369,6 +536,8 @@ class BM25Index:
             if toks:
                 qt[i, : len(toks)] = self._query_term_ids(toks)
         k = max(1, min(int(top_k), _lib.RR_MAX_K))
+        if k != int(top_k):
+            logger.warning(f"BM25 top_k={top_k} outside [1, {_lib.RR_MAX_K}]: {k} results per query are returned")
         idx, score, count = self.device_index().search_batch(qt, k)
         idx_h, score_h, count_h = idx.cpu().tolist(), score.cpu().tolist(), count.cpu().tolist()
         out: List[List[Tuple[str, float]]] = []
@@ -401,7 +570,7 @@ class BM25Index:
         return index
 
     @classmethod
-    def from_reference(cls, ref_index, device: int = 0, tile_docs: int = 8192) -> "BM25Index":
+    def from_reference(cls, ref_index, device: int = 0, tile_docs: int = 1024) -> "BM25Index":
         """Adopt a live reference ``BM25Index`` INCLUDING its current idf / avgdl / df tables
         (they may be stale after incremental adds; they are copied, not recomputed)."""
         inst = cls(doc_ids=list(ref_index.doc_ids), doc_tokens=list(ref_index.doc_tokens),

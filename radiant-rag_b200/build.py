@@ -1,51 +1,79 @@
-"""Build librr_b200.so in-tree with nvcc for sm_100a (no torch dependency)."""
+"""Build librr_b200.so in-tree with nvcc for sm_100a (no torch dependency).
+
+Every .cu is compiled to its own object (in parallel, only when stale) and the objects are
+linked into one shared library; nvcc cross-compiles without a GPU, so this also runs in the
+CPU-only build container."""
 
 from __future__ import annotations
 
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
+OBJ_DIR = PKG_DIR.parent / "build" / "obj"
 LIB_PATH = PKG_DIR / "librr_b200.so"
-SOURCES = ["api.cu", "quantize.cu", "hamming.cu", "rescore.cu", "exact.cu", "bm25.cu", "rrf.cu", "synth.cu", "tc_search.cu"]
+SOURCES = ["api.cu", "quantize.cu", "hamming.cu", "rescore.cu", "exact.cu", "bm25.cu", "bm25_fast.cu",
+           "rrf.cu", "synth.cu", "tc_search.cu", "probe.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
-    "--shared",
 ]
 
 
-def _stale() -> bool:
-    if not LIB_PATH.exists():
+def _headers():
+    return list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "radiant_rag_b200.h"]
+
+
+def _obj_stale(src: Path, obj: Path) -> bool:
+    if not obj.exists():
         return True
-    t = LIB_PATH.stat().st_mtime
-    deps = list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG_DIR.parent / "include" / "radiant_rag_b200.h"]
-    return any(d.stat().st_mtime > t for d in deps)
+    t = obj.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in [src, Path(__file__)] + _headers())
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source into one shared library.  nvcc cross-compiles
-    without a GPU, so this also runs in the CPU-only build container."""
-    if not force and not _stale():
-        return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", str(LIB_PATH)] + [str(CSRC / s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+    extra = os.environ.get("RR_NVCC_EXTRA", "").split()
+    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    jobs = []
+    for s in SOURCES:
+        src, obj = CSRC / s, OBJ_DIR / (s[:-3] + ".o")
+        if force or extra or _obj_stale(src, obj):
+            cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            jobs.append((s, cmd))
+
+    def run(job):
+        name, cmd = job
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return name, res
+
+    failed = False
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
+        for name, res in pool.map(run, jobs):
+            if res.returncode != 0:
+                sys.stderr.write(f"--- {name}\n{res.stdout}{res.stderr}")
+                failed = True
+            elif verbose:
+                sys.stderr.write(f"--- {name}\n{res.stderr}")
+    if failed:
         raise RuntimeError("nvcc failed building librr_b200.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+    objs = [OBJ_DIR / (s[:-3] + ".o") for s in SOURCES]
+    if jobs or not LIB_PATH.exists() or any(o.stat().st_mtime > LIB_PATH.stat().st_mtime for o in objs):
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", str(LIB_PATH)] + [str(o) for o in objs]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed linking librr_b200.so")
     return LIB_PATH
 
 
 if __name__ == "__main__":
-    print(build_library(force=True, verbose="-v" in sys.argv))
+    print(build_library(force="-f" in sys.argv, verbose="-v" in sys.argv))

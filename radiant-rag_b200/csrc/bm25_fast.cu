@@ -1,0 +1,615 @@
+// R6, batched: BM25 top-k as filter-and-refine, with the postings shared across the query batch.
+//
+// Replaces BM25Index.search (reference radiant/storage/bm25_index.py:218-270) for BATCHES of
+// queries.  rr_bm25_topk (bm25.cu) walks every (query, tile) pair's postings out of L2 into
+// float64 accumulators and is bound by that traffic (sum_t df(t) * 12 B per query, nothing
+// shared between queries).  This path returns the SAME bits in a fraction of the time:
+//
+//   phase A  (bm25_fast_kernel)  float32 scores for every (query, document), in any order.
+//            A persistent CTA per SM owns a tile of <= 1024 documents at a time and serves ALL
+//            queries of the batch from it: the dense "head" terms of the tile (the <= 32 terms
+//            with the largest document frequency - most of the posting mass under Zipf) are
+//            staged ONCE per tile into shared memory as float32 columns and then read by every
+//            query that contains them; the sparse "tail" terms of a query are scattered into a
+//            per-warp float32 accumulator with shared-memory atomics.  One warp = one query;
+//            the score of a document lives in a register and is only compared with a bound.
+//            pass 1 (SAMPLE) runs on every s-th tile and keeps one maximum per lane;
+//            tau_q = the k'-th largest of them is a score that >= k' documents reach;
+//            pass 2 (FILTER) keeps the documents with score >= tau_q (about s * k' per query).
+//   phase B  (bm25_refine_kernel) exact float64 scores of the survivors in the reference's
+//            operation order (query-token order, __dadd_rn, impacts as rr_bm25_impacts built
+//            them), exact top-k by (score desc, row asc), score > 0.
+//
+// Exactness.  All impacts are positive, so |A - E| <= eps * E with eps = (q_len + 4) * 2^-24 for
+// the float32 score A and the reference's float64 score E of any document.  A document outside
+// the survivor list has A < tau, hence E < tau * (1 + eps).  If the k-th exact score among the
+// survivors exceeds that, no outside document can enter or tie the top-k and the result is the
+// reference's, bit for bit.  The refine kernel CHECKS this per query (and list overflow); a query
+// that fails is flagged and counted, and the caller redoes it with rr_bm25_topk.  Impacts
+// outside [2^-100, 2^100] or non-positive disable this path at index build time (bm25_index.py).
+//
+// Algorithmic bytes per batch: one pass over the index (postings * 12 B + head columns); per
+// query without sharing: sum_t df(t) * 12 B (SURVEY.md 8d reports both).
+#include "common.cuh"
+#include "select.cuh"
+
+namespace rr {
+
+constexpr int BF_WARPS = 16;
+constexpr int BF_THREADS = BF_WARPS * 32;
+constexpr int BF_MAX_HEAD = 32;
+constexpr int BF_MAX_TILE = 1024;
+constexpr int BF_ROWS4 = BF_MAX_TILE / 128;  // float4 groups a lane owns in a 1024-doc tile
+
+struct BfArgs {
+  const long long* tile_term_ptr;  // [n_tiles][n_terms + 1]
+  const u32* post_row;
+  const double* post_impact;
+  const int* head_slot;    // [n_terms] slot of a head term, -1 for tail terms
+  const double* head_imp;  // [n_tiles][n_head][tile_docs] dense float64 impacts, 0 = absent
+  int n_head;
+  int n_tiles;
+  int tile_docs;
+  int n_terms;
+  long long n_docs;
+  const int* q_terms;  // [q][q_len]
+  int q;
+  int q_len;
+  int stride;        // this pass visits tiles 0, stride, 2*stride, ...
+  int n_pass_tiles;
+  float* lane_max;   // SAMPLE out: [q][n_pass_tiles * 32]
+  const float* tau;  // FILTER in:  [q]
+  u32* list_cnt;     // FILTER out: [q]
+  u64* list;         // FILTER out: [q][cap]  float bits << 32 | local row
+  int cap;
+};
+
+struct TokenInfo {
+  int hs;        // head slot or -1
+  int len;       // tail segment length in this tile (0 for head / unknown tokens)
+  long long lo;  // first posting of the segment
+};
+
+// lane j describes query token j0 + j for this tile
+__device__ __forceinline__ TokenInfo bf_token_info(const BfArgs& a, const long long* ptr, int t) {
+  TokenInfo ti;
+  ti.hs = -1;
+  ti.len = 0;
+  ti.lo = 0;
+  if (t >= 0 && t < a.n_terms) {  // unknown token: skipped (bm25_index.py:238-239)
+    // three independent loads (the bounds of a head term are fetched and dropped: one load
+    // latency per query instead of two)
+    const int hs = __ldg(a.head_slot + t);
+    const long long lo = __ldg(ptr + t);
+    const long long hi = __ldg(ptr + t + 1);
+    ti.hs = hs;
+    ti.lo = lo;
+    ti.len = hs < 0 ? (int)(hi - lo) : 0;
+  }
+  return ti;
+}
+
+template <bool SAMPLE>
+__global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a) {
+  extern __shared__ __align__(16) unsigned char bf_smem[];
+  const int T = a.tile_docs;
+  float* cols = reinterpret_cast<float*>(bf_smem);       // [n_head][T]
+  float* tacc_all = cols + (size_t)a.n_head * T;         // [BF_WARPS][T]
+  __shared__ int s_excl[BF_WARPS][33];
+  __shared__ long long s_lo[BF_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tacc = tacc_all + (size_t)warp * T;
+  const int t4 = T >> 2;  // float4 per column
+
+  for (int pt = blockIdx.x; pt < a.n_pass_tiles; pt += gridDim.x) {
+    const int tile = pt * a.stride;
+    const long long tile_lo = (long long)tile * T;
+    const int rows_here = (int)min((long long)T, a.n_docs - tile_lo);
+    __syncthreads();  // every warp is done with the previous tile's columns
+    {
+      const double2* src = reinterpret_cast<const double2*>(a.head_imp + (size_t)tile * a.n_head * T);
+      float2* dst = reinterpret_cast<float2*>(cols);
+      const int n2 = (a.n_head * T) >> 1;
+      for (int i = threadIdx.x; i < n2; i += BF_THREADS) {
+        const double2 v = __ldg(src + i);
+        dst[i] = make_float2((float)v.x, (float)v.y);
+      }
+    }
+    __syncthreads();
+    const long long* ptr = a.tile_term_ptr + (size_t)tile * (a.n_terms + 1);
+
+    // software pipeline over this warp's queries: token ids two queries ahead, their head
+    // slots / segment bounds one query ahead (a chain of dependent loads otherwise)
+    int t_n2 = -1, t_n1 = -1;
+    TokenInfo ti_n1;
+    ti_n1.hs = -1;
+    ti_n1.len = 0;
+    ti_n1.lo = 0;
+    if (warp < a.q) {
+      t_n1 = (lane < a.q_len) ? __ldg(a.q_terms + (size_t)warp * a.q_len + lane) : -1;
+      ti_n1 = bf_token_info(a, ptr, t_n1);
+    }
+    if (warp + BF_WARPS < a.q)
+      t_n2 = (lane < a.q_len) ? __ldg(a.q_terms + (size_t)(warp + BF_WARPS) * a.q_len + lane) : -1;
+
+    for (int qi = warp; qi < a.q; qi += BF_WARPS) {
+      TokenInfo ti = ti_n1;
+      const int t_cur_next = t_n2;  // tokens of query qi + BF_WARPS
+      if (qi + 2 * BF_WARPS < a.q)
+        t_n2 = (lane < a.q_len) ? __ldg(a.q_terms + (size_t)(qi + 2 * BF_WARPS) * a.q_len + lane) : -1;
+      else
+        t_n2 = -1;
+      if (qi + BF_WARPS < a.q) ti_n1 = bf_token_info(a, ptr, t_cur_next);
+      float tau = 0.0f;
+      if (!SAMPLE) tau = __ldg(a.tau + qi);
+
+      // zero the tail accumulator
+      for (int i = lane; i < t4; i += 32) reinterpret_cast<float4*>(tacc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      int head_cnt = 0;  // lane h: multiplicity of head slot h in this query
+      __syncwarp();
+
+      for (int j0 = 0; j0 < a.q_len; j0 += 32) {
+        if (j0 > 0) {  // long queries: later chunks are not prefetched
+          const int t = (j0 + lane < a.q_len) ? __ldg(a.q_terms + (size_t)qi * a.q_len + j0 + lane) : -1;
+          ti = bf_token_info(a, ptr, t);
+        }
+        // head tokens: count multiplicities per slot
+        unsigned hm = __ballot_sync(0xffffffffu, ti.hs >= 0);
+        while (hm) {
+          const int src = __ffs(hm) - 1;
+          hm &= hm - 1;
+          const int h = __shfl_sync(0xffffffffu, ti.hs, src);
+          if (lane == h) ++head_cnt;
+        }
+        // tail tokens: all their postings of this tile as ONE flat index space, so that the
+        // loads of different tokens are independent and in flight together
+        int incl = ti.len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total > 0) {
+          s_excl[warp][lane] = incl - ti.len;
+          s_lo[warp][lane] = ti.lo;
+          __syncwarp();
+          for (int f0 = 0; f0 < total; f0 += 128) {
+            u32 row[4];
+            double imp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int f = f0 + u * 32 + lane;
+              row[u] = 0xFFFFFFFFu;
+              imp[u] = 0.0;
+              if (f < total) {
+                int j = 0;  // largest j with s_excl[j] <= f
+#pragma unroll
+                for (int step = 16; step >= 1; step >>= 1)
+                  if (s_excl[warp][j + step] <= f) j += step;
+                const long long p = s_lo[warp][j] + (f - s_excl[warp][j]);
+                row[u] = __ldg(a.post_row + p);
+                imp[u] = __ldg(a.post_impact + p);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (row[u] != 0xFFFFFFFFu) atomicAdd(tacc + (int)((long long)row[u] - tile_lo), (float)imp[u]);
+          }
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+
+      // scores of the 32 documents this lane owns: tail sum + head columns
+      float4 acc[BF_ROWS4];
+#pragma unroll
+      for (int i = 0; i < BF_ROWS4; ++i) {
+        const int v = i * 32 + lane;
+        acc[i] = (v < t4) ? reinterpret_cast<const float4*>(tacc)[v] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      unsigned hm = __ballot_sync(0xffffffffu, head_cnt > 0);
+      while (hm) {
+        const int h = __ffs(hm) - 1;
+        hm &= hm - 1;
+        const float c = (float)__shfl_sync(0xffffffffu, head_cnt, h);
+        const float4* cp = reinterpret_cast<const float4*>(cols + (size_t)h * T);
+#pragma unroll
+        for (int i = 0; i < BF_ROWS4; ++i) {
+          const int v = i * 32 + lane;
+          if (v < t4) {
+            const float4 x = cp[v];
+            acc[i].x = fmaf(c, x.x, acc[i].x);
+            acc[i].y = fmaf(c, x.y, acc[i].y);
+            acc[i].z = fmaf(c, x.z, acc[i].z);
+            acc[i].w = fmaf(c, x.w, acc[i].w);
+          }
+        }
+      }
+
+      if (SAMPLE) {
+        float m = 0.0f;
+#pragma unroll
+        for (int i = 0; i < BF_ROWS4; ++i) {
+          const int d = (i * 32 + lane) * 4;
+          if (d + 0 < rows_here) m = fmaxf(m, acc[i].x);
+          if (d + 1 < rows_here) m = fmaxf(m, acc[i].y);
+          if (d + 2 < rows_here) m = fmaxf(m, acc[i].z);
+          if (d + 3 < rows_here) m = fmaxf(m, acc[i].w);
+        }
+        a.lane_max[(size_t)qi * ((size_t)a.n_pass_tiles * 32) + (size_t)pt * 32 + lane] = m;
+      } else {
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < BF_ROWS4; ++i) {
+          const float mx = fmaxf(fmaxf(acc[i].x, acc[i].y), fmaxf(acc[i].z, acc[i].w));
+          any |= (mx >= tau) && (mx > 0.0f);
+        }
+        if (any) {  // rare: about s * k' survivors per query over the whole corpus
+#pragma unroll
+          for (int i = 0; i < BF_ROWS4; ++i) {
+            const int d = (i * 32 + lane) * 4;
+            const float v4[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (v4[e] >= tau && v4[e] > 0.0f && d + e < rows_here) {
+                const u32 slot = atomicAdd(a.list_cnt + qi, 1u);
+                if (slot < (u32)a.cap)
+                  a.list[(size_t)qi * a.cap + slot] =
+                      ((u64)__float_as_uint(v4[e]) << 32) | (u64)(u32)(tile_lo + d + e);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();  // tacc is re-zeroed by the next query
+    }
+  }
+}
+
+// tau_q = the kp-th largest per-lane maximum of the sampled tiles (0 = no bound).
+struct BtArgs {
+  const float* lane_max;  // [q][m]
+  long long m;
+  int kp;
+  int cap;
+  float* tau;
+};
+
+__global__ void __launch_bounds__(256) bm25_tau_kernel(const BtArgs a) {
+  extern __shared__ __align__(16) unsigned char bt_smem[];
+  u64* s_k1 = reinterpret_cast<u64*>(bt_smem);
+  u32* s_k2 = reinterpret_cast<u32*>(s_k1 + a.cap);
+  __shared__ SelectScratch<256> sc;
+  const int q = blockIdx.x;
+  const float* v = a.lane_max + (size_t)q * a.m;
+  auto get = [&](long long i, u64& x, u32& y) {
+    const float s = v[i];
+    x = (s > 0.0f) ? (u64)(~f32_orderable(s)) : K1_INVALID;
+    y = (u32)i;
+  };
+  const int got = block_select_sorted<256, true>(get, a.m, a.kp, s_k1, s_k2, a.cap, sc);
+  if (threadIdx.x == 0) a.tau[q] = (got == a.kp) ? f32_from_orderable((u32)(~s_k1[a.kp - 1])) : 0.0f;
+}
+
+struct BrArgs {
+  const long long* tile_term_ptr;
+  const u32* post_row;
+  const double* post_impact;
+  const int* head_slot;
+  const double* head_imp;
+  int n_head;
+  int tile_docs;
+  int n_terms;
+  const int* q_terms;
+  int q_len;
+  const u32* list_cnt;
+  const u64* list;
+  int cap;
+  const float* tau;
+  double* escore;  // [q][cap] workspace
+  int k;
+  int sel_cap;
+  long long row_base;
+  double eps;
+  double* out_score;
+  long long* out_idx;
+  int* out_count;
+  unsigned char* flags;
+  u32* counter;
+};
+
+__global__ void __launch_bounds__(256) bm25_refine_kernel(const BrArgs a) {
+  extern __shared__ __align__(16) unsigned char br_smem[];
+  u64* s_k1 = reinterpret_cast<u64*>(br_smem);
+  u32* s_k2 = reinterpret_cast<u32*>(s_k1 + a.sel_cap);
+  int* s_term = reinterpret_cast<int*>(s_k2 + a.sel_cap);  // [q_len]
+  int* s_hs = s_term + a.q_len;                            // [q_len]
+  __shared__ SelectScratch<256> sc;
+  const int q = blockIdx.x;
+  const u32 cnt = a.list_cnt[q];
+  const int n_s = (int)min(cnt, (u32)a.cap);
+  for (int j = threadIdx.x; j < a.q_len; j += 256) {
+    int t = a.q_terms[(size_t)q * a.q_len + j];
+    int hs = -1;
+    if (t >= 0 && t < a.n_terms) hs = a.head_slot[t];
+    else t = -1;
+    s_term[j] = t;
+    s_hs[j] = hs;
+  }
+  __syncthreads();
+  const u64* lst = a.list + (size_t)q * a.cap;
+  double* es = a.escore + (size_t)q * a.cap;
+  const int T = a.tile_docs;
+  for (int i = threadIdx.x; i < n_s; i += 256) {
+    const u32 row = (u32)lst[i];
+    const int tile = (int)(row / (u32)T);
+    const int r = (int)(row - (u32)tile * (u32)T);
+    const long long* ptr = a.tile_term_ptr + (size_t)tile * (a.n_terms + 1);
+    const double* hcol = a.head_imp + (size_t)tile * a.n_head * T + r;
+    double acc = 0.0;
+    for (int j = 0; j < a.q_len; ++j) {  // query-token order, repeats included
+      const int t = s_term[j];
+      if (t < 0) continue;
+      const int hs = s_hs[j];
+      double imp = 0.0;
+      if (hs >= 0) {
+        imp = __ldg(hcol + (size_t)hs * T);  // 0.0 where the document lacks the term: x + 0 = x
+      } else {
+        long long lo = __ldg(ptr + t), hi = __ldg(ptr + t + 1);
+        while (lo < hi) {  // rows ascend inside a (tile, term) segment
+          const long long mid = (lo + hi) >> 1;
+          const u32 rm = __ldg(a.post_row + mid);
+          if (rm < row) lo = mid + 1;
+          else if (rm > row) hi = mid;
+          else {
+            imp = __ldg(a.post_impact + mid);
+            break;
+          }
+        }
+      }
+      acc = __dadd_rn(acc, imp);
+    }
+    es[i] = acc;
+  }
+  __syncthreads();
+  auto get = [&](long long i, u64& x, u32& y) {
+    const double s = es[i];
+    x = (s > 0.0) ? ~f64_orderable(s) : K1_INVALID;  // score <= 0 dropped (bm25_index.py:267)
+    y = (u32)lst[i];
+  };
+  const int m = block_select_sorted<256, true>(get, n_s, a.k, s_k1, s_k2, a.sel_cap, sc);
+  for (int j = threadIdx.x; j < a.k; j += 256) {
+    const size_t o = (size_t)q * a.k + j;
+    if (j < m) {
+      a.out_score[o] = f64_from_orderable(~s_k1[j]);
+      a.out_idx[o] = (long long)s_k2[j] + a.row_base;
+    } else {
+      a.out_score[o] = 0.0;
+      a.out_idx[o] = -1;
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (a.out_count) a.out_count[q] = m;
+    const double tau = (double)a.tau[q];
+    bool ok = cnt <= (u32)a.cap;
+    if (tau > 0.0) {  // documents below tau were dropped: the k-th exact score must clear it
+      if (m < a.k) {
+        ok = false;
+      } else {
+        const double theta = f64_from_orderable(~s_k1[a.k - 1]);
+        if (!(theta * (1.0 - 4.0 * a.eps) > tau)) ok = false;
+      }
+    }
+    if (a.flags) a.flags[q] = ok ? 0 : 1;
+    if (!ok && a.counter) atomicAdd(a.counter, 1u);
+  }
+}
+
+static inline int bf_kprime(int k) { return k + k / 4 + 16; }
+static inline int bf_list_cap(int k) {
+  int c = 2048;
+  while (c < 16 * bf_kprime(k)) c <<= 1;
+  if (c > 32768) c = 32768;
+  return c;
+}
+// sample stride (0 = no sample pass: every positive score survives)
+static inline int bf_stride(int n_tiles, int tile_docs, long long n_docs, int k) {
+  const int cap = bf_list_cap(k), kp = bf_kprime(k);
+  if (n_docs <= cap) return 0;
+  int s = cap / (3 * kp);
+  if (s > 8) s = 8;
+  const long long by_count = (long long)n_tiles * 32 / (4LL * kp);
+  if (s > by_count) s = (int)by_count;
+  if (s < 1) s = 1;
+  return s;
+}
+
+struct BfLayout {
+  size_t lane_max, tau, list_cnt, list, escore, total;
+};
+static BfLayout bf_layout(int n_tiles, int tile_docs, long long n_docs, int q, int k) {
+  BfLayout l;
+  const int s = bf_stride(n_tiles, tile_docs, n_docs, k);
+  const size_t n_samp = s ? (size_t)(n_tiles + s - 1) / s : 0;
+  const size_t cap = (size_t)bf_list_cap(k);
+  size_t off = 0;
+  l.lane_max = off;
+  off += align_up((size_t)q * n_samp * 32 * 4, 256);
+  l.tau = off;
+  off += align_up((size_t)q * 4, 256);
+  l.list_cnt = off;
+  off += align_up((size_t)q * 4, 256);
+  l.list = off;
+  off += align_up((size_t)q * cap * 8, 256);
+  l.escore = off;
+  off += align_up((size_t)q * cap * 8, 256);
+  l.total = off + 256;
+  return l;
+}
+
+// optional per-kernel event timing (rr_bm25_timing), per host thread like rr_tc_timing:
+// events 0..4 bracket sample pass, tau, filter pass, refine
+static thread_local bool g_bf_timing = false;
+static thread_local bool g_bf_timed = false;
+static thread_local cudaEvent_t g_bf_ev[5];
+static thread_local bool g_bf_ev_ready = false;
+static void bf_mark(int i, cudaStream_t st) {
+  if (g_bf_timing && g_bf_ev_ready) cudaEventRecord(g_bf_ev[i], st);
+}
+
+}  // namespace rr
+
+using namespace rr;
+
+extern "C" int rr_bm25_timing(int32_t enable) {
+  if (enable && !g_bf_ev_ready) {
+    for (int i = 0; i < 5; ++i) RR_CUDA(cudaEventCreate(&g_bf_ev[i]));
+    g_bf_ev_ready = true;
+  }
+  g_bf_timing = enable != 0;
+  if (!g_bf_timing) g_bf_timed = false;
+  return RR_OK;
+}
+
+extern "C" int rr_bm25_last_timing_ms(float* out_ms) {
+  RR_CHECK_ARG(out_ms != nullptr, "null pointer");
+  if (!g_bf_timed) {
+    set_error("rr_bm25_last_timing_ms: no timed call (rr_bm25_timing(1) first)");
+    return RR_ERR_INVALID;
+  }
+  RR_CUDA(cudaEventSynchronize(g_bf_ev[4]));
+  for (int i = 0; i < 4; ++i) RR_CUDA(cudaEventElapsedTime(&out_ms[i], g_bf_ev[i], g_bf_ev[i + 1]));
+  return RR_OK;
+}
+
+extern "C" size_t rr_bm25_fast_workspace_bytes(int32_t n_tiles, int32_t tile_docs, int64_t n_docs,
+                                               int32_t q, int32_t k) {
+  if (n_tiles <= 0 || q <= 0 || k <= 0 || tile_docs <= 0) return 256;
+  return bf_layout(n_tiles, tile_docs, n_docs, q, k).total;
+}
+
+extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* post_row,
+                                 const double* post_impact, const int32_t* head_slot,
+                                 const double* head_imp, int32_t n_head, int32_t n_tiles,
+                                 int32_t tile_docs, int32_t n_terms, int64_t n_docs,
+                                 const int32_t* q_terms, int32_t q, int32_t q_len, int32_t k,
+                                 int64_t row_base, double* out_score, int64_t* out_idx,
+                                 int32_t* out_count, uint8_t* inexact_flags,
+                                 uint32_t* inexact_counter, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  RR_CHECK_ARG(q >= 0 && n_docs > 0 && q_len > 0 && n_tiles > 0 && n_terms > 0, "bad size");
+  if (q == 0) return RR_OK;
+  RR_CHECK_ARG(out_score && out_idx, "null pointer");
+  RR_CHECK_ARG(tile_term_ptr && post_row && post_impact && head_slot && q_terms, "null pointer");
+  RR_CHECK_ARG(k >= 1 && k <= RR_MAX_K, "k out of range");
+  RR_CHECK_ARG(tile_docs >= 128 && tile_docs <= BF_MAX_TILE && tile_docs % 128 == 0,
+               "tile_docs must be a multiple of 128 in [128, 1024]");
+  RR_CHECK_ARG(n_head >= 0 && n_head <= BF_MAX_HEAD, "n_head must be in [0, 32]");
+  RR_CHECK_ARG(n_head == 0 || head_imp, "head_imp is null");
+  RR_CHECK_ARG((long long)n_tiles * tile_docs >= n_docs, "tiles do not cover n_docs");
+  RR_CHECK_ARG(n_docs < (1LL << 32), "n_docs must be < 2^32");
+  const BfLayout l = bf_layout(n_tiles, tile_docs, n_docs, q, k);
+  if (!workspace || workspace_bytes < l.total) {
+    set_error("rr_bm25_topk_fast: workspace %zu < %zu", workspace_bytes, l.total);
+    return RR_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  char* ws = (char*)workspace;
+  const int stride = bf_stride(n_tiles, tile_docs, n_docs, k);
+  const int cap = bf_list_cap(k);
+  const int kp = bf_kprime(k);
+  BfArgs a;
+  a.tile_term_ptr = (const long long*)tile_term_ptr;
+  a.post_row = post_row;
+  a.post_impact = post_impact;
+  a.head_slot = head_slot;
+  a.head_imp = head_imp;
+  a.n_head = n_head;
+  a.n_tiles = n_tiles;
+  a.tile_docs = tile_docs;
+  a.n_terms = n_terms;
+  a.n_docs = n_docs;
+  a.q_terms = q_terms;
+  a.q = q;
+  a.q_len = q_len;
+  a.lane_max = (float*)(ws + l.lane_max);
+  a.tau = (const float*)(ws + l.tau);
+  a.list_cnt = (u32*)(ws + l.list_cnt);
+  a.list = (u64*)(ws + l.list);
+  a.cap = cap;
+  const size_t smem = ((size_t)n_head + BF_WARPS) * tile_docs * 4;
+  RR_CHECK_ARG((int)smem + 8192 <= max_smem_optin(), "tile does not fit shared memory");
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  RR_CUDA(cudaMemsetAsync(ws + l.list_cnt, 0, (size_t)q * 4, st));
+  bf_mark(0, st);
+  if (stride > 0) {
+    a.stride = stride;
+    a.n_pass_tiles = (n_tiles + stride - 1) / stride;
+    RR_CUDA(cudaFuncSetAttribute(bm25_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = a.n_pass_tiles < sms ? a.n_pass_tiles : sms;
+    bm25_fast_kernel<true><<<grid, BF_THREADS, smem, st>>>(a);
+    RR_LAUNCH_CHECK();
+    bf_mark(1, st);
+    BtArgs t;
+    t.lane_max = a.lane_max;
+    t.m = (long long)a.n_pass_tiles * 32;
+    t.kp = kp;
+    t.cap = 4096;
+    while (t.cap < 2 * kp) t.cap <<= 1;
+    t.tau = (float*)(ws + l.tau);
+    const size_t tsm = (size_t)t.cap * 12;
+    RR_CUDA(cudaFuncSetAttribute(bm25_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+    bm25_tau_kernel<<<q, 256, tsm, st>>>(t);
+    RR_LAUNCH_CHECK();
+  } else {
+    bf_mark(1, st);
+    RR_CUDA(cudaMemsetAsync(ws + l.tau, 0, (size_t)q * 4, st));
+  }
+  bf_mark(2, st);
+  a.stride = 1;
+  a.n_pass_tiles = n_tiles;
+  RR_CUDA(cudaFuncSetAttribute(bm25_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    const int grid = n_tiles < sms ? n_tiles : sms;
+    bm25_fast_kernel<false><<<grid, BF_THREADS, smem, st>>>(a);
+    RR_LAUNCH_CHECK();
+  }
+  bf_mark(3, st);
+  BrArgs r;
+  r.tile_term_ptr = a.tile_term_ptr;
+  r.post_row = post_row;
+  r.post_impact = post_impact;
+  r.head_slot = head_slot;
+  r.head_imp = head_imp;
+  r.n_head = n_head;
+  r.tile_docs = tile_docs;
+  r.n_terms = n_terms;
+  r.q_terms = q_terms;
+  r.q_len = q_len;
+  r.list_cnt = a.list_cnt;
+  r.list = a.list;
+  r.cap = cap;
+  r.tau = a.tau;
+  r.escore = (double*)(ws + l.escore);
+  r.k = k;
+  r.sel_cap = 64;
+  while (r.sel_cap < 2 * k) r.sel_cap <<= 1;
+  if (r.sel_cap > 2048) r.sel_cap = 2048;
+  while (r.sel_cap < k) r.sel_cap <<= 1;
+  r.row_base = row_base;
+  r.eps = (double)(q_len + 4) * 5.9604644775390625e-08;  // (q_len + 4) * 2^-24
+  r.out_score = out_score;
+  r.out_idx = (long long*)out_idx;
+  r.out_count = out_count;
+  r.flags = inexact_flags;
+  r.counter = inexact_counter;
+  const size_t rsm = (size_t)r.sel_cap * 12 + (size_t)q_len * 8;
+  RR_CUDA(cudaFuncSetAttribute(bm25_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+  bm25_refine_kernel<<<q, 256, rsm, st>>>(r);
+  RR_LAUNCH_CHECK();
+  bf_mark(4, st);
+  g_bf_timed = g_bf_timing && g_bf_ev_ready;
+  return RR_OK;
+}

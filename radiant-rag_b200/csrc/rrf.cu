@@ -43,8 +43,9 @@ __device__ __forceinline__ void rrf_bitonic_u64(u64* keys, int p) {
 }
 
 struct RrfArgs {
-  const long long* run_idx;  // [q][len]
-  int run_off[RRF_MAX_RUNS + 1];
+  const long long* run_ptr[RRF_MAX_RUNS];  // run r of query q: run_ptr[r] + q * run_stride[r]
+  int run_stride[RRF_MAX_RUNS];
+  int run_off[RRF_MAX_RUNS + 1];  // position of run r inside the concatenated list
   int n_runs;
   int len;
   int p;  // power of two >= len
@@ -62,12 +63,16 @@ __global__ void __launch_bounds__(RRF_THREADS) rrf_fuse_kernel(const RrfArgs a) 
   u32* s_k2 = reinterpret_cast<u32*>(s_k1 + a.p);  // [p] first position
   __shared__ int s_groups;
   const int q = blockIdx.x;
-  const long long* runs = a.run_idx + (size_t)q * a.len;
+  auto entry = [&](int pos) -> long long {
+    int r = 0;
+    while (r + 1 < a.n_runs && pos >= a.run_off[r + 1]) ++r;
+    return a.run_ptr[r][(size_t)q * a.run_stride[r] + (pos - a.run_off[r])];
+  };
 
   for (int pos = threadIdx.x; pos < a.p; pos += RRF_THREADS) {
     u64 key = K1_INVALID;
     if (pos < a.len) {
-      const long long id = runs[pos];
+      const long long id = entry(pos);
       if (id >= 0) key = ((u64)(u32)id << 32) | (u64)(u32)pos;
     }
     key_a[pos] = key;
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(RRF_THREADS) rrf_fuse_kernel(const RrfArgs a) 
   for (int j = threadIdx.x; j < a.k; j += RRF_THREADS) {
     const size_t o = (size_t)q * a.k + j;
     if (j < m) {
-      a.out_idx[o] = runs[s_k2[j]];
+      a.out_idx[o] = entry((int)s_k2[j]);
       a.out_score[o] = f64_from_orderable(~s_k1[j]);
     } else {
       a.out_idx[o] = -1;
@@ -120,6 +125,9 @@ __global__ void __launch_bounds__(RRF_THREADS) rrf_fuse_kernel(const RrfArgs a) 
 }  // namespace rr
 
 using namespace rr;
+
+static int launch_rrf(RrfArgs& a, int32_t n_runs, int32_t q, double rrf_k, int32_t k,
+                      int64_t* out_idx, double* out_score, int32_t* out_count, void* stream);
 
 extern "C" int rr_rrf_fuse(const int64_t* run_idx, const int32_t* run_off_host, int32_t n_runs,
                            int32_t q, double rrf_k, int32_t k, int64_t* out_idx, double* out_score,
@@ -134,9 +142,37 @@ extern "C" int rr_rrf_fuse(const int64_t* run_idx, const int32_t* run_off_host, 
   for (int r = 0; r < n_runs; ++r)
     RR_CHECK_ARG(a.run_off[r + 1] >= a.run_off[r], "run_off must be non-decreasing");
   RR_CHECK_ARG(a.run_off[0] == 0, "run_off[0] must be 0");
+  for (int r = 0; r < n_runs; ++r) {
+    a.run_ptr[r] = (const long long*)run_idx + a.run_off[r];
+    a.run_stride[r] = a.run_off[n_runs];
+  }
+  return launch_rrf(a, n_runs, q, rrf_k, k, out_idx, out_score, out_count, stream);
+}
+
+extern "C" int rr_rrf_fuse_runs(const int64_t* const* run_ptrs_host, const int32_t* run_len_host,
+                                int32_t n_runs, int32_t q, double rrf_k, int32_t k, int64_t* out_idx,
+                                double* out_score, int32_t* out_count, void* stream) {
+  RR_CHECK_ARG(q >= 0, "negative size");
+  if (q == 0) return RR_OK;
+  RR_CHECK_ARG(run_ptrs_host && run_len_host && out_idx && out_score, "null pointer");
+  RR_CHECK_ARG(n_runs >= 1 && n_runs <= RRF_MAX_RUNS, "n_runs must be in [1, 16]");
+  RR_CHECK_ARG(k >= 1 && k <= RR_MAX_K, "k out of range");
+  RrfArgs a;
+  a.run_off[0] = 0;
+  for (int r = 0; r < n_runs; ++r) {
+    RR_CHECK_ARG(run_len_host[r] >= 0, "negative run length");
+    RR_CHECK_ARG(run_ptrs_host[r] || run_len_host[r] == 0, "null run pointer");
+    a.run_ptr[r] = (const long long*)run_ptrs_host[r];
+    a.run_stride[r] = run_len_host[r];
+    a.run_off[r + 1] = a.run_off[r] + run_len_host[r];
+  }
+  return launch_rrf(a, n_runs, q, rrf_k, k, out_idx, out_score, out_count, stream);
+}
+
+static int launch_rrf(RrfArgs& a, int32_t n_runs, int32_t q, double rrf_k, int32_t k,
+                      int64_t* out_idx, double* out_score, int32_t* out_count, void* stream) {
   a.len = a.run_off[n_runs];
   RR_CHECK_ARG(a.len >= 1 && a.len <= RRF_MAX_LEN, "total run length must be in [1, 4096]");
-  a.run_idx = (const long long*)run_idx;
   a.n_runs = n_runs;
   a.p = 1;
   while (a.p < a.len) a.p <<= 1;

@@ -37,6 +37,7 @@
 
 #include "common.cuh"
 #include "merge.cuh"
+#include "tc_ptx.cuh"
 
 namespace rr {
 
@@ -62,99 +63,6 @@ constexpr int TC_MAX_KB = 8;                  // dim <= 1024
 #endif
 constexpr int TC_KBPS = RR_TC_KBPS;           // K blocks per tensor-memory ring stage (1, 2 or 4)
 
-// ---- PTX wrappers -------------------------------------------------------------------------
-__device__ __forceinline__ u32 tc_smem(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void tc_mbar_init(u32 bar, u32 count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_expect_tx(u32 bar, u32 bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_arrive(u32 bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mbar_wait(u32 bar, u32 parity) {
-  u32 done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-  } while (!done);
-}
-// for waiters that are far ahead of their partner (the copy producer): back off between
-// polls so the spin does not take issue slots from the warps sharing the scheduler
-__device__ __forceinline__ void tc_mbar_wait_backoff(u32 bar, u32 parity) {
-  u32 done;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (done) break;
-    __nanosleep(200);
-  }
-}
-__device__ __forceinline__ void tc_tma_load_2d(u32 dst, const CUtensorMap* map, int c0, int c1, u32 bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(u32 bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_i8(u32 d_tmem, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-// Warp-uniform issue helpers: every lane executes the asm with identical (uniform) operands
-// and elect.sync picks the single issuing lane, so the compiler keeps descriptors and
-// addresses in uniform registers instead of broadcasting them out of a divergent branch
-// (the MMA warp's own instruction latency is what paces short MMAs).
-__device__ __forceinline__ void tc_mma_i8_ss_elect(u32 d_tmem, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred pe, pa;\n\t"
-      "elect.sync _|pe, 0xffffffff;\n\t"
-      "setp.ne.b32 pa, %4, 0;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, pa;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void tc_mma_i8_ts_elect(u32 d_tmem, u32 a_tmem, u64 bdesc, u32 idesc, u32 accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred pe, pa;\n\t"
-      "elect.sync _|pe, 0xffffffff;\n\t"
-      "setp.ne.b32 pa, %4, 0;\n\t"
-      "@pe tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, pa;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void tc_commit_elect(u32 bar) {
-  asm volatile(
-      "{\n\t.reg .pred pe;\n\t"
-      "elect.sync _|pe, 0xffffffff;\n\t"
-      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
-      ::"r"(bar) : "memory");
-}
-// A operand from tensor memory (lane = row, four int8 K-elements per 32-bit column)
-__device__ __forceinline__ void tc_mma_i8_ts(u32 d_tmem, u32 a_tmem, u64 bdesc, u32 idesc, u32 accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start address >> 4 | LBO = 1 (unused for swizzled K-major) | SBO = 1024 B (8-row group) |
-// version 1 (Blackwell) | layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ u64 tc_smem_desc(u32 saddr) {
-  return (u64)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((u64)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
 // cute::UMMA::InstrDescriptor for kind::i8: D = S32, A = B = signed int8, both K-major,
 // N = 128 (>>3 at bit 17), M = 128 (>>4 at bit 24).
 constexpr u32 TC_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((u32)(TC_BN >> 3) << 17) | ((u32)(TC_BM >> 4) << 24);
@@ -878,8 +786,10 @@ static int make_map(CUtensorMap* map, const void* ptr, long long rows, int dim) 
 // reach the sampled bound (list appends + final select) cost ~ stride * k per query, so the
 // optimum grows like sqrt(n / k); the constant is fitted on B200 (profiles/).
 static int tc_sample_stride(long long n, int k) {
-  const char* e = getenv("RR_TC_STRIDE");  // experiments only
+#ifdef RR_TC_EXPERIMENTS  // never in the shipped library: an environment variable must not change results
+  const char* e = getenv("RR_TC_STRIDE");
   if (e && atoi(e) > 0) return atoi(e);
+#endif
   const double want = 0.2 * sqrt((double)n / (double)k);
   int s = 4;
   while (s < 128 && (double)s * 1.4142 < want) s <<= 1;
@@ -932,11 +842,13 @@ static TcPlan tc_plan(long long n, int q, int k) {
   return p;
 }
 
-// optional per-kernel event timing (rr_tc_timing): events 0..4 bracket the four kernels
-static bool g_tc_timing = false;
-static bool g_tc_timed = false;
-static cudaEvent_t g_tc_ev[5];
-static bool g_tc_ev_ready = false;
+// optional per-kernel event timing (rr_tc_timing): events 0..4 bracket the four kernels.
+// The state is per host thread (the reference drives retrieval from two threads,
+// radiant/orchestrator.py:994-998): a thread that enables timing times its own calls only.
+static thread_local bool g_tc_timing = false;
+static thread_local bool g_tc_timed = false;
+static thread_local cudaEvent_t g_tc_ev[5];
+static thread_local bool g_tc_ev_ready = false;
 static void tc_mark(int i, cudaStream_t st) {
   if (g_tc_timing && g_tc_ev_ready) cudaEventRecord(g_tc_ev[i], st);
 }
@@ -1015,10 +927,13 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   a.stages = lay.stages;
   a.packed = packed ? 1 : 0;
   a.packed_codes = packed_codes;
+  a.debug = 0;
+#ifdef RR_TC_EXPERIMENTS  // isolation runs (skip a role; results are garbage): experiment builds only
   {
     const char* e = getenv("RR_TC_DEBUG");
     a.debug = e ? atoi(e) : 0;
   }
+#endif
 
   // ---- pass 0: dense scores of a strided sample of row tiles -> tau
   const bool full_sample = p.sample_tiles == p.tiles;

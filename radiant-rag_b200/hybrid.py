@@ -1,0 +1,293 @@
+"""One product call for the batched hybrid retrieval step: dense -> BM25 -> RRF on device.
+
+This is the path BASELINE.json's metric names ("hybrid retrieval queries/sec @ top-10").  The
+reference runs it one query at a time through three agents:
+
+    RadiantRAG.search(query, mode="hybrid", top_k)          radiant/app.py:1178-1249
+    RAGOrchestrator._run_retrieval / _fuse_results          radiant/orchestrator.py:918-1151, 1153-1196
+
+``HybridSearch.search_batch`` is the device-level form (tensors in, tensors out, replayable from
+a CUDA graph); ``BatchedRetrieval`` is the host-level form with the reference's objects (query
+strings in, ``[(StoredDoc, score)]`` out) that replaces the orchestrator's per-sub-query loop
+and two-thread pool with ONE batched call per phase.
+
+Row ids: the dense index and the BM25 index must number documents identically (row = position
+in upsert order); both return GLOBAL rows (``row_base`` + local row) so the fused
+list is the same on one GPU and on a row-sharded corpus.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .agents import rrf_fuse_runs_device
+from .index import DenseIndex, to_device
+from .sharded import GpuShardOps, ShardedBM25Search, ShardedDenseSearch
+
+
+@dataclass
+class HybridResult:
+    """Static-shape outputs of one hybrid step (device tensors).
+
+    idx int64 [Q, top_k] (-1 padded) / score f64 [Q, top_k] / count int32 [Q]: the RRF-fused list,
+    (score desc, first-insertion asc) exactly as RRFAgent._execute orders it.  The two input runs
+    are returned as well: the reference's ``search`` falls back to the non-empty run when the
+    other one is empty (app.py:1234-1239) and the host wrapper needs their own scores for that."""
+    idx: torch.Tensor
+    score: torch.Tensor
+    count: torch.Tensor
+    dense_idx: torch.Tensor
+    dense_score: torch.Tensor
+    dense_count: torch.Tensor
+    bm25_idx: torch.Tensor
+    bm25_score: torch.Tensor
+    bm25_count: torch.Tensor
+
+    def tensors(self) -> Tuple[torch.Tensor, ...]:
+        return (self.idx, self.score, self.count, self.dense_idx, self.dense_score, self.dense_count,
+                self.bm25_idx, self.bm25_score, self.bm25_count)
+
+
+class HybridSearch:
+    """dense top-``dense_top_k`` (two-stage quantised, or the exact scan) + BM25
+    top-``bm25_top_k`` fused by RRF into the top-``top_k``, for a batch of queries, entirely on
+    the device: three C-ABI calls chains and no host decision in between.
+
+    dense: a ``DenseIndex`` (this rank's shard); bm25: a ``Bm25DeviceIndex`` over the same rows.
+    With ``torch.distributed`` initialised (one process per GPU) both halves exchange their
+    per-shard candidates (sharded.py) and every rank returns the same fused lists."""
+
+    def __init__(self, dense: DenseIndex, bm25: Any, group: Optional[Any] = None,
+                 rescore_multiplier: float = 4.0, prefer_int8: bool = True,
+                 dense_mode: str = "quantized") -> None:
+        if dense_mode not in ("quantized", "exact"):
+            raise ValueError("dense_mode must be 'quantized' or 'exact'")
+        self.dense_index = dense
+        self.bm25_index = bm25
+        self.device = dense.device
+        self.group = group
+        self.rescore_multiplier = float(rescore_multiplier)
+        self.prefer_int8 = bool(prefer_int8)
+        self.dense_mode = dense_mode
+        self.ops = GpuShardOps(dense)
+        self.dense = ShardedDenseSearch(self.ops, group)
+        self.sparse = ShardedBM25Search(bm25, self.ops, group)
+
+    def search_batch(self, queries, q_terms, top_k: int = 10, dense_top_k: int = 100,
+                     bm25_top_k: int = 100, rrf_k: float = 60, min_similarity: float = 0.0,
+                     tag_mask: int = 0, tag_value: int = 0, check: bool = True) -> HybridResult:
+        """queries f32 [Q, D] (host or device); q_terms int32 [Q, L] BM25 term ids in query-token
+        order (-1 = unknown / padding), identical on every rank.
+
+        check=False leaves out every host synchronisation (the step can then be captured into a
+        CUDA graph); the tensor-core overflow counter and the BM25 inexact counter are accumulated
+        on the device instead and must be read by the caller (``unchecked_events``)."""
+        for name, kk in (("top_k", top_k), ("dense_top_k", dense_top_k), ("bm25_top_k", bm25_top_k)):
+            if not 1 <= int(kk) <= _lib.RR_MAX_K:
+                raise ValueError(f"{name}={kk} outside [1, {_lib.RR_MAX_K}]")
+        if self.dense_mode == "quantized":
+            d_idx, d_score, d_count = self.dense.search_quantized(
+                queries, dense_top_k, rescore_multiplier=self.rescore_multiplier,
+                min_similarity=min_similarity, tag_mask=tag_mask, tag_value=tag_value,
+                prefer_int8=self.prefer_int8, check_overflow=check)
+        else:
+            if self.dense.world() > 1:
+                raise ValueError("dense_mode='exact' is a single-GPU path")
+            d_idx, d_score, d_count = self.dense_index.search_exact(queries, dense_top_k, min_similarity,
+                                                                    tag_mask, tag_value)
+        b_idx, b_score, b_count = self.sparse.search_batch(q_terms, bm25_top_k, check=check)
+        f_idx, f_score, f_count = rrf_fuse_runs_device([d_idx, b_idx], top_k, rrf_k)
+        return HybridResult(f_idx, f_score, f_count, d_idx, d_score, d_count, b_idx, b_score, b_count)
+
+    def unchecked_events(self) -> int:
+        """Tensor-core list overflows + BM25 inexact flags accumulated by ``check=False`` calls on
+        this rank since the last ``reset_unchecked_events`` (0 = every result was exact)."""
+        n = self.dense_index.tc_overflow_total()
+        fn = getattr(self.bm25_index, "inexact_total", None)
+        return n + (int(fn()) if fn else 0)
+
+    def reset_unchecked_events(self) -> None:
+        self.dense_index.tc_overflow_reset()
+        fn = getattr(self.bm25_index, "inexact_reset", None)
+        if fn:
+            fn()
+
+
+class GraphedHybridSearch:
+    """CUDA-graph replay of one fixed-shape hybrid step on ONE GPU.
+
+        g = GraphedHybridSearch(hybrid, n_queries, dim, q_len, top_k=10, ...)
+        res = g(queries_host_pinned, q_terms_host_pinned)      # HybridResult of static tensors
+
+    Host inputs go through two staging buffers on a copy stream (the H2D of step i+1 overlaps
+    step i).  Results are the graph's static outputs: copy them out before the next replay."""
+
+    def __init__(self, hybrid: HybridSearch, n_queries: int, dim: int, q_len: int, warmup: int = 3,
+                 **search_kwargs: Any) -> None:
+        self.hybrid = hybrid
+        self.device = hybrid.device
+        dev = self.device
+        self.static_q = torch.zeros((n_queries, dim), dtype=torch.float32, device=dev)
+        self.static_t = torch.full((n_queries, q_len), -1, dtype=torch.int32, device=dev)
+        kwargs = dict(search_kwargs, check=False)
+
+        def step() -> HybridResult:
+            return hybrid.search_batch(self.static_q, self.static_t, **kwargs)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        launches0 = _lib.launch_count
+        with torch.cuda.graph(self.graph):
+            self.static_out = step()
+        self.kernels_per_replay = _lib.launch_count - launches0
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._stage = [(torch.empty_like(self.static_q), torch.empty_like(self.static_t)) for _ in range(2)]
+        self._filled = [torch.cuda.Event() for _ in range(2)]
+        self._consumed = [torch.cuda.Event() for _ in range(2)]
+        self._turn = 0
+
+    def load(self, queries: torch.Tensor, q_terms: torch.Tensor) -> None:
+        if queries.is_cuda and q_terms.is_cuda:
+            self.static_q.copy_(queries, non_blocking=True)
+            self.static_t.copy_(q_terms, non_blocking=True)
+            return
+        b = self._turn
+        self._turn ^= 1
+        main = torch.cuda.current_stream(self.device)
+        cs = self._copy_stream
+        cs.wait_event(self._consumed[b])
+        with torch.cuda.stream(cs):
+            self._stage[b][0].copy_(queries, non_blocking=True)
+            self._stage[b][1].copy_(q_terms, non_blocking=True)
+            self._filled[b].record(cs)
+        main.wait_event(self._filled[b])
+        self.static_q.copy_(self._stage[b][0], non_blocking=True)
+        self.static_t.copy_(self._stage[b][1], non_blocking=True)
+        self._consumed[b].record(main)
+
+    def replay(self) -> HybridResult:
+        self.graph.replay()
+        _lib.launch_count += self.kernels_per_replay
+        return self.static_out
+
+    def __call__(self, queries: torch.Tensor, q_terms: torch.Tensor) -> HybridResult:
+        self.load(queries, q_terms)
+        return self.replay()
+
+
+class BatchedRetrieval:
+    """Host-level batched replacement of the reference's retrieval phase.
+
+    The reference embeds the sub-queries, then loops ``store.retrieve_by_embedding`` and
+    ``index.search`` per sub-query in two threads, de-duplicates by ``doc_id`` (first occurrence
+    wins, orchestrator.py:953-965, 980-987) and fuses the two merged runs with RRFAgent
+    (:1153-1196); ``RadiantRAG.search`` does the same for one query (app.py:1178-1249).  Here the
+    whole batch is one embedding call, one dense search, one BM25 search and one RRF launch.
+
+    store: ``B200VectorStore``; bm25_index: this package's ``PersistentBM25Index`` built over the
+    same store; local_models: anything with ``embed(list[str])`` or ``embed_single(str)``;
+    config: a ``RetrievalConfig`` (dense_top_k, bm25_top_k, fused_top_k, rrf_k, min_similarity,
+    search_scope)."""
+
+    def __init__(self, store: Any, bm25_index: Any, local_models: Any, config: Any,
+                 use_quantized: Optional[bool] = None) -> None:
+        self._store = store
+        self._index = bm25_index
+        self._local_models = local_models
+        self._config = config
+        if use_quantized is None:
+            use_quantized = bool(getattr(getattr(store, "_quant_config", None), "enabled", False))
+        self._use_quantized = use_quantized
+
+    def _doc_level_filter(self, search_scope: Optional[str]) -> Optional[str]:
+        scope = search_scope or getattr(self._config, "search_scope", "leaves")
+        if scope == "parents":
+            return "parent"
+        if scope == "all":
+            return None
+        return "child"
+
+    def _embed(self, queries: Sequence[str]) -> np.ndarray:
+        embed = getattr(self._local_models, "embed", None)
+        vecs = embed(list(queries)) if embed else [self._local_models.embed_single(q) for q in queries]
+        return np.asarray(vecs, dtype=np.float32)
+
+    def dense_batch(self, queries: Sequence[str], top_k: Optional[int] = None,
+                    search_scope: Optional[str] = None) -> List[List[Tuple[Any, float]]]:
+        k = top_k or self._config.dense_top_k
+        level = self._doc_level_filter(search_scope)
+        vecs = self._embed(queries)
+        if self._use_quantized:
+            return self._store.retrieve_batch_quantized(vecs, k, self._config.min_similarity,
+                                                        doc_level_filter=level)
+        return self._store.retrieve_batch(vecs, k, self._config.min_similarity, doc_level_filter=level)
+
+    def bm25_batch(self, queries: Sequence[str], top_k: Optional[int] = None) -> List[List[Tuple[Any, float]]]:
+        return self._index.search_batch(list(queries), top_k or self._config.bm25_top_k)
+
+    def search_batch(self, queries: Sequence[str], mode: str = "hybrid", top_k: int = 10,
+                     search_scope: Optional[str] = None) -> List[List[Tuple[Any, float]]]:
+        """Batched ``RadiantRAG.search`` (app.py:1178-1249): every query is searched with
+        ``top_k`` in both retrievers, fused with ``top_k``; if one of a query's runs is empty
+        the other run is returned as it is."""
+        from .agents import RRFAgent
+
+        if mode not in ("hybrid", "dense", "bm25"):
+            raise ValueError("mode must be 'hybrid', 'dense' or 'bm25'")
+        nq = len(queries)
+        dense = self.dense_batch(queries, top_k, search_scope) if mode in ("hybrid", "dense") else [[] for _ in range(nq)]
+        if mode == "dense":
+            return dense
+        sparse = self.bm25_batch(queries, top_k) if mode in ("hybrid", "bm25") else [[] for _ in range(nq)]
+        if mode == "bm25":
+            return sparse
+        both = [i for i in range(nq) if dense[i] and sparse[i]]
+        fused = RRFAgent(self._config, device=getattr(self._store, "_device", 0)).fuse_batch(
+            [[dense[i], sparse[i]] for i in both], top_k=top_k) if both else []
+        out: List[List[Tuple[Any, float]]] = [dense[i] if dense[i] else sparse[i] for i in range(nq)]
+        for j, i in enumerate(both):
+            out[i] = fused[j][:top_k]
+        return out
+
+    def run_retrieval(self, sub_queries: Sequence[str], retrieval_mode: str = "hybrid",
+                      search_scope: Optional[str] = None
+                      ) -> Tuple[List[Tuple[Any, float]], List[Tuple[Any, float]], List[Tuple[Any, float]]]:
+        """Batched ``_run_retrieval`` + ``_fuse_results`` for ONE user query expanded into
+        ``sub_queries``: -> (dense_retrieved, bm25_retrieved, fused).  Each retriever's per-sub-query
+        lists are concatenated in sub-query order keeping the first occurrence of a doc_id
+        (orchestrator.py:953-965, 980-987); the merged runs are fused with the config's
+        ``fused_top_k`` / ``rrf_k`` when both are non-empty, otherwise the non-empty one is the
+        result (:1195-1196)."""
+        from .agents import RRFAgent
+
+        def merged(per_query: List[List[Tuple[Any, float]]]) -> List[Tuple[Any, float]]:
+            seen, out = set(), []
+            for results in per_query:
+                for doc, score in results:
+                    doc_id = getattr(doc, "doc_id", id(doc))
+                    if doc_id not in seen:
+                        seen.add(doc_id)
+                        out.append((doc, score))
+            return out
+
+        dense = merged(self.dense_batch(sub_queries, None, search_scope)) if retrieval_mode in ("hybrid", "dense") else []
+        sparse = merged(self.bm25_batch(sub_queries, None)) if retrieval_mode in ("hybrid", "bm25") else []
+        lists = [r for r in (dense, sparse) if r]
+        if len(lists) > 1:
+            fused = RRFAgent(self._config, device=getattr(self._store, "_device", 0)).fuse_batch([lists])[0]
+        elif lists:
+            fused = lists[0]
+        else:
+            fused = []
+        return dense, sparse, fused

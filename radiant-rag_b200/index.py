@@ -75,7 +75,9 @@ class LanguageTable:
 
 
 def make_tag(doc_level: Optional[str], lang_id: int) -> int:
-    return _LEVEL_BITS.get(doc_level or "child", LEVEL_CHILD) | (lang_id << 2)
+    """Level bits: 1 = "child", 2 = "parent", 0 = any other stored value - the reference's filters
+    match the stored string exactly (redis_store.py:684, 915-916), so such a row passes neither."""
+    return _LEVEL_BITS.get("child" if doc_level is None else doc_level, 0) | (lang_id << 2)
 
 
 def tag_predicate(level_value: Optional[str], lang_id: int) -> Tuple[int, int]:
@@ -103,10 +105,7 @@ class DenseIndex:
         int8_ranges: Optional[ArrayLike] = None,
         row_base: int = 0,
         capacity: int = 0,
-        store_pm1: bool = False,
     ) -> None:
-        """store_pm1: deprecated no-op (the tensor-core scan expands the packed codes on chip
-        and needs no extra copy in HBM)."""
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         if self.device.type != "cuda":
             raise _lib.RadiantB200Error("DenseIndex needs a CUDA device; there is no CPU fallback")
@@ -274,6 +273,8 @@ class DenseIndex:
         _lib.call("rr_quantize_ubinary", e.data_ptr(), 1, self.dim, self.codes[row:row + 1].data_ptr(),
                   self.words * 4, _stream())
         if self.store_int8:
+            if self.ranges is None:
+                raise ValueError("int8 storage needs calibration ranges (set_int8_ranges)")
             _lib.call("rr_quantize_int8", e.data_ptr(), 1, self.dim, self.ranges.data_ptr(),
                       self.int8[row:row + 1].data_ptr(), _stream())
         if self.store_f32:
@@ -389,6 +390,10 @@ class DenseIndex:
         """Overflow events of tensor-core calls made with check_overflow=False (0 = all exact)."""
         return 0 if self._tc_overflow is None else int(self._tc_overflow.item())
 
+    def tc_overflow_reset(self) -> None:
+        if self._tc_overflow is not None:
+            self._tc_overflow.zero_()
+
     def rescore_source(self, prefer_int8: bool = True) -> Tuple[torch.Tensor, int]:
         """int8 rows preferred, float32 fallback (reference redis_store.py:820-840)."""
         if prefer_int8 and self.int8 is not None:
@@ -462,8 +467,10 @@ class DenseIndex:
         Without rescoring the score is the placeholder 1.0 (reference chroma_store.py:624-631).
         """
         qf, qc = self.quantize_queries(queries)
+        if not 1 <= int(top_k) <= _lib.RR_MAX_K:
+            raise ValueError(f"top_k={top_k} outside [1, {_lib.RR_MAX_K}]")
         candidate_k = int(top_k * rescore_multiplier) if use_rescoring else top_k
-        candidate_k = max(1, min(candidate_k, _lib.RR_MAX_K))
+        candidate_k = max(int(top_k), min(candidate_k, _lib.RR_MAX_K))  # documented limit: INTEGRATION.md
         # Stage 2 is queued behind stage 1 before the tensor-core overflow counter is read, so
         # the (single) host sync of a checked call sits at its end and the GPU never idles
         # between the stages; an overflow (adversarial data) redoes the call on the POPC path.
@@ -515,6 +522,8 @@ class DenseIndex:
         self._activate()
         if self.int8 is None:
             raise _lib.RadiantB200Error("index has no int8 rows")
+        if self.row_base + self.n >= (1 << 32):
+            raise ValueError("global rows do not fit the 32-bit row field of the int32-score merge")
         qi = to_device(queries_i8, self.device, torch.int8)
         if qi.ndim == 1:
             qi = qi[None, :]

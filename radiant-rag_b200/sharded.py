@@ -146,6 +146,21 @@ class ShardedDenseSearch:
         self.ops = ops
         self.group = group
 
+    def world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def overflow_total(self) -> int:
+        """Tensor-core candidate-list overflows of ``check_overflow=False`` calls, summed over ALL
+        ranks (an overflow on one shard makes the merged result inexact on every rank, so the
+        per-rank counter alone is not enough).  Collective: every rank must call it."""
+        index = getattr(self.ops, "index", None)
+        local = index.tc_overflow_total() if index is not None else 0
+        if self.world() == 1:
+            return local
+        t = torch.tensor([local], dtype=torch.int64, device=getattr(self.ops, "device", "cpu"))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
+
     def search_quantized(self, queries, top_k: int, rescore_multiplier: float = 4.0,
                          use_rescoring: bool = True, min_similarity: float = 0.0,
                          tag_mask: int = 0, tag_value: int = 0, prefer_int8: bool = True,
@@ -192,8 +207,10 @@ class ShardedBM25Search:
         self.ops = ops
         self.group = group
 
-    def search_batch(self, q_terms, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        idx, score, count = self.local.search_batch(q_terms, k)
+    def search_batch(self, q_terms, k: int, check: bool = True
+                     ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """check=False: no host synchronisation (see Bm25DeviceIndex.search_batch)."""
+        idx, score, count = self.local.search_batch(q_terms, k, check=check)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
             return idx, score, count

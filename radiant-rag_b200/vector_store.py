@@ -40,14 +40,12 @@ class B200VectorStore(BaseVectorStore):
         int8_ranges: Optional[np.ndarray] = None,
         inner: Optional[Any] = None,
         max_content_chars: int = 200_000,
-        tensor_core_batches: bool = False,
     ) -> None:
         """quantization: a QuantizationConfig (this package's or the reference's);
         int8_ranges: [2, D] calibration, or loaded from ``quantization.int8_ranges_file``
         (reference redis_store.py:174-181); inner: optional reference store that keeps
         the documents themselves."""
         self._device = device
-        self._tensor_core_batches = tensor_core_batches  # keep +-1 rows: batched stage 1 on tcgen05
         self._quant_config = quantization or QuantizationConfig()
         self._inner = inner
         self._max_chars = max_content_chars
@@ -86,8 +84,7 @@ class B200VectorStore(BaseVectorStore):
                                "rescoring falls back to float32 rows")
             self._embedding_dim = dim
             self._index = DenseIndex(dim, device=self._device, store_int8=want_int8, store_f32=True,
-                                     int8_ranges=self._int8_ranges if want_int8 else None,
-                                     store_pm1=self._tensor_core_batches)
+                                     int8_ranges=self._int8_ranges if want_int8 else None)
 
     @property
     def index(self) -> Optional[DenseIndex]:
@@ -130,45 +127,77 @@ class B200VectorStore(BaseVectorStore):
 
     def upsert_batch(self, documents: List[Dict[str, Any]]) -> int:
         """Batch insert/update; unlike the reference's batch path
-        (redis_store.py:476-532) the quantised rows ARE written here."""
+        (redis_store.py:476-532) the quantised rows ARE written here.
+        All-or-nothing: the whole batch is validated and staged first, the GPU append runs, and
+        only then are the id <-> row maps and the document store updated - a bad document in the
+        middle of a batch leaves the store exactly as it was."""
         if not documents:
             return 0
         with self._lock:
-            new_rows: List[np.ndarray] = []
-            new_tags: List[int] = []
+            staged = []           # (doc_id, content, meta, emb, tag)
+            dim = self._index.dim if self._index is not None else self._embedding_dim
             for d in documents:
                 emb = np.asarray(d["embedding"], dtype=np.float32)
-                self._ensure_index(emb.shape[0])
+                if emb.ndim != 1 or emb.size == 0:
+                    raise ValueError(f"{d.get('doc_id')}: embedding must be a non-empty 1-D vector")
+                if dim is None:
+                    dim = int(emb.shape[0])
+                if emb.shape[0] != dim:
+                    raise ValueError(f"{d.get('doc_id')}: embedding dim {emb.shape[0]} != index dim {dim}")
                 content, meta, level, lang = self._prep_doc(d["content"], d.get("meta"), "child")
-                doc_id = d["doc_id"]
+                staged.append((d["doc_id"], content, meta, emb, level, lang))
+            self._ensure_index(dim)
+            idx = self._index
+            if idx.store_int8 and idx.ranges is None:
+                raise ValueError("int8 storage needs calibration ranges")
+            # rows: existing ids are overwritten in place, new ids appended (last one of a repeated id wins)
+            new_pos: Dict[str, int] = {}
+            new_rows: List[np.ndarray] = []
+            new_tags: List[int] = []
+            new_ids: List[str] = []
+            updates: List[Tuple[int, np.ndarray, int]] = []
+            langs_before = dict(self._langs._ids)
+            try:
+                for doc_id, _content, _meta, emb, level, lang in staged:
+                    tag = make_tag(level, self._langs.id_for(lang, create=True))
+                    if doc_id in self._row_of:
+                        updates.append((self._row_of[doc_id], emb, tag))
+                    elif doc_id in new_pos:
+                        new_rows[new_pos[doc_id]] = emb
+                        new_tags[new_pos[doc_id]] = tag
+                    else:
+                        new_pos[doc_id] = len(new_rows)
+                        new_ids.append(doc_id)
+                        new_rows.append(emb)
+                        new_tags.append(tag)
+                base = idx.n
+                if new_rows:
+                    idx.add(np.stack(new_rows), np.asarray(new_tags, dtype=np.uint8))
+            except Exception:
+                self._langs._ids = langs_before
+                raise
+            # ---- commit (nothing below can fail half way on the GPU side)
+            for row, emb, tag in updates:
+                idx.set_row(row, emb, tag)
+            for j, doc_id in enumerate(new_ids):
+                self._row_of[doc_id] = base + j
+                self._id_of.append(doc_id)
+            for doc_id, content, meta, emb, _level, _lang in staged:
                 if self._inner is not None:
                     self._inner.upsert(doc_id, content, emb.tolist(), meta)
                 else:
                     self._store_doc(doc_id, content, meta)
-                tag = make_tag(normalize_doc_level(level) or "child", self._langs.id_for(lang, create=True))
-                if doc_id in self._row_of:
-                    row = self._row_of[doc_id]
-                    if row >= self._index.n:  # same id twice in this batch: last one wins
-                        new_rows[row - self._index.n] = emb
-                        new_tags[row - self._index.n] = tag
-                    else:
-                        self._index.set_row(row, emb, tag)
-                else:
-                    self._row_of[doc_id] = self._index.n + len(new_rows)
-                    self._id_of.append(doc_id)
-                    new_rows.append(emb)
-                    new_tags.append(tag)
-            if new_rows:
-                self._index.add(np.stack(new_rows), np.asarray(new_tags, dtype=np.uint8))
             return len(documents)
 
     def import_quantized_batch(self, documents: List[Dict[str, Any]]) -> int:
         """Bulk-load documents whose quantised rows already exist in the reference's wire format
         (SURVEY.md 8f): each dict has ``doc_id``, ``content``, ``meta`` and ``binary`` = the raw
         bytes of the ``...:doc_binary:{id}`` key (np.packbits of the embedding, D/8 bytes,
-        redis_store.py:329-338), optionally ``int8`` = the raw bytes of ``...:doc_int8:{id}``
-        (D bytes, :339-349) and ``embedding`` (float32, needed when the index keeps float rows).
-        The payloads are stored as they are; new doc_ids only."""
+        redis_store.py:329-338) - or of the pgvector ``*_binary.embedding`` BYTEA column
+        (pgvector_store.py:322-355, same bytes) - optionally ``int8`` = the raw bytes of
+        ``...:doc_int8:{id}`` / the ``*_int8.embedding`` BYTEA column (D bytes, :339-349) and
+        ``embedding`` (float32, needed when the index keeps float rows).
+        The payloads are stored as they are; new doc_ids only; all-or-nothing like upsert_batch."""
         if not documents:
             return 0
         with self._lock:
@@ -177,31 +206,68 @@ class B200VectorStore(BaseVectorStore):
                                           else len(first["binary"]) * 8)
             self._ensure_index(dim)
             idx = self._index
-            codes, i8, f32, tags = [], [], [], []
-            for d in documents:
-                doc_id = d["doc_id"]
-                if doc_id in self._row_of:
-                    raise ValueError(f"import_quantized_batch: {doc_id} is already indexed (use upsert)")
-                content, meta, level, lang = self._prep_doc(d["content"], d.get("meta"), "child")
-                codes.append(np.frombuffer(d["binary"], dtype=np.uint8))
-                if idx.store_int8:
-                    if d.get("int8") is None:
-                        raise ValueError(f"{doc_id}: the index keeps int8 rows but no int8 payload was given")
-                    i8.append(np.frombuffer(d["int8"], dtype=np.int8))
-                if idx.store_f32:
-                    if d.get("embedding") is None:
-                        raise ValueError(f"{doc_id}: the index keeps float32 rows but no embedding was given")
-                    f32.append(np.asarray(d["embedding"], dtype=np.float32))
+            nbytes = (idx.dim + 7) // 8
+            codes, i8, f32, tags, staged = [], [], [], [], []
+            seen = set()
+            langs_before = dict(self._langs._ids)
+            try:
+                for d in documents:
+                    doc_id = d["doc_id"]
+                    if doc_id in self._row_of or doc_id in seen:
+                        raise ValueError(f"import_quantized_batch: {doc_id} is already indexed (use upsert)")
+                    seen.add(doc_id)
+                    content, meta, level, lang = self._prep_doc(d["content"], d.get("meta"), "child")
+                    c = np.frombuffer(bytes(d["binary"]), dtype=np.uint8)
+                    if c.size != nbytes:
+                        raise ValueError(f"{doc_id}: binary payload has {c.size} bytes, expected {nbytes}")
+                    codes.append(c)
+                    if idx.store_int8:
+                        if d.get("int8") is None:
+                            raise ValueError(f"{doc_id}: the index keeps int8 rows but no int8 payload was given")
+                        r = np.frombuffer(bytes(d["int8"]), dtype=np.int8)
+                        if r.size != idx.dim:
+                            raise ValueError(f"{doc_id}: int8 payload has {r.size} bytes, expected {idx.dim}")
+                        i8.append(r)
+                    if idx.store_f32:
+                        if d.get("embedding") is None:
+                            raise ValueError(f"{doc_id}: the index keeps float32 rows but no embedding was given")
+                        e = np.asarray(d["embedding"], dtype=np.float32)
+                        if e.shape != (idx.dim,):
+                            raise ValueError(f"{doc_id}: embedding shape {e.shape} != ({idx.dim},)")
+                        f32.append(e)
+                    tags.append(make_tag(level, self._langs.id_for(lang, create=True)))
+                    staged.append((doc_id, content, meta))
+                base = idx.n
+                idx.add_quantized(np.stack(codes), np.stack(i8) if i8 else None, np.stack(f32) if f32 else None,
+                                  np.asarray(tags, dtype=np.uint8))
+            except Exception:
+                self._langs._ids = langs_before
+                raise
+            for j, (doc_id, content, meta) in enumerate(staged):
+                self._row_of[doc_id] = base + j
+                self._id_of.append(doc_id)
                 if self._inner is not None:
                     self._inner.upsert_doc_only(doc_id, content, meta)
                 else:
                     self._store_doc(doc_id, content, meta)
-                tags.append(make_tag(normalize_doc_level(level) or "child", self._langs.id_for(lang, create=True)))
-                self._row_of[doc_id] = idx.n + len(codes) - 1
-                self._id_of.append(doc_id)
-            idx.add_quantized(np.stack(codes), np.stack(i8) if i8 else None, np.stack(f32) if f32 else None,
-                              np.asarray(tags, dtype=np.uint8))
             return len(documents)
+
+    def import_pgvector_rows(self, doc_rows, binary_rows, int8_rows=None) -> int:
+        """Bulk-load from the reference's pgvector tables (pgvector_store.py:322-355, 421-458):
+        ``doc_rows`` = rows of the leaf table as (doc_id, content, meta dict, embedding list or
+        None); ``binary_rows`` / ``int8_rows`` = rows of ``<table>_binary`` / ``<table>_int8`` as
+        (doc_id, embedding BYTEA) - ``bytes`` or ``memoryview`` as psycopg2 returns them.  Documents
+        without a binary row are skipped (they were stored through the reference's batch path,
+        which writes no quantised rows - SURVEY.md 0.5).  SQL I/O itself stays in the reference."""
+        b = {doc_id: bytes(payload) for doc_id, payload in binary_rows}
+        i8 = {doc_id: bytes(payload) for doc_id, payload in (int8_rows or [])}
+        docs = []
+        for doc_id, content, meta, embedding in doc_rows:
+            if doc_id not in b:
+                continue
+            docs.append({"doc_id": doc_id, "content": content, "meta": meta, "binary": b[doc_id],
+                         "int8": i8.get(doc_id), "embedding": embedding})
+        return self.import_quantized_batch(docs)
 
     def upsert_doc_only_batch(self, documents: List[Dict[str, Any]]) -> int:
         for d in documents:
@@ -281,6 +347,15 @@ class B200VectorStore(BaseVectorStore):
     def _predicate(self, language_filter: Optional[str], doc_level_filter: Optional[str]) -> Tuple[int, int]:
         return tag_predicate(normalize_doc_level(doc_level_filter), self._langs.id_for(language_filter))
 
+    @staticmethod
+    def _check_k(top_k: int) -> int:
+        """The kernels select at most RR_MAX_K entries per query: say so instead of clamping."""
+        if int(top_k) < 1:
+            raise ValueError(f"top_k must be >= 1, got {top_k}")
+        if int(top_k) > _lib.RR_MAX_K:
+            raise ValueError(f"top_k={top_k} exceeds the limit of {_lib.RR_MAX_K} results per query")
+        return int(top_k)
+
     def _hydrate(self, idx_row, score_row, count: int) -> List[Tuple[StoredDoc, float]]:
         out: List[Tuple[StoredDoc, float]] = []
         for r, s in zip(idx_row[:count], score_row[:count]):
@@ -295,12 +370,16 @@ class B200VectorStore(BaseVectorStore):
                        language_filter: Optional[str] = None, doc_level_filter: Optional[str] = None
                        ) -> List[List[Tuple[StoredDoc, float]]]:
         """Exact float32 cosine retrieval for a batch of queries [Q, D]."""
-        if self._index is None or self._index.n == 0:
-            return [[] for _ in range(len(queries))]
-        mask, value = self._predicate(language_filter, doc_level_filter)
-        idx, score, count = self._index.search_exact(queries, top_k, min_similarity, mask, value)
-        idx_h, score_h, count_h = idx.cpu().tolist(), score.cpu().tolist(), count.cpu().tolist()
-        return [self._hydrate(idx_h[i], score_h[i], count_h[i]) for i in range(len(idx_h))]
+        top_k = self._check_k(top_k)
+        # the lock is held from the launch to the row -> doc_id translation: delete_doc's
+        # swap-with-last and a growing upsert must not move rows under a search in flight
+        with self._lock:
+            if self._index is None or self._index.n == 0:
+                return [[] for _ in range(len(queries))]
+            mask, value = self._predicate(language_filter, doc_level_filter)
+            idx, score, count = self._index.search_exact(queries, top_k, min_similarity, mask, value)
+            idx_h, score_h, count_h = idx.cpu().tolist(), score.cpu().tolist(), count.cpu().tolist()
+            return [self._hydrate(idx_h[i], score_h[i], count_h[i]) for i in range(len(idx_h))]
 
     def retrieve_batch_quantized(self, queries, top_k: int, min_similarity: float = 0.0,
                                  rescore_multiplier: Optional[float] = None,
@@ -311,16 +390,21 @@ class B200VectorStore(BaseVectorStore):
         """Two-stage quantised retrieval for a batch of queries [Q, D]."""
         if not getattr(self._quant_config, "enabled", False):
             return self.retrieve_batch(queries, top_k, min_similarity, language_filter, doc_level_filter)
-        if self._index is None or self._index.n == 0:
-            return [[] for _ in range(len(queries))]
+        top_k = self._check_k(top_k)
         mult = rescore_multiplier if rescore_multiplier is not None else self._quant_config.rescore_multiplier
         use = use_rescoring if use_rescoring is not None else self._quant_config.use_rescoring
-        mask, value = self._predicate(language_filter, doc_level_filter)
-        idx, score, count = self._index.search_quantized(
-            queries, top_k, rescore_multiplier=mult, use_rescoring=use, min_similarity=min_similarity,
-            tag_mask=mask, tag_value=value)
-        idx_h, score_h, count_h = idx.cpu().tolist(), score.cpu().tolist(), count.cpu().tolist()
-        return [self._hydrate(idx_h[i], score_h[i], count_h[i]) for i in range(len(idx_h))]
+        if use and int(top_k * mult) > _lib.RR_MAX_K:
+            logger.warning(f"candidate_k = int({top_k} * {mult}) exceeds the kernel limit {_lib.RR_MAX_K}; "
+                           f"{_lib.RR_MAX_K} candidates are rescored instead")
+        with self._lock:
+            if self._index is None or self._index.n == 0:
+                return [[] for _ in range(len(queries))]
+            mask, value = self._predicate(language_filter, doc_level_filter)
+            idx, score, count = self._index.search_quantized(
+                queries, top_k, rescore_multiplier=mult, use_rescoring=use, min_similarity=min_similarity,
+                tag_mask=mask, tag_value=value)
+            idx_h, score_h, count_h = idx.cpu().tolist(), score.cpu().tolist(), count.cpu().tolist()
+            return [self._hydrate(idx_h[i], score_h[i], count_h[i]) for i in range(len(idx_h))]
 
     def retrieve_by_embedding(
         self,

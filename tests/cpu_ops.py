@@ -117,7 +117,7 @@ class CpuBm25Shard:
         self.orc = orc_shard
         self.row_base = row_base
 
-    def search_batch(self, q_terms, k):
+    def search_batch(self, q_terms, k, check=True):
         qt = np.asarray(q_terms)
         q = qt.shape[0]
         idx = np.full((q, k), -1, np.int64)

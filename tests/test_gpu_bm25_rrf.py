@@ -123,6 +123,105 @@ def test_bm25_long_queries_many_tiles(interleave):
             assert score[qi, :m].cpu().tolist() == sc.tolist(), (k, qi)
 
 
+@pytest.mark.parametrize("n_docs,v,tile,k,qlen,mean_len", [
+    (150_000, 5000, 1024, 100, 8, 60),   # the production shape of the batched path
+    (40_000, 3000, 256, 5, 70, 40),      # 70-token queries (three token chunks), small k
+    (40_000, 3000, 128, 300, 40, 40),    # smallest tile, k above many queries' match count
+    (9_000, 300, 512, 50, 8, 30),        # tiny vocabulary: most terms are dense head columns
+    (3_000, 200, 1024, 20, 6, 30),       # three tiles: the sample pass visits every tile
+    (2_000, 200, 1024, 20, 6, 30),       # fewer documents than the candidate list holds: no sample pass
+])
+def test_bm25_fast_path_vs_oracle(n_docs, v, tile, k, qlen, mean_len):
+    """The batched filter-and-refine path (float32 filter against a sampled bound, float64 refine in
+    the reference's operation order): ids and float64 scores == oracle, checked and unchecked."""
+    require_gpu()
+    ptr, toks = synthetic.zipf_corpus(n_docs, v, seed=n_docs + tile, mean_len=mean_len)
+    orc = BM25Oracle(ptr, toks, v)
+    bm = Bm25DeviceIndex.build(ptr, toks, v, orc.idf, orc.avgdl, orc.k1, orc.b, device=0, tile_docs=tile,
+                               row_base=11_000)
+    bm.fast_min_docs = 0
+    assert bm.fast_ok and bm.n_head > 0 and bm.uses_fast_path(1, k)
+    qt = synthetic.zipf_queries(80, qlen, v, seed=n_docs)
+    qt[0, :] = -1               # all tokens unknown
+    qt[1, 3:] = -1              # short query
+    qt[2, :] = qt[2, 0]         # one token repeated
+    qt[3, :] = np.int32(v - 1)  # a rare token only
+    qt[4, :] = 0                # the most frequent term only (a dense column, massive near-ties)
+    qt[5, 1:] = -1
+    qt[6, ::2] = -1             # unknown tokens interleaved
+    qt[7, :] = np.arange(qlen, dtype=np.int32) % min(v, 8)  # head terms only
+    want = [orc.search(qt[qi].tolist(), k) for qi in range(qt.shape[0])]
+
+    def check(idx, score, count, skip=()):
+        for qi in range(qt.shape[0]):
+            if qi in skip:
+                continue
+            rows, sc = want[qi]
+            m = int(count[qi])
+            assert m == rows.size, qi
+            assert idx[qi, :m].cpu().tolist() == (rows + 11_000).tolist(), qi
+            assert score[qi, :m].cpu().tolist() == sc.tolist(), qi   # float64 bit-exact
+            assert (idx[qi, m:].cpu().numpy() == -1).all()
+
+    idx, score, count = bm.search_batch(qt, k)
+    torch.cuda.synchronize()
+    check(idx, score, count)
+    assert bm.last_flagged <= 12, bm.last_flagged  # the fast path answered most queries itself
+    # unchecked call: every query that is NOT flagged is exact; the counter equals the flags
+    qd = torch.from_numpy(qt).cuda()
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    u_idx, u_score, u_count, flags = bm._search_fast(qd, k, counter)
+    torch.cuda.synchronize()
+    flagged = set(np.nonzero(flags.cpu().numpy())[0].tolist())
+    assert int(counter.item()) == len(flagged)
+    check(u_idx, u_score, u_count, skip=flagged)
+    bm.inexact_reset()
+    bm.search_batch(qt, k, check=False)
+    assert bm.inexact_total() == len(flagged)
+    # a single query (the reference's call shape) takes the same path
+    i1, s1, c1 = bm.search_batch(qt[9:10], k)
+    rows, sc = want[9]
+    assert i1[0, : int(c1[0])].cpu().tolist() == (rows + 11_000).tolist() and s1[0, : int(c1[0])].cpu().tolist() == sc.tolist()
+
+
+def test_bm25_fast_path_degenerate_ties_fall_back_to_exact_kernel():
+    """Every document scores the same: the sampled bound equals the top score, the candidate list
+    overflows, the query is flagged and the checked call answers it with the exact kernel."""
+    require_gpu()
+    n_docs = 70_000
+    ptr = np.arange(n_docs + 1, dtype=np.int64) * 2
+    toks = np.tile(np.array([0, 1], dtype=np.int32), n_docs)
+    toks[2 * 123 + 1] = 2  # one document differs
+    orc = BM25Oracle(ptr, toks, 3)
+    bm = Bm25DeviceIndex.build(ptr, toks, 3, orc.idf, orc.avgdl, orc.k1, orc.b, device=0)
+    assert bm.uses_fast_path(3, 10)
+    qt = np.array([[0, -1], [1, 0], [2, 1]], dtype=np.int32)
+    idx, score, count = bm.search_batch(qt, 10)
+    assert bm.last_flagged >= 2
+    for qi in range(3):
+        rows, sc = orc.search(qt[qi].tolist(), 10)
+        assert idx[qi, : int(count[qi])].cpu().tolist() == rows.tolist(), qi
+        assert score[qi, : int(count[qi])].cpu().tolist() == sc.tolist(), qi
+
+
+def test_bm25_fast_path_disabled_for_out_of_range_impacts():
+    """Impacts outside the float32-safe range (or non-positive) switch the batched path off."""
+    require_gpu()
+    ptr, toks = synthetic.zipf_corpus(70_000, 500, seed=4, mean_len=20)
+    orc = BM25Oracle(ptr, toks, 500)
+    idf = orc.idf.copy()
+    idf[7] = 1e-40
+    bm = Bm25DeviceIndex.build(ptr, toks, 500, idf, orc.avgdl, orc.k1, orc.b, device=0)
+    assert not bm.fast_ok and not bm.uses_fast_path(8, 10)
+    orc.idf = idf
+    qt = synthetic.zipf_queries(8, 6, 500, seed=4)
+    qt[0, 0] = 7
+    idx, score, count = bm.search_batch(qt, 10)
+    for qi in range(8):
+        rows, sc = orc.search(qt[qi].tolist(), 10)
+        assert idx[qi, : int(count[qi])].cpu().tolist() == rows.tolist() and score[qi, : int(count[qi])].cpu().tolist() == sc.tolist()
+
+
 def test_bm25_impacts_kernel_bit_exact():
     require_gpu()
     rng = np.random.default_rng(3)
@@ -151,7 +250,7 @@ def test_rrf_reference_goldens_bit_exact(golden_dir):
         if c["rrf_k"] is not None:
             kwargs["rrf_k"] = c["rrf_k"]
         res = agent.run(**kwargs)
-        assert res.success and res.status == "success", res.error
+        assert res.success and res.status.value == "success", res.error
         assert [int(d.doc_id[1:]) for d, _ in res.data] == c["ids"], c
         assert [s for _, s in res.data] == c["scores"], c  # float64 bit-exact
 
@@ -186,6 +285,6 @@ def test_rrf_error_behaviour():
     require_gpu()
     agent = RRFAgent(RetrievalConfig())
     res = agent.run(runs=[[("not a doc", 1.0)]])
-    assert res.data == [] and res.status == "partial" and res.success
+    assert res.data == [] and res.status.value == "partial" and res.success
     assert agent.run(runs=[[], []]).data == []
-    assert RRFAgent(RetrievalConfig(), enabled=False).run(runs=[]).status == "skipped"
+    assert RRFAgent(RetrievalConfig(), enabled=False).run(runs=[]).status.value == "skipped"

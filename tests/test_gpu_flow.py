@@ -188,7 +188,7 @@ def test_dense_agent_error_becomes_empty_list():
 
     agent = DenseRetrievalAgent(B200VectorStore(), Broken(), RetrievalConfig())
     res = agent.run(query="x")
-    assert res.data == [] and res.status == "partial"
+    assert res.data == [] and res.status.value == "partial"
     with pytest.raises(ValueError):
         DenseRetrievalAgent(None, Broken(), RetrievalConfig())
 
