@@ -424,6 +424,237 @@ def run_config2(bx: Bench, steps: int, warmup: int) -> dict:
     return out
 
 
+def _gather_obj(bx: Bench, obj):
+    """Python object from every rank -> list on every rank (host-side; parity checks only)."""
+    if bx.world == 1:
+        return [obj]
+    out = [None] * bx.world
+    bx.dist.all_gather_object(out, obj)
+    return out
+
+
+def run_config4(bx: Bench, steps: int) -> dict:
+    """BASELINE config 4: 10M x 1024 int8 exact search on the tensor cores, batch 4096, top-10,
+    row-sharded over the ranks (local exact top-k -> all_gather -> merge).  Parity: every rank
+    scores a sample of the queries against ITS rows with the oracle (exact int32 through float32
+    BLAS), rank 0 merges the per-shard lists on the CPU and compares with the GPUs' merged result."""
+    torch = bx.torch
+    import oracle
+    from radiant_rag_b200 import synthetic
+    from radiant_rag_b200.index import DenseIndex, synth_query_rows_device, synth_rows_device
+    from radiant_rag_b200.sharded import GpuShardOps, ShardedInt8Search, shard_range
+
+    n_total, nq, dim, seed, top_k = 10_000_000, 4096, 1024, 3, 10
+    lo, hi = shard_range(n_total, bx.rank, bx.world)
+    bound = 131070.0 * 2.0 ** -synthetic.value_shift(dim)
+    ranges = np.stack([np.full(dim, -bound, np.float32), np.full(dim, bound, np.float32)])
+    index = DenseIndex(dim, device=bx.local_rank, store_int8=True, store_f32=False, int8_ranges=ranges, row_base=lo,
+                       capacity=hi - lo)
+    for a in range(lo, hi, 250_000):
+        index.add(synth_rows_device(a, min(250_000, hi - a), dim, seed, bx.dev))
+    q8 = index.quantize_int8_queries(synth_query_rows_device(0, nq, dim, seed, n_total, bx.dev))
+    search = ShardedInt8Search(GpuShardOps(index))
+    out = {}
+
+    def step():
+        out["r"] = search.search(q8, top_k)
+
+    total_ms = bx.timed(step, steps, 2)
+    idx, score = out["r"]
+    ms = total_ms / steps
+    sample = np.arange(0, nq, 512)  # 8 queries
+    sel = torch.from_numpy(sample).to(bx.dev)
+    t0 = time.perf_counter()
+    w_r, w_s = oracle.int8_exact_topk_blas(q8[sel].cpu().numpy(), index.int8[: hi - lo].cpu().numpy(), top_k)
+    cpu_s = time.perf_counter() - t0
+    parts = _gather_obj(bx, (w_r + lo, w_s))
+    res = {"workload": f"config4: {n_total} x {dim} int8 exact search (tcgen05 kind::i8), batch {nq}, top-{top_k}, "
+                       f"row-sharded x{bx.world} (NCCL all_gather of per-shard top-k + merge)",
+           "ms_per_batch": ms, "value": nq / (ms * 1e-3), "unit": "queries/s", "rows_per_gpu": hi - lo,
+           "int8_TOPS_per_gpu": 2.0 * (hi - lo) * dim * nq / (ms * 1e-3) / 1e12}
+    if bx.rank == 0:
+        agree = 0
+        gi, gs = idx[sel].cpu().numpy(), score[sel].cpu().numpy()
+        for j in range(sample.size):
+            r = np.concatenate([p[0][j] for p in parts])
+            sc = np.concatenate([p[1][j] for p in parts]).astype(np.int64)
+            order = np.lexsort((r, -sc))[:top_k]
+            agree += int(np.array_equal(gi[j], r[order]) and np.array_equal(gs[j].astype(np.int64), sc[order]))
+        pk = _peaks()
+        peak = pk.get("i8_ss_tops") or 2.0 * pk["bf16_tflops"]
+        res["frac_of_int8_peak_per_gpu"] = res["int8_TOPS_per_gpu"] / peak
+        res["cpu_baseline"] = {"value": sample.size / cpu_s, "unit": "queries/s over one shard", "cores": "BLAS threads",
+                               "kind": "port", "sample": f"{sample.size} queries x {hi - lo} rows per rank (float32 BLAS, exact)",
+                               "gpu_matches_cpu_on_sample": f"{agree}/{sample.size}"}
+    del index, search, q8
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_config5(bx: Bench) -> dict:
+    """BASELINE config 5: 100M x 1024 binary codes + int8 rescore (k' = 40) and BM25 over the same
+    100M documents (50k vocabulary, ~200 tokens), fused by RRF, top-10, batch 8192, row-sharded
+    over 8 GPUs: the hybrid product call with NCCL exchanges of the per-shard candidates.
+    Parity on a sample of the queries: the dense half against a distributed oracle at full size
+    (per-shard Hamming lists merged on the CPU, owners rescore), BM25 by exact float64 scores of
+    every returned document recomputed from its regenerated tokens plus a selection check over
+    the deterministic first 1M documents, RRF against oracle.rrf_fuse."""
+    torch, dist = bx.torch, bx.dist
+    import oracle
+    from oracle.bm25 import BM25Oracle
+    from radiant_rag_b200 import synthetic
+    from radiant_rag_b200.bm25_index import Bm25DeviceIndex, synth_zipf_corpus_device
+    from radiant_rag_b200.hybrid import HybridSearch
+    from radiant_rag_b200.index import DenseIndex, synth_query_rows_device, synth_rows_device
+    from radiant_rag_b200.sharded import shard_range
+
+    n_total, dim, nq, v, mean_len, q_len, seed = 100_000_000, 1024, 8192, 50_000, 200, 8, 4
+    top_k, mult = 10, 4.0
+    dev = bx.dev
+    t0 = time.time()
+    lo, hi = shard_range(n_total, bx.rank, bx.world)
+    n_local = hi - lo
+    bound = 131070.0 * 2.0 ** -synthetic.value_shift(dim)
+    ranges = np.stack([np.full(dim, -bound, np.float32), np.full(dim, bound, np.float32)])
+    index = DenseIndex(dim, device=bx.local_rank, store_int8=True, store_f32=False, int8_ranges=ranges, row_base=lo,
+                       capacity=n_local)
+    for a in range(lo, hi, 500_000):
+        index.add(synth_rows_device(a, min(500_000, hi - a), dim, seed, dev))
+    ptr, toks = synth_zipf_corpus_device(n_local, v, seed, mean_len, device=bx.local_rank, row_start=lo)
+    bm = Bm25DeviceIndex.build(ptr, toks, v, None, None, 1.5, 0.75, device=bx.local_rank, row_base=lo, sharded=True)
+    del ptr, toks
+    torch.cuda.empty_cache()
+    build_s = time.time() - t0
+    queries = synth_query_rows_device(0, nq, dim, seed, n_total, dev)
+    qt_np = synthetic.zipf_queries(nq, q_len, v, seed)
+    qt = torch.from_numpy(qt_np).to(dev)
+    hybrid = HybridSearch(index, bm, rescore_multiplier=mult, prefer_int8=True)
+    kw = dict(top_k=top_k, dense_top_k=top_k, bm25_top_k=top_k, rrf_k=60)
+    out = {}
+
+    def step():
+        out["r"] = hybrid.search_batch(queries, qt, check=False, **kw)
+
+    hybrid.reset_unchecked_events()
+    total_ms = bx.timed(step, 3, 2)
+    ms = total_ms / 3
+    events = bx.sum_over_ranks(hybrid.unchecked_events())
+    res_g = out["r"]
+    # per-half times on this rank (each half contains its own collectives)
+    d_ms = bx.timed(lambda: hybrid.dense.search_quantized(queries, top_k, rescore_multiplier=mult, check_overflow=False), 2, 1) / 2
+    b_ms = bx.timed(lambda: hybrid.sparse.search_batch(qt, top_k, check=False), 2, 1) / 2
+    res = {"workload": f"config5: {n_total} x {dim} binary codes + int8 rescore (k'=40) + BM25 over {n_total} docs "
+                       f"(50k vocab, ~200 tokens) fused by RRF, top-{top_k}, batch {nq}, row-sharded x{bx.world}",
+           "ms_per_batch": ms, "value": nq / (ms * 1e-3), "unit": "hybrid queries/s", "rows_per_gpu": n_local,
+           "postings_per_gpu": bm.n_postings, "index_build_s": round(build_s, 1),
+           "ms": {"dense_top10": d_ms, "bm25_top10": b_ms}, "unchecked_exactness_events": events,
+           "dense_queries_per_s": nq / (d_ms * 1e-3), "bm25_queries_per_s": nq / (b_ms * 1e-3)}
+
+    # ---- parity on a sample
+    sample = [int(x) for x in np.linspace(1, nq - 1, 8).astype(int)]
+    sel = torch.tensor(sample, device=dev)
+    qh = queries[sel].cpu().numpy()
+    # dense: every rank's local Hamming top-40 from the oracle over ITS codes (full shard size)
+    codes = index.codes[:n_local].cpu().numpy()[:, : dim // 8]
+    loc_lists = []
+    for j in range(len(sample)):
+        dd, cc = oracle.hamming_topk(codes, oracle.quantize_ubinary(qh[j:j + 1]), 40)
+        loc_lists.append((dd[0], cc[0] + lo))
+    del codes
+    all_lists = _gather_obj(bx, loc_lists)
+    own_scores = []
+    for j in range(len(sample)):
+        d_all = np.concatenate([p[j][0] for p in all_lists]).astype(np.int64)
+        r_all = np.concatenate([p[j][1] for p in all_lists])
+        order = np.lexsort((r_all, d_all))[:40]
+        cand = r_all[order]
+        mine = (cand >= lo) & (cand < hi)
+        rows = index.int8[torch.from_numpy(cand[mine] - lo).to(dev)].cpu().numpy()
+        sc = (rows.astype(np.float64) @ qh[j].astype(np.float64)).astype(np.float32)
+        own_scores.append((cand, mine, sc))
+    all_scores = _gather_obj(bx, own_scores)
+    dense_ok = 0
+    if bx.rank == 0:
+        for j, qi in enumerate(sample):
+            cand = all_scores[0][j][0]
+            s = np.full(cand.size, -np.inf, dtype=np.float32)
+            for p in all_scores:
+                s[p[j][1]] = p[j][2]
+            order = np.argsort(-s.astype(np.float64), kind="stable")[:top_k]
+            order = order[s[order] >= 0.0]
+            m = int(res_g.dense_count[qi])
+            dense_ok += int(res_g.dense_idx[qi, :m].cpu().tolist() == cand[order].tolist())
+    # BM25: exact float64 scores of EVERY returned document recomputed from its regenerated tokens
+    # (global idf / avgdl are the index's inputs, R7), and no document of the deterministic first
+    # 1M documents beats the k-th returned one
+    from radiant_rag_b200 import _lib
+    bm25_ok = rrf_ok = 0
+    need = sorted(set(int(t) for qi in sample for t in qt_np[qi]))
+    need_t = torch.tensor(need, device=dev)
+    df_need = (bm.tile_term_ptr[:, 1:] - bm.tile_term_ptr[:, :-1])[:, need_t].sum(dim=0)
+    lens_local = torch.empty(n_local, dtype=torch.int32, device=dev)
+    _lib.call("rr_synth_doc_lengths", lens_local.data_ptr(), lo, n_local, seed, mean_len,
+              torch.cuda.current_stream().cuda_stream)
+    ptr_local = torch.zeros(n_local + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens_local.to(torch.int64), 0, out=ptr_local[1:])
+    totals = _gather_obj(bx, int(ptr_local[-1].item()))
+    pos0 = sum(totals[: bx.rank])  # global token position of this shard's first token
+    if bx.world > 1:
+        dist.all_reduce(df_need)
+    rows_all = res_g.bm25_idx[sel].flatten()
+    mine = rows_all[(rows_all >= lo) & (rows_all < hi)] - lo
+    where = {int(r) + lo: (pos0 + int(p), int(ln)) for r, p, ln in
+             zip(mine.cpu().tolist(), ptr_local[mine].cpu().tolist(), lens_local[mine].cpu().tolist())}
+    where_all = _gather_obj(bx, where)
+    if bx.rank == 0:
+        loc = {}
+        for w in where_all:
+            loc.update(w)
+        n_glob, tok_glob = n_total, sum(totals)
+        avgdl = tok_glob / n_glob
+        idf = np.zeros(v, dtype=np.float64)
+        for t, d in zip(need, df_need.cpu().tolist()):
+            if d:
+                idf[t] = np.log((n_glob - d + 0.5) / (d + 0.5) + 1.0)
+        cdf = synthetic.zipf_cdf_u32(v)
+        sub = 1_000_000
+        sub_ptr, sub_toks = synth_zipf_corpus_device(sub, v, seed, mean_len, device=bx.local_rank)
+        orc_sub = BM25Oracle(sub_ptr.cpu().numpy(), sub_toks.cpu().numpy(), v, 1.5, 0.75, idf=idf, avgdl=avgdl,
+                             only_terms=need)
+        orc_sub.known = idf > 0
+        del sub_ptr, sub_toks
+        for j, qi in enumerate(sample):
+            m = int(res_g.bm25_count[qi])
+            rows = res_g.bm25_idx[qi, :m].cpu().numpy()
+            got = res_g.bm25_score[qi, :m].cpu().numpy()
+            ok = m == top_k
+            # (a) a mini-corpus of just the returned documents, tokens regenerated on the CPU
+            mini_toks = [synthetic.zipf_tokens(loc[int(r)][0], loc[int(r)][1], seed, cdf) for r in rows]
+            mini_ptr = np.concatenate([[0], np.cumsum([t.size for t in mini_toks])])
+            orc_mini = BM25Oracle(mini_ptr, np.concatenate(mini_toks), v, 1.5, 0.75, idf=idf, avgdl=avgdl)
+            orc_mini.known = idf > 0
+            ok = ok and np.array_equal(orc_mini.scores(qt_np[qi].tolist()), got)
+            ok = ok and all((got[i] > got[i + 1]) or (got[i] == got[i + 1] and rows[i] < rows[i + 1]) for i in range(m - 1))
+            # (b) selection: nothing among the first 1M documents outranks the returned k-th
+            s_sub = orc_sub.scores(qt_np[qi].tolist())
+            kth_s, kth_r = got[-1], rows[-1]
+            better = np.nonzero((s_sub > kth_s) | ((s_sub == kth_s) & (np.arange(sub) < kth_r)))[0]
+            ok = ok and set(better.tolist()) <= set(rows.tolist())
+            bm25_ok += int(ok)
+            dm = int(res_g.dense_count[qi])
+            ids, sc = oracle.rrf_fuse([res_g.dense_idx[qi, :dm].cpu().tolist(), rows.tolist()], top_k, 60)
+            fm = int(res_g.count[qi])
+            rrf_ok += int(res_g.idx[qi, :fm].cpu().tolist() == ids.tolist() and res_g.score[qi, :fm].cpu().tolist() == sc.tolist())
+        res["parity_on_sample"] = {
+            "queries": len(sample),
+            "dense_matches_distributed_oracle": f"{dense_ok}/{len(sample)}",
+            "bm25_returned_scores_exact_and_selection_holds_on_first_1M_docs": f"{bm25_ok}/{len(sample)}",
+            "rrf_matches_oracle": f"{rrf_ok}/{len(sample)}"}
+    del hybrid, bm, index
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_gpu_arm(args) -> None:
     bx = Bench(args)
     torch, dist = bx.torch, bx.dist

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RR_ABI_VERSION 1
+#define RR_ABI_VERSION 2
 
 typedef enum rr_status {
   RR_OK = 0,
@@ -91,8 +91,9 @@ int rr_hamming_topk(const uint32_t* codes, int64_t n, int32_t words, const uint8
  *   q_pm1     i8 [q, 32*words]  the query codes expanded by rr_unpack_codes_pm1(qcodes, q,
  *             4*words, 32*words, ...);
  *   *overflow device u32, zeroed by the caller; incremented when a query's bounded candidate
- *             list overflowed - the caller must then redo the call with rr_hamming_topk
- *             (the results of an overflowed call are not exact);
+ *             list overflowed (the results of that query are then not exact);
+ *   overflow_flags device u8 [q] or NULL: 1 for every query whose list overflowed - the caller
+ *             redoes exactly those queries with rr_hamming_topk;
  *   workspace from rr_tc_search_workspace_bytes. */
 int rr_unpack_codes_pm1(const uint8_t* codes, int64_t n, int32_t code_stride, int32_t dim,
                         int8_t* out, void* stream);
@@ -100,14 +101,15 @@ size_t rr_tc_search_workspace_bytes(int64_t n, int32_t q, int32_t k);
 int rr_hamming_topk_tc(const uint32_t* codes, int64_t n, int32_t words, const uint8_t* tags,
                        uint8_t tag_mask, uint8_t tag_value, const int8_t* q_pm1, int32_t q,
                        int32_t k, int64_t row_base, int32_t* out_dist, int64_t* out_idx,
-                       uint32_t* overflow, void* workspace, size_t workspace_bytes, void* stream);
+                       uint32_t* overflow, uint8_t* overflow_flags, void* workspace,
+                       size_t workspace_bytes, void* stream);
 /* BASELINE config 4 on tensor cores: exact int8 x int8 -> int32 search, (score desc, row asc);
  * same contract as rr_int8_search_topk, workspace from rr_tc_search_workspace_bytes. */
 int rr_int8_search_topk_tc(const int8_t* emb, int64_t n, int32_t dim, const uint8_t* tags,
                            uint8_t tag_mask, uint8_t tag_value, const int8_t* queries_i8,
                            int32_t q, int32_t top_k, int64_t row_base, int32_t* out_score,
-                           int64_t* out_idx, uint32_t* overflow, void* workspace,
-                           size_t workspace_bytes, void* stream);
+                           int64_t* out_idx, uint32_t* overflow, uint8_t* overflow_flags,
+                           void* workspace, size_t workspace_bytes, void* stream);
 
 /* Test/debug: raw tensor-core scores as order-preserving keys, u32 [q][ceil(n/128)*128]
  * (key = ~(score ^ 0x80000000), 0xFFFFFFFF = padded row). */

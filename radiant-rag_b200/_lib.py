@@ -44,8 +44,8 @@ PROTOTYPES = {
     "rr_hamming_topk": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _sz, _p]),
     "rr_unpack_codes_pm1": (_i32, [_p, _i64, _i32, _i32, _p, _p]),
     "rr_tc_search_workspace_bytes": (_sz, [_i64, _i32, _i32]),
-    "rr_hamming_topk_tc": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
-    "rr_int8_search_topk_tc": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
+    "rr_hamming_topk_tc": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "rr_int8_search_topk_tc": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "rr_tc_dense_keys": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p]),
     "rr_tc_timing": (_i32, [_i32]),
     "rr_tc_last_timing_ms": (_i32, [_p]),

@@ -128,6 +128,7 @@ class Bm25DeviceIndex:
         head_terms: int = 32,
         sharded: bool = False,
         group: Any = None,
+        chunk_docs: int = 2_000_000,
     ) -> "Bm25DeviceIndex":
         """doc_ptr int64 [N+1] / doc_terms int32 [T]: the documents of THIS shard as CSR of
         term ids; idf f64 [n_terms] (0 for unknown terms), avgdl, k1, b: global tables
@@ -146,10 +147,10 @@ class Bm25DeviceIndex:
         dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         _lib.init(dev.index or 0)
         ptr = to_device(doc_ptr, dev, torch.int64)
-        terms = to_device(doc_terms, dev, torch.int64)
+        terms_all = to_device(doc_terms, dev, torch.int32)
         n = int(ptr.numel() - 1)
         v = int(n_terms)
-        if n <= 0 or v <= 0 or terms.numel() == 0:
+        if n <= 0 or v <= 0 or terms_all.numel() == 0:
             z64 = torch.zeros((1, max(v, 0) + 1), dtype=torch.int64, device=dev)
             return cls(dev, 0, v, tile_docs, z64, torch.zeros(0, dtype=torch.int32, device=dev),
                        torch.zeros(0, dtype=torch.float64, device=dev), row_base)
@@ -165,27 +166,44 @@ class Bm25DeviceIndex:
                                  "shard the documents over more GPUs or prune the vocabulary")
         lens = ptr[1:] - ptr[:-1]
         dlen = lens.to(torch.int32) if doc_len is None else to_device(doc_len, dev, torch.int32)
-        rows = torch.repeat_interleave(torch.arange(n, dtype=torch.int64, device=dev), lens)
-        # key = (tile * V + term) * tile_docs + row_in_tile  -> sorted by (tile, term, row)
-        key = ((rows // tile_docs) * v + terms) * tile_docs + (rows % tile_docs)
-        del rows, terms
-        key, _ = torch.sort(key)
-        ukey, tf = torch.unique_consecutive(key, return_counts=True)
-        del key
-        if bank_interleave and ukey.numel() > 1:
-            ukey, tf = cls._bank_interleave(ukey, tf, tile_docs)
-        tt = ukey // tile_docs  # tile * V + term, non-decreasing
-        post_row64 = (tt // v) * tile_docs + (ukey % tile_docs)
-        term = tt % v
-        del ukey
-        # offsets of every (tile, term) segment: ONE searchsorted over the sorted segment ids, laid
-        # out [n_tiles, V+1] by a strided view of the flat [n_tiles*V + 1] result (row t of the
-        # table is flat[t*V : t*V + V + 1]; no dense bincount / cumsum / gather temporaries)
-        flat = torch.searchsorted(tt, torch.arange(n_tiles * v + 1, dtype=torch.int64, device=dev))
-        del tt
-        tile_term_ptr = flat.as_strided((n_tiles, v + 1), (v, 1)).contiguous()
-        del flat
-        df_dev = torch.bincount(term, minlength=v)
+        # ---- pass 1: (tile, term, row) order.  Tiles are independent, so the documents are sorted
+        # in chunks of whole tiles (bounded temporaries: a 12.5M-document shard holds 2.5G tokens)
+        chunk = max(tile_docs, (int(chunk_docs) // tile_docs) * tile_docs)
+        tile_term_ptr = torch.empty((n_tiles, v + 1), dtype=torch.int64, device=dev)
+        df_dev = torch.zeros(v, dtype=torch.int64, device=dev)
+        rows_c, term_c, tf_c = [], [], []
+        n_post = 0
+        for c0 in range(0, n, chunk):
+            c1 = min(n, c0 + chunk)
+            t0, t1 = c0 // tile_docs, (c1 + tile_docs - 1) // tile_docs
+            a, b_ = int(ptr[c0].item()), int(ptr[c1].item())
+            rows = torch.repeat_interleave(torch.arange(c0, c1, dtype=torch.int64, device=dev), lens[c0:c1])
+            # key = (tile * V + term) * tile_docs + row_in_tile  -> sorted by (tile, term, row)
+            key = ((rows // tile_docs) * v + terms_all[a:b_].to(torch.int64)) * tile_docs + (rows % tile_docs)
+            del rows
+            key, _ = torch.sort(key)
+            ukey, tf = torch.unique_consecutive(key, return_counts=True)
+            del key
+            if bank_interleave and ukey.numel() > 1:
+                ukey, tf = cls._bank_interleave(ukey, tf, tile_docs)
+            tt = ukey // tile_docs  # tile * V + term, non-decreasing
+            # offsets of every (tile, term) segment of these tiles: ONE searchsorted over the sorted
+            # segment ids; row t of the table is flat[(t - t0)*V : (t - t0)*V + V + 1] (a strided view,
+            # no dense bincount / cumsum / gather temporaries)
+            flat = torch.searchsorted(tt, torch.arange(t0 * v, t1 * v + 1, dtype=torch.int64, device=dev))
+            tile_term_ptr[t0:t1] = flat.as_strided((t1 - t0, v + 1), (v, 1)) + n_post
+            del flat
+            term = tt % v
+            rows_c.append(((tt // v) * tile_docs + (ukey % tile_docs)).to(torch.int32))
+            del ukey, tt
+            df_dev += torch.bincount(term, minlength=v)
+            term_c.append(term.to(torch.int32))
+            tf_c.append(tf.to(torch.int32))
+            n_post += int(term.numel())
+            del term, tf
+        del terms_all
+        post_row = torch.cat(rows_c) if len(rows_c) > 1 else rows_c[0]
+        del rows_c
         if idf is None or avgdl is None:
             df_glob = df_dev.clone()
             stats = torch.tensor([n, int(lens.sum().item()) if doc_len is None else int(dlen.sum(dtype=torch.int64).item())],
@@ -206,14 +224,17 @@ class Bm25DeviceIndex:
                     idf[t] = np.log((n_glob - d + 0.5) / (d + 0.5) + 1.0)
             del df_glob
         idf_t = to_device(idf, dev, torch.float64)
-        post_idf = idf_t[term].contiguous()
-        post_len = dlen[post_row64].contiguous()
-        post_tf = tf.to(torch.int32).contiguous()
-        post_impact = torch.empty(post_tf.shape, dtype=torch.float64, device=dev)
-        _lib.call("rr_bm25_impacts", post_tf.data_ptr(), post_len.data_ptr(), post_idf.data_ptr(),
-                  post_tf.numel(), float(k1), float(b), float(avgdl), post_impact.data_ptr(), _stream())
-        del post_idf, post_len, post_tf
-        post_row = post_row64.to(torch.int32).contiguous()
+        # ---- pass 2: impacts in the reference's operation order, chunk by chunk
+        post_impact = torch.empty(n_post, dtype=torch.float64, device=dev)
+        off = 0
+        for term, tf in zip(term_c, tf_c):
+            m = int(term.numel())
+            post_idf = idf_t[term.to(torch.int64)].contiguous()
+            post_len = dlen[post_row[off:off + m].to(torch.int64)].contiguous()
+            _lib.call("rr_bm25_impacts", tf.data_ptr(), post_len.data_ptr(), post_idf.data_ptr(), m, float(k1),
+                      float(b), float(avgdl), post_impact[off:off + m].data_ptr(), _stream())
+            off += m
+            del post_idf, post_len
         # ---- head terms: dense float64 columns per tile for the batched path
         head_slot = head_imp = None
         fast_ok = False
@@ -232,14 +253,19 @@ class Bm25DeviceIndex:
             head_slot[order] = torch.arange(n_head, dtype=torch.int32, device=dev)
             head_imp = torch.zeros((n_tiles, max(n_head, 1), tile_docs), dtype=torch.float64, device=dev)
             if n_head:
-                slot = head_slot[term].to(torch.int64)
-                sel = slot >= 0
-                pos = ((post_row64[sel] // tile_docs) * n_head + slot[sel]) * tile_docs + post_row64[sel] % tile_docs
-                head_imp.view(-1)[pos] = post_impact[sel]
-                del slot, sel, pos
+                off = 0
+                for term in term_c:
+                    m = int(term.numel())
+                    slot = head_slot[term.to(torch.int64)].to(torch.int64)
+                    sel = torch.nonzero(slot >= 0).flatten()
+                    r64 = post_row[off:off + m][sel].to(torch.int64)
+                    pos = ((r64 // tile_docs) * n_head + slot[sel]) * tile_docs + r64 % tile_docs
+                    head_imp.view(-1)[pos] = post_impact[off:off + m][sel]
+                    off += m
+                    del slot, sel, r64, pos
             else:
                 head_imp = head_imp[:, :0, :].contiguous()
-        del post_row64, term, df_dev
+        del term_c, tf_c, df_dev
         torch.cuda.current_stream().synchronize()  # temporaries die here
         return cls(dev, n, v, tile_docs, tile_term_ptr, post_row, post_impact, row_base,
                    head_slot=head_slot, head_imp=head_imp, fast_ok=fast_ok)

@@ -13,29 +13,28 @@
 namespace rr {
 
 __global__ void __launch_bounds__(256) probe_popc_kernel(int iters, u32* sink) {
-  u32 x[8], acc[8];
+  // 8 independent dependent chains x = popc(x) ^ k per thread: one POPC + one LOP3 per step, so
+  // the figure is a LOWER bound of the POPC pipe when it is not the narrower of the two
+  u32 x[8], k[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     x[j] = threadIdx.x * 2654435761u + blockIdx.x * 40503u + j * 0x9E3779B9u;
-    acc[j] = 0;
+    k[j] = x[j] * 0x85EBCA6Bu + sink[1];  // not a compile-time constant
   }
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[j] += __popc(x[j]);
-      x[j] += 0x61C88647u;
-    }
+    for (int j = 0; j < 8; ++j) x[j] = __popc(x[j]) ^ k[j];
   }
   u32 s = 0;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) s += acc[j];
-  if (s == 0xFFFFFFFFu) sink[0] = s;  // never true: keeps the chains alive
+  for (int j = 0; j < 8; ++j) s += x[j];
+  if (s == 0xFFFFFFFFu) sink[0] = s;  // practically never: keeps the chains alive
 }
 
 __global__ void __launch_bounds__(512) probe_smem_kernel(int iters, float* sink) {
   extern __shared__ __align__(16) unsigned char ps_smem[];
   float4* s4 = reinterpret_cast<float4*>(ps_smem);
-  const int n4 = 32768 / 16;  // 32 KB window
+  const int n4 = 65536 / 16;  // 64 KB window: the 8 loads of an iteration hit 8 different addresses
   for (int i = threadIdx.x; i < n4; i += blockDim.x) s4[i] = make_float4(1.f, 2.f, 3.f, 4.f);
   __syncthreads();
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -138,6 +137,7 @@ extern "C" int rr_probe_popc(int32_t iters, double* out_popc32_per_s, void* stre
   cudaStream_t st = (cudaStream_t)stream;
   u32* sink = nullptr;
   RR_CUDA(cudaMalloc(&sink, 256));
+  RR_CUDA(cudaMemsetAsync(sink, 0, 256, st));
   int sms = sm_count() > 0 ? sm_count() : 148;
   const int blocks = sms * 8;
   float ms = 0.f;
@@ -156,7 +156,8 @@ extern "C" int rr_probe_smem(int32_t iters, double* out_bytes_per_s, void* strea
   int sms = sm_count() > 0 ? sm_count() : 148;
   const int blocks = sms * 2;
   float ms = 0.f;
-  int rc = probe_time([&] { probe_smem_kernel<<<blocks, 512, 32768, st>>>(iters, sink); }, st, &ms);
+  RR_CUDA(cudaFuncSetAttribute(probe_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+  int rc = probe_time([&] { probe_smem_kernel<<<blocks, 512, 65536, st>>>(iters, sink); }, st, &ms);
   cudaFree(sink);
   if (rc != RR_OK) return rc;
   *out_bytes_per_s = (double)blocks * 512.0 * 8.0 * 16.0 * iters / (ms * 1e-3);

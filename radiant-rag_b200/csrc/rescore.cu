@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "select.cuh"
+#include "tc_ptx.cuh"
 
 namespace rr {
 
@@ -240,6 +241,106 @@ __global__ void __launch_bounds__(RS_THREADS) rescore_f32_kernel(const RescoreAr
   }
 }
 
+// Batched scoring with the candidate rows STAGED through shared memory by the bulk-copy engine.
+// The gather is a random read of contiguous rows (3 KB float32 / 1 KB int8 at the BASELINE
+// shapes); what limits it is the number of bytes a CTA keeps in flight, and with register-staged
+// loads that is bounded by registers (the kernel above reaches ~40 % of HBM).  Here one elected
+// thread issues cp.async.bulk (global -> shared, mbarrier complete_tx) for up to `stages` rows ahead
+// of the seven consumer warps; bytes in flight are bounded by shared memory only.  A consumer warp
+// owns a row (and, the ring depth being a multiple of seven, always the same ring slots): same lane-strided float64 accumulation and the same shuffle tree as
+// dot_f32_row / dot_i8_row, so the scores are bit-identical to the register-staged kernel.
+constexpr int RG_THREADS = 256;
+constexpr int RG_CONSUMERS = RG_THREADS / 32 - 1;
+constexpr int RG_MAX_STAGES = 32;
+
+template <int EMB>
+__global__ void __launch_bounds__(RG_THREADS) rescore_ring_kernel(const RescoreArgs a, int stages, int row_bytes, int per) {
+  extern __shared__ __align__(128) unsigned char rg_smem[];
+  unsigned char* ring = rg_smem;                                               // [stages][row_bytes]
+  float* sq = reinterpret_cast<float*>(ring + (size_t)stages * row_bytes);     // [dim]
+  long long* s_loc = reinterpret_cast<long long*>(sq + align_up_dev((size_t)a.dim, 4));  // [per]
+  int* s_ci = reinterpret_cast<int*>(s_loc + per);                             // [per]
+  __shared__ __align__(8) u64 full[RG_MAX_STAGES];
+  __shared__ __align__(8) u64 empty[RG_MAX_STAGES];
+  __shared__ int s_nvalid;
+  const int q = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lo = blockIdx.y * per;
+  const int hi = min(a.c, lo + per);
+  if (threadIdx.x == 0) {
+    s_nvalid = 0;
+    for (int s = 0; s < stages; ++s) {
+      tc_mbar_init(tc_smem(full + s), 1);
+      tc_mbar_init(tc_smem(empty + s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int d = threadIdx.x; d < a.dim; d += RG_THREADS) sq[d] = a.queries[(size_t)q * a.dim + d];
+  __syncthreads();
+  const long long* cand = a.cand_idx + (size_t)q * a.c;
+  for (int ci = lo + threadIdx.x; ci < hi; ci += RG_THREADS) {
+    const long long idx = cand[ci];
+    const long long loc = idx - a.row_base;
+    if (idx >= 0 && loc >= 0 && loc < a.n) {
+      const int slot = atomicAdd(&s_nvalid, 1);  // rows are independent: their order is free
+      s_loc[slot] = loc;
+      s_ci[slot] = ci;
+    } else {
+      a.out_score[(size_t)q * a.c + ci] = -INFINITY;  // not owned by this shard / padding
+    }
+  }
+  __syncthreads();
+  const int nv = s_nvalid;
+  if (warp == 0) {
+    if (lane == 0) {
+      const unsigned char* base = reinterpret_cast<const unsigned char*>(a.emb);
+      for (int j = 0; j < nv; ++j) {
+        const int s = j % stages;
+        const int f = j / stages;
+        if (f > 0) tc_mbar_wait(tc_smem(empty + s), (u32)(f - 1) & 1u);
+        tc_mbar_expect_tx(tc_smem(full + s), (u32)row_bytes);
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+            ::"r"(tc_smem(ring + (size_t)s * row_bytes)), "l"(base + (size_t)s_loc[j] * row_bytes), "r"((u32)row_bytes),
+              "r"(tc_smem(full + s)) : "memory");
+      }
+    }
+  } else {
+    const float4* q4 = reinterpret_cast<const float4*>(sq);
+    const int nv4 = a.dim >> 2;
+    for (int j = warp - 1; j < nv; j += RG_CONSUMERS) {
+      const int s = j % stages;
+      tc_mbar_wait(tc_smem(full + s), (u32)(j / stages) & 1u);
+      double acc = 0.0;
+      if (EMB == RR_F32) {
+        const float4* r4 = reinterpret_cast<const float4*>(ring + (size_t)s * row_bytes);
+        for (int v = lane; v < nv4; v += 32) {
+          const float4 e = r4[v];
+          const float4 w = q4[v];
+          acc += (double)w.x * (double)e.x;
+          acc += (double)w.y * (double)e.y;
+          acc += (double)w.z * (double)e.z;
+          acc += (double)w.w * (double)e.w;
+        }
+      } else {
+        const int* r4 = reinterpret_cast<const int*>(ring + (size_t)s * row_bytes);
+        for (int v = lane; v < nv4; v += 32) {
+          const int e = r4[v];
+          const float4 w = q4[v];
+          acc += (double)w.x * (double)(int)(signed char)(e & 0xFF);
+          acc += (double)w.y * (double)(int)(signed char)((e >> 8) & 0xFF);
+          acc += (double)w.z * (double)(int)(signed char)((e >> 16) & 0xFF);
+          acc += (double)w.w * (double)(int)(signed char)((e >> 24) & 0xFF);
+        }
+      }
+      __syncwarp();  // every lane has read its part of the slot
+      if (lane == 0) tc_mbar_arrive(tc_smem(empty + s));
+      acc = warp_sum_f64(acc);
+      if (lane == 0) a.out_score[(size_t)q * a.c + s_ci[j]] = (float)acc;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(RS_THREADS)
     rank_scored_f32_kernel(const float* scores, const long long* cand_idx, int c, int p, int top_k,
                            double min_sim, float* out_score, long long* out_idx, int* out_count) {
@@ -378,8 +479,42 @@ extern "C" int rr_score_candidates_f32(const float* queries, int32_t q, int32_t 
   RR_CHECK_ARG(emb_dtype == RR_F32 || emb_dtype == RR_I8, "emb_dtype must be RR_F32 or RR_I8");
   RescoreArgs a{queries, dim, emb, n, row_base, (const long long*)cand_idx, c, 1,
                 0.0, out_score, nullptr, nullptr};
-  const size_t smem = align_up((size_t)dim * 4, 16) + 8;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // rows staged through shared memory by the bulk-copy engine when they are 16-byte multiples
+    // (float32: dim % 4 == 0, int8: dim % 16 == 0) at 16-byte aligned addresses
+    const int row_bytes = emb_dtype == RR_F32 ? dim * 4 : dim;
+    if ((dim & 3) == 0 && (row_bytes & 15) == 0 && ((size_t)emb & 15) == 0 && n > 0) {
+      int split = (2 * 148 + q - 1) / q;  // two CTAs per SM are resident
+      const int max_split = (c + 4 * RG_CONSUMERS - 1) / (4 * RG_CONSUMERS);
+      if (split > max_split) split = max_split;
+      if (split > 16) split = 16;
+      if (split < 1) split = 1;
+      const int per = (c + split - 1) / split;
+      const size_t fixed = align_up((size_t)dim * 4, 16) + (size_t)per * 12 + 16;
+      // a ring slot must always be consumed by the SAME warp (row j -> slot j % stages, warp j % 7):
+      // a parity wait is only meaningful for a waiter that has seen the previous phase complete,
+      // so the ring depth is a multiple of the consumer count
+      int stages = (int)((100 * 1024 - fixed) / row_bytes);
+      if (stages > RG_MAX_STAGES) stages = RG_MAX_STAGES;
+      stages = stages / RG_CONSUMERS * RG_CONSUMERS;
+      if (stages >= RG_CONSUMERS && per <= 65535) {
+        const size_t rsm = (size_t)stages * row_bytes + fixed;
+        dim3 grid(q, split);
+        RescoreArgs ar = a;
+        if (emb_dtype == RR_F32) {
+          RR_CUDA(cudaFuncSetAttribute(rescore_ring_kernel<RR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+          rescore_ring_kernel<RR_F32><<<grid, RG_THREADS, rsm, st>>>(ar, stages, row_bytes, per);
+        } else {
+          RR_CUDA(cudaFuncSetAttribute(rescore_ring_kernel<RR_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+          rescore_ring_kernel<RR_I8><<<grid, RG_THREADS, rsm, st>>>(ar, stages, row_bytes, per);
+        }
+        RR_LAUNCH_CHECK();
+        return RR_OK;
+      }
+    }
+  }
+  const size_t smem = align_up((size_t)dim * 4, 16) + 8;
   // enough CTAs for ~4 per SM, at least one warp iteration of work each
   int split = (4 * 148 + q - 1) / q;
   const int max_split = (c + RS_ROWS * RS_WARPS - 1) / (RS_ROWS * RS_WARPS);

@@ -627,7 +627,8 @@ template <int MODE>  // MERGE_I32_DESC: scores as is; MERGE_HAMMING: dist = popc
 __global__ void __launch_bounds__(LIST_THREADS, 2)
     tc_select_lists_kernel(const u32* cnt, const int* list_score, const u32* list_row, int n_cta, int cap_cta,
                            int k, int kcap, int dim, const int8_t* q_pm1, const int* tau, long long row_base,
-                           void* out_a, long long* out_idx, int* out_count, unsigned* overflow) {
+                           void* out_a, long long* out_idx, int* out_count, unsigned* overflow,
+                           unsigned char* overflow_flags) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
   u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
   u32* s_k2 = reinterpret_cast<u32*>(s_k1 + kcap);
@@ -638,7 +639,9 @@ __global__ void __launch_bounds__(LIST_THREADS, 2)
   __shared__ u32 s_off[256];
   __shared__ u32 s_total;
   __shared__ int s_qpop;
+  __shared__ int s_ovf;
   const int q = blockIdx.x;
+  if (threadIdx.x == 0) s_ovf = 0;
   if (MODE == MERGE_HAMMING) {
     if (threadIdx.x == 0) s_qpop = 0;
     __syncthreads();
@@ -649,10 +652,14 @@ __global__ void __launch_bounds__(LIST_THREADS, 2)
   }
   for (int i = threadIdx.x; i < n_cta; i += LIST_THREADS) {
     const u32 c = cnt[(size_t)q * n_cta + i];
-    if (c > (u32)cap_cta) atomicAdd(overflow, 1u);
+    if (c > (u32)cap_cta) {
+      atomicAdd(overflow, 1u);
+      s_ovf = 1;  // this query's result is not guaranteed: the caller redoes it on the exact path
+    }
     s_seg[i] = c < (u32)cap_cta ? c : (u32)cap_cta;
   }
   __syncthreads();
+  if (overflow_flags && threadIdx.x == 0) overflow_flags[q] = (unsigned char)s_ovf;
   const int* ls = list_score + (size_t)q * n_cta * cap_cta;
   const u32* lr = list_row + (size_t)q * n_cta * cap_cta;
   // i / cap_cta by multiply-high where that is exact (i * cap_cta < 2^32 for every slot)
@@ -881,8 +888,8 @@ static TcSmem tc_smem_layout(int kb, bool packed) {
 static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n, int dim, const uint8_t* tags,
                      unsigned tag_mask, unsigned tag_value, const int8_t* queries, int q, int k, long long row_base,
                      int hamming,
-                     int* out_a, long long* out_idx, unsigned* overflow_out, void* ws, size_t ws_bytes,
-                     cudaStream_t st) {
+                     int* out_a, long long* out_idx, unsigned* overflow_out, unsigned char* overflow_flags,
+                     void* ws, size_t ws_bytes, cudaStream_t st) {
   const TcPlan p = tc_plan(n, q, k);
   if (!ws || ws_bytes < p.total) {
     set_error("tensor-core search: workspace %zu < %zu", ws_bytes, p.total);
@@ -976,11 +983,11 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   if (hamming)
     tc_select_lists_kernel<MERGE_HAMMING><<<q, LIST_THREADS, list_smem, st>>>(
         a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, queries, (const int*)(w + p.off_tau), row_base, out_a,
-        out_idx, nullptr, overflow_out);
+        out_idx, nullptr, overflow_out, overflow_flags);
   else
     tc_select_lists_kernel<MERGE_I32_DESC><<<q, LIST_THREADS, list_smem, st>>>(
         a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, queries, (const int*)(w + p.off_tau), row_base, out_a,
-        out_idx, nullptr, overflow_out);
+        out_idx, nullptr, overflow_out, overflow_flags);
   RR_LAUNCH_CHECK();
   tc_mark(4, st);
   g_tc_timed = g_tc_timing && g_tc_ev_ready;
@@ -1042,26 +1049,28 @@ static int tc_check(int64_t n, int32_t dim, int32_t q, int32_t k) {
 extern "C" int rr_hamming_topk_tc(const uint32_t* codes, int64_t n, int32_t words, const uint8_t* tags,
                                   uint8_t tag_mask, uint8_t tag_value, const int8_t* q_pm1, int32_t q,
                                   int32_t k, int64_t row_base, int32_t* out_dist, int64_t* out_idx,
-                                  uint32_t* overflow, void* workspace, size_t workspace_bytes, void* stream) {
+                                  uint32_t* overflow, uint8_t* overflow_flags, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
   RR_CHECK_ARG(words >= 4 && words <= RR_MAX_WORDS && words % 4 == 0, "words must be a multiple of 4 in [4, 32]");
   const int dim = words * 32;  // padded width; padding bits are 0 in rows and queries alike
   int rc = tc_check(n, dim, q, k);
   if (rc != RR_OK) return rc;
   RR_CHECK_ARG(codes && q_pm1 && out_dist && out_idx && overflow, "null pointer");
   return tc_search(nullptr, (const uint8_t*)codes, n, dim, tags, tag_mask, tag_value, q_pm1, q, k, row_base, 1,
-                   out_dist, (long long*)out_idx, overflow, workspace, workspace_bytes, (cudaStream_t)stream);
+                   out_dist, (long long*)out_idx, overflow, overflow_flags, workspace, workspace_bytes,
+                   (cudaStream_t)stream);
 }
 
 extern "C" int rr_int8_search_topk_tc(const int8_t* emb, int64_t n, int32_t dim, const uint8_t* tags,
                                       uint8_t tag_mask, uint8_t tag_value, const int8_t* queries_i8, int32_t q,
                                       int32_t top_k, int64_t row_base, int32_t* out_score, int64_t* out_idx,
-                                      uint32_t* overflow, void* workspace, size_t workspace_bytes,
-                                      void* stream) {
+                                      uint32_t* overflow, uint8_t* overflow_flags, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
   int rc = tc_check(n, dim, q, top_k);
   if (rc != RR_OK) return rc;
   RR_CHECK_ARG(emb && queries_i8 && out_score && out_idx && overflow, "null pointer");
   return tc_search(emb, nullptr, n, dim, tags, tag_mask, tag_value, queries_i8, q, top_k, row_base, 0, out_score,
-                   (long long*)out_idx, overflow, workspace, workspace_bytes, (cudaStream_t)stream);
+                   (long long*)out_idx, overflow, overflow_flags, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 // Debug / test entry: raw tensor-core scores of every row as order-preserving keys

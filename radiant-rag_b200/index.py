@@ -127,6 +127,7 @@ class DenseIndex:
         self.use_tensor_cores = True   # batched stage 1 on tcgen05 (rr_hamming_topk_tc)
         self.tc_min_queries = 16       # below this the POPC scan (memory-bound) is the faster path
         self._tc_overflow: Optional[torch.Tensor] = None
+        self.last_tc_redone = 0        # queries the last checked tensor-core call redid on the exact path
         self.ranges: Optional[torch.Tensor] = None
         if int8_ranges is not None:
             self.set_int8_ranges(int8_ranges)
@@ -329,9 +330,10 @@ class DenseIndex:
 
     def _hamming_topk_tc(self, qcodes: torch.Tensor, k: int, tag_mask: int, tag_value: int,
                          ovf: Optional[torch.Tensor] = None
-                         ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Tensor-core path; also returns the device overflow counter of this call (`ovf`: an
-        existing counter the kernel adds to, instead of a fresh zeroed one)."""
+                         ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Tensor-core path -> (dist, idx, ovf, flags): the device overflow counter of this call
+        (`ovf`: an existing counter the kernel adds to, instead of a fresh zeroed one) and one flag
+        per query whose bounded candidate list overflowed."""
         q = qcodes.shape[0]
         dpad = self.words * 32  # padded width: padding bits are 0 (-1) in rows and queries alike
         q_pm1 = torch.empty((q, dpad), dtype=torch.int8, device=self.device)
@@ -339,6 +341,7 @@ class DenseIndex:
                   _stream())
         dist = torch.empty((q, k), dtype=torch.int32, device=self.device)
         idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        flags = torch.empty((q,), dtype=torch.uint8, device=self.device)
         if ovf is None:
             ovf = torch.zeros(1, dtype=torch.int32, device=self.device)
         lib = _lib.load()
@@ -347,8 +350,8 @@ class DenseIndex:
         tptr, tm, tv = self._tag_args(tag_mask, tag_value)
         _lib.call("rr_hamming_topk_tc", self.codes.data_ptr(), self.n, self.words, tptr, tm, tv,
                   q_pm1.data_ptr(), q, k, self.row_base, dist.data_ptr(), idx.data_ptr(), ovf.data_ptr(),
-                  ws.data_ptr(), ws_bytes, _stream())
-        return dist, idx, ovf
+                  flags.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+        return dist, idx, ovf, flags
 
     def hamming_topk(self, qcodes: torch.Tensor, k: int, tag_mask: int = 0, tag_value: int = 0,
                      use_tc: Optional[bool] = None, check_overflow: bool = True
@@ -358,19 +361,22 @@ class DenseIndex:
         Batches of >= tc_min_queries run on the tensor cores (packed codes expanded on chip
         to a 0/255 u8 operand in tensor memory); both paths return identical results.  The
         tensor-core path keeps, per query, the rows that beat a sampled bound in a bounded list:
-        if a list overflows
-        (adversarial data) the call is redone on the POPC path.  check_overflow=False skips
-        that host-side check (one device sync) and accumulates the counter in
-        ``tc_overflow_total()`` for the caller to verify later."""
-        dist, idx, ovf = self._hamming_topk_auto(qcodes, k, tag_mask, tag_value, use_tc,
-                                                 accumulate=not check_overflow)
+        the queries whose list overflows (clustered rows, selective filters) are redone on the
+        POPC path - only those.  check_overflow=False skips that host-side check (one device
+        sync) and accumulates the counter in ``tc_overflow_total()`` for the caller to verify."""
+        dist, idx, ovf, flags = self._hamming_topk_auto(qcodes, k, tag_mask, tag_value, use_tc,
+                                                        accumulate=not check_overflow)
         if ovf is not None and check_overflow and int(ovf.item()) != 0:
-            return self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
+            bad = torch.nonzero(flags).flatten()
+            self.last_tc_redone = int(bad.numel())
+            d2, i2 = self._hamming_topk_popc(qcodes[bad].contiguous(), k, tag_mask, tag_value)
+            dist[bad] = d2
+            idx[bad] = i2
         return dist, idx
 
     def _hamming_topk_auto(self, qcodes: torch.Tensor, k: int, tag_mask: int, tag_value: int,
                            use_tc: Optional[bool] = None, accumulate: bool = False):
-        """-> (dist, idx, ovf): ovf is the device overflow counter of a tensor-core call, None
+        """-> (dist, idx, ovf, flags): ovf is the device overflow counter of a tensor-core call, None
         when the POPC path ran (always exact).  accumulate: the kernel adds straight into the
         index's running counter (``tc_overflow_total``) - no per-call counter, no extra launches."""
         self._activate()
@@ -379,7 +385,7 @@ class DenseIndex:
             use_tc = self.use_tensor_cores and q >= self.tc_min_queries and self.n >= 4096
         if not use_tc or self.n == 0:
             dist, idx = self._hamming_topk_popc(qcodes, k, tag_mask, tag_value)
-            return dist, idx, None
+            return dist, idx, None, None
         if accumulate:
             if self._tc_overflow is None:
                 self._tc_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -474,22 +480,27 @@ class DenseIndex:
         # Stage 2 is queued behind stage 1 before the tensor-core overflow counter is read, so
         # the (single) host sync of a checked call sits at its end and the GPU never idles
         # between the stages; an overflow (adversarial data) redoes the call on the POPC path.
-        _dist, cand, ovf = self._hamming_topk_auto(qc, candidate_k, tag_mask, tag_value,
-                                                   accumulate=not check_overflow)
+        _dist, cand, ovf, flags = self._hamming_topk_auto(qc, candidate_k, tag_mask, tag_value,
+                                                          accumulate=not check_overflow)
 
-        def stage2(cand_rows):
+        def stage2(q_rows, cand_rows):
             if not use_rescoring:
                 idx = cand_rows[:, :top_k].contiguous()
                 score = torch.ones(idx.shape, dtype=torch.float32, device=self.device)
                 count = (idx >= 0).sum(dim=1).to(torch.int32)
                 return idx, score, count
-            score, idx, count = self.rescore(qf, cand_rows, top_k, min_similarity, prefer_int8)
+            score, idx, count = self.rescore(q_rows, cand_rows, top_k, min_similarity, prefer_int8)
             return idx, score, count
 
-        out = stage2(cand)
+        out = stage2(qf, cand)
         if ovf is not None and check_overflow and int(ovf.item()) != 0:
-            _dist, cand = self._hamming_topk_popc(qc, candidate_k, tag_mask, tag_value)
-            out = stage2(cand)
+            # only the queries whose candidate list overflowed go through the POPC path again
+            bad = torch.nonzero(flags).flatten()
+            self.last_tc_redone = int(bad.numel())
+            _dist, cand_b = self._hamming_topk_popc(qc[bad].contiguous(), candidate_k, tag_mask, tag_value)
+            out_b = stage2(qf[bad].contiguous(), cand_b)
+            for t, tb in zip(out, out_b):
+                t[bad] = tb
         return out
 
     def search_exact(self, queries: ArrayLike, top_k: int, min_similarity: float = 0.0,
@@ -534,20 +545,32 @@ class DenseIndex:
         tptr, tm, tv = self._tag_args(tag_mask, tag_value)
         use_tc = (self.dim % 128 == 0 and 128 <= self.dim <= 1024 and q >= 8 and self.n >= 4096
                   if use_tc is None else use_tc)
-        if use_tc:
-            ovf = torch.zeros(1, dtype=torch.int32, device=self.device)
-            ws_bytes = lib.rr_tc_search_workspace_bytes(self.n, q, top_k)
+        def dp4a(q_rows):
+            qn = q_rows.shape[0]
+            s2 = torch.empty((qn, top_k), dtype=torch.int32, device=self.device)
+            i2 = torch.empty((qn, top_k), dtype=torch.int64, device=self.device)
+            ws_bytes = lib.rr_int8_search_topk_workspace_bytes(self.n, qn, top_k)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-            _lib.call("rr_int8_search_topk_tc", self.int8.data_ptr(), self.n, self.dim, tptr, tm, tv,
-                      qi.data_ptr(), q, top_k, self.row_base, score.data_ptr(), idx.data_ptr(),
-                      ovf.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
-            if int(ovf.item()) == 0:
-                return idx, score
-        ws_bytes = lib.rr_int8_search_topk_workspace_bytes(self.n, q, top_k)
+            _lib.call("rr_int8_search_topk", self.int8.data_ptr(), self.n, self.dim, tptr, tm, tv,
+                      q_rows.data_ptr(), qn, top_k, self.row_base, s2.data_ptr(), i2.data_ptr(),
+                      ws.data_ptr(), ws_bytes, _stream())
+            return i2, s2
+
+        if not use_tc:
+            return dp4a(qi)
+        ovf = torch.zeros(1, dtype=torch.int32, device=self.device)
+        flags = torch.empty((q,), dtype=torch.uint8, device=self.device)
+        ws_bytes = lib.rr_tc_search_workspace_bytes(self.n, q, top_k)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-        _lib.call("rr_int8_search_topk", self.int8.data_ptr(), self.n, self.dim, tptr, tm, tv,
+        _lib.call("rr_int8_search_topk_tc", self.int8.data_ptr(), self.n, self.dim, tptr, tm, tv,
                   qi.data_ptr(), q, top_k, self.row_base, score.data_ptr(), idx.data_ptr(),
-                  ws.data_ptr(), ws_bytes, _stream())
+                  ovf.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+        if int(ovf.item()) != 0:  # redo only the queries whose list overflowed, on the CUDA-core path
+            bad = torch.nonzero(flags).flatten()
+            self.last_tc_redone = int(bad.numel())
+            i2, s2 = dp4a(qi[bad].contiguous())
+            idx[bad] = i2
+            score[bad] = s2
         return idx, score
 
     def quantize_int8_queries(self, queries: ArrayLike) -> torch.Tensor:

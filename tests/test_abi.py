@@ -44,7 +44,7 @@ def test_exports_are_c_linkage(lib):
 
 
 def test_version_and_error_string(lib):
-    assert lib.rr_abi_version() == 1
+    assert lib.rr_abi_version() == 2
     assert isinstance(lib.rr_last_error(), bytes)
 
 

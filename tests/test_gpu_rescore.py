@@ -142,3 +142,52 @@ def test_int8_exact_search_bit_exact(n, dim, nq, k):
     w_ids, w_s = oracle.int8_exact_topk(qs, emb, k)
     assert np.array_equal(ids.cpu().numpy(), w_ids)
     assert np.array_equal(score.cpu().numpy(), w_s)
+
+
+@pytest.mark.parametrize("dim,use_int8,c", [(768, False, 400), (1024, True, 40), (1024, False, 200)])
+def test_bulk_copy_ring_scoring_stress(dim, use_int8, c):
+    """The shared-memory-staged scoring kernel (one elected thread bulk-copies candidate rows into a
+    ring, seven warps consume) at the BASELINE batch shapes: every score equals the correctly
+    rounded oracle value and the register-staged fused kernel bit for bit, on rows spread over a
+    300k-row index (copies complete out of order) with invalid candidates mixed in."""
+    require_gpu()
+    n, nq = 300_000, 1024
+    from radiant_rag_b200 import _lib
+    from radiant_rag_b200.index import DenseIndex, _stream, synth_query_rows_device, synth_rows_device
+    bound = 131070.0 * 2.0 ** -synthetic.value_shift(dim)
+    ranges = np.stack([np.full(dim, -bound, np.float32), np.full(dim, bound, np.float32)])
+    idx = DenseIndex(dim, device=0, store_int8=use_int8, store_f32=not use_int8, int8_ranges=ranges if use_int8 else None,
+                     row_base=1000, capacity=n)
+    for lo in range(0, n, 100_000):
+        idx.add(synth_rows_device(1000 + lo, 100_000, dim, seed=5))
+    queries = synth_query_rows_device(0, nq, dim, seed=5, n_corpus=n)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    cand = torch.randint(0, n, (nq, c), generator=g, device="cuda", dtype=torch.int64) + 1000
+    cand[5, 3] = -1
+    cand[6, :] = -1
+    cand[7, 1] = 999          # not owned by this shard
+    cand[8, 2] = 1000 + n     # not owned either
+    for _ in range(3):
+        ring = idx.score_candidates(queries, cand, prefer_int8=use_int8)
+    # the fused register-staged kernel with top_k = c returns every valid score, sorted
+    f_score = torch.empty((nq, c), dtype=torch.float32, device="cuda")
+    f_idx = torch.empty((nq, c), dtype=torch.int64, device="cuda")
+    f_cnt = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    rows, dt = idx.rescore_source(use_int8)
+    _lib.call("rr_rescore_f32", queries.data_ptr(), nq, dim, rows.data_ptr(), dt, idx.n, idx.row_base, cand.data_ptr(),
+              c, c, float("-inf"), f_score.data_ptr(), f_idx.data_ptr(), f_cnt.data_ptr(), _stream())
+    torch.cuda.synchronize()
+    ring_h, cand_h = ring.cpu().numpy(), cand.cpu().numpy()
+    f_s, f_c = f_score.cpu().numpy(), f_cnt.cpu().numpy()
+    for qi in range(nq):
+        valid = ring_h[qi] != -np.inf
+        local = cand_h[qi] - 1000
+        assert np.array_equal(valid, (cand_h[qi] >= 0) & (local >= 0) & (local < n)), qi
+        assert np.array_equal(np.sort(ring_h[qi][valid])[::-1], f_s[qi, : f_c[qi]]), qi
+    qh = queries.cpu().numpy()
+    for qi in (0, 5, 7, 8, 500, 1023):
+        local = cand_h[qi] - 1000
+        ok = (cand_h[qi] >= 0) & (local >= 0) & (local < n)
+        src = rows[torch.from_numpy(np.where(ok, local, 0)).cuda()].cpu().numpy()
+        want = (src.astype(np.float64) @ qh[qi].astype(np.float64)).astype(np.float32)
+        assert np.array_equal(ring_h[qi][ok], want[ok]), qi

@@ -116,6 +116,36 @@ def test_tc_overflow_falls_back_to_exact_path():
     assert (i.cpu().numpy() == np.arange(10)[None, :]).all() and (d.cpu().numpy() == 0).all()
 
 
+def test_tc_clustered_rows_redo_only_overflowed_queries():
+    """Real embeddings cluster: 4000 near-duplicates stored next to each other (one ingest batch)
+    that the strided sample mostly misses.  The queries aimed at the cluster overflow their
+    candidate lists; a checked call redoes exactly those on the POPC path and every result equals
+    the oracle, while the other queries keep their tensor-core answer."""
+    require_gpu()
+    rng = np.random.default_rng(11)
+    n, dim, nq, k = 300_000, 256, 32, 100
+    corpus = rng.standard_normal((n, dim)).astype(np.float32)
+    center = rng.standard_normal(dim).astype(np.float32)
+    lo = 123_456
+    corpus[lo: lo + 4000] = center + 0.05 * rng.standard_normal((4000, dim)).astype(np.float32)
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    queries[[3, 17, 30]] = center + 0.05 * rng.standard_normal((3, dim)).astype(np.float32)
+    idx = DenseIndex(dim, device=0, store_int8=False, store_f32=False)
+    idx.add(corpus)
+    _qf, qc = idx.quantize_queries(queries)
+    d, i = idx.hamming_topk(qc, k, use_tc=True, check_overflow=True)
+    want_d, want_i = oracle.hamming_topk(oracle.quantize_ubinary(corpus), oracle.quantize_ubinary(queries), k)
+    assert np.array_equal(d.cpu().numpy(), want_d) and np.array_equal(i.cpu().numpy(), want_i)
+    assert idx.last_tc_redone <= 6, idx.last_tc_redone  # the clustered queries, not the whole batch
+    # the two-stage entry point redoes the same queries and still returns the oracle's lists
+    idx2 = DenseIndex(dim, device=0, store_int8=False, store_f32=True)
+    idx2.add(corpus)
+    got_i, got_s, got_c = idx2.search_quantized(queries, 10, rescore_multiplier=10.0, prefer_int8=False)
+    want = oracle.two_stage_search(queries, oracle.quantize_ubinary(corpus), corpus, 10, 10.0, exact=True)
+    for qi, (w_ids, _w_s) in enumerate(want):
+        assert got_i[qi, : int(got_c[qi])].cpu().tolist() == w_ids.tolist(), qi
+
+
 @pytest.mark.parametrize("n,dim,nq,k", [(8000, 1024, 40, 10), (50_000, 256, 130, 100), (4096, 128, 8, 10)])
 def test_tc_int8_exact_search(n, dim, nq, k):
     require_gpu()

@@ -1,0 +1,5 @@
+mkdir -p gpurun_out/r2
+timeout 120 python tools/peak_probe.py gpurun_out/r2/peaks.json > gpurun_out/r2/peaks.log 2>&1; echo probe $?; tail -2 gpurun_out/r2/peaks.log
+cp gpurun_out/r2/peaks.json profiles/r2_peaks.json
+timeout 300 python -m pytest tests/test_gpu_rescore.py tests/test_gpu_bm25_rrf.py -x -q -m gpu > gpurun_out/r2/t_rs.log 2>&1; echo tests $?; tail -15 gpurun_out/r2/t_rs.log
+timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/r2/bench1.json 2> gpurun_out/r2/bench1.err; echo bench $?; tail -5 gpurun_out/r2/bench1.err; cat gpurun_out/r2/bench1.json
