@@ -271,6 +271,40 @@ class Bench:
                 os.dup2(saved, 1)
                 os.close(saved)
         self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+        # candidate exchanges are NCCL calls on the step's own stream, so that a sharded step
+        # (kernels + collectives) replays as ONE CUDA graph
+        self.comm = None
+        if self.world > 1:
+            from radiant_rag_b200.nccl import NcclComm
+            self.comm = NcclComm(self.dev)
+
+    def exchange_us(self, shapes, reps: int = 20) -> float:
+        """Event-timed latency of one step's collectives alone (same payload shapes, this rank)."""
+        if self.comm is None:
+            return 0.0
+        torch = self.torch
+        bufs = []
+        for kind, shape, dtype in shapes:
+            t = torch.zeros(shape, dtype=dtype, device=self.dev)
+            bufs.append((kind, t, torch.empty((self.world,) + tuple(shape), dtype=dtype, device=self.dev)))
+
+        def run():
+            for kind, t, out in bufs:
+                if kind == "all_gather":
+                    self.comm.all_gather(t, out)
+                else:
+                    self.comm.all_reduce(t, "max")
+
+        for _ in range(3):
+            run()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            run()
+        e1.record()
+        self.barrier()
+        return e0.elapsed_time(e1) / reps * 1e3
 
     def barrier(self) -> None:
         self.torch.cuda.synchronize()
@@ -371,7 +405,7 @@ def run_config2(bx: Bench, steps: int, warmup: int) -> dict:
         index.add(synth_rows_device(a, min(125_000, hi - a), dim, seed, bx.dev))
     queries_dev = synth_query_rows_device(0, nq, dim, seed, n, bx.dev)
     queries_host = queries_dev.cpu().pin_memory()
-    search = ShardedDenseSearch(GpuShardOps(index))
+    search = ShardedDenseSearch(GpuShardOps(index), comm=bx.comm)
     out_host = {"idx": torch.empty((nq, top_k), dtype=torch.int64).pin_memory(),
                 "score": torch.empty((nq, top_k), dtype=torch.float32).pin_memory(),
                 "count": torch.empty((nq,), dtype=torch.int32).pin_memory()}
@@ -453,7 +487,7 @@ def run_config4(bx: Bench, steps: int) -> dict:
     for a in range(lo, hi, 250_000):
         index.add(synth_rows_device(a, min(250_000, hi - a), dim, seed, bx.dev))
     q8 = index.quantize_int8_queries(synth_query_rows_device(0, nq, dim, seed, n_total, bx.dev))
-    search = ShardedInt8Search(GpuShardOps(index))
+    search = ShardedInt8Search(GpuShardOps(index), comm=bx.comm)
     out = {}
 
     def step():
@@ -528,7 +562,7 @@ def run_config5(bx: Bench) -> dict:
     queries = synth_query_rows_device(0, nq, dim, seed, n_total, dev)
     qt_np = synthetic.zipf_queries(nq, q_len, v, seed)
     qt = torch.from_numpy(qt_np).to(dev)
-    hybrid = HybridSearch(index, bm, rescore_multiplier=mult, prefer_int8=True)
+    hybrid = HybridSearch(index, bm, rescore_multiplier=mult, prefer_int8=True, comm=bx.comm)
     kw = dict(top_k=top_k, dense_top_k=top_k, bm25_top_k=top_k, rrf_k=60)
     out = {}
 
@@ -687,7 +721,7 @@ def run_gpu_arm(args) -> None:
     qt_host = torch.from_numpy(qt_np).pin_memory()
     torch.cuda.synchronize()
     build_s = time.time() - t_build
-    hybrid = HybridSearch(index, bm, rescore_multiplier=mult, prefer_int8=False)
+    hybrid = HybridSearch(index, bm, rescore_multiplier=mult, prefer_int8=False, comm=bx.comm)
     kw = dict(top_k=top_k, dense_top_k=dense_k, bm25_top_k=bm25_k, rrf_k=rrf_k)
 
     out_host = {"idx": torch.empty((nq, top_k), dtype=torch.int64).pin_memory(),
@@ -695,7 +729,7 @@ def run_gpu_arm(args) -> None:
                 "count": torch.empty((nq,), dtype=torch.int32).pin_memory()}
 
     graphed = None
-    if world == 1 and not args.no_graph:
+    if not args.no_graph:  # at N > 1 the NCCL exchanges are part of the graph (nccl.NcclComm)
         graphed = GraphedHybridSearch(hybrid, nq, dim, q_len, **kw)
         graphed.load(queries_dev, qt_dev)
         torch.cuda.synchronize()
@@ -737,6 +771,8 @@ def run_gpu_arm(args) -> None:
             dist.barrier()
             dist.destroy_process_group()
         raise SystemExit(2)
+    exchange_us = bx.exchange_us([("all_gather", (nq, cand_k), torch.int64), ("all_reduce", (nq, cand_k), torch.float32),
+                                  ("all_gather", (nq, bm25_k), torch.float64), ("all_gather", (nq, bm25_k), torch.int64)])
     res_dev = step_device()
     fused_idx = res_dev.idx.clone()
     dense_idx = res_dev.dense_idx.clone()
@@ -868,11 +904,12 @@ def run_gpu_arm(args) -> None:
                        "rrf_k": rrf_k, "docs_per_gpu": n_local, "parallelism": f"row-sharded x{world}",
                        "postings_per_gpu": bm.n_postings, "index_build_s": round(build_s, 1),
                        "l2": "flushed between timed iterations (256 MB fill)",
-                       "issue": "CUDA graph replay of the step" if graphed is not None else
-                                "eager launches + NCCL exchanges"},
+                       "issue": ("CUDA graph replay of the step" + (" (NCCL exchanges inside the graph)" if world > 1 else ""))
+                                if graphed is not None else "eager launches + NCCL exchanges"},
             "e2e": {"value": nq / (e2e_ms / args.steps * 1e-3), "unit": "queries/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": nq * dim * 4 + nq * q_len * 4, "d2h_bytes_per_step": nq * top_k * 16 + nq * 4},
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "exchange_us": exchange_us,
             "stages_ms": {"dense_top100": dense_ms, "bm25_top100": bm25_ms, "rrf_top10": rrf_ms,
                           "dense_stage1": {"sample_pass": sample_ms, "tau": tau_ms, "filter_pass": filter_ms,
                                            "list_select": select_ms},

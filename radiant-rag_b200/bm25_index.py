@@ -75,17 +75,23 @@ class Bm25DeviceIndex:
     dense float64 columns per tile:
         head_slot     int32 [n_terms]                 slot of a head term, -1 otherwise
         head_imp      f64   [n_tiles, n_head, tile_docs]  impact, 0.0 where the term is absent
+        post_pack     int64 [P]   row-in-tile << 32 | round(impact * 2^fx_shift): what the filter
+                                  pass reads (one 8-byte load per posting, integer accumulation)
+        head_max      f32   [n_head] upper bound of the head term's float32 impact over all rows
     """
 
     FAST_MIN_DOCS = 65_536   # below this the exact kernel alone is as fast (few tiles)
     FAST_MAX_TILE = 1024
+    FAST_MAX_QLEN = 64       # tokens per query the fixed-point filter sums have headroom for
     MAX_HEAD = 32
     MAX_TABLE_BYTES = 8 << 30  # [n_tiles, n_terms+1] int64 offset table
 
     def __init__(self, device: torch.device, n_docs: int, n_terms: int, tile_docs: int,
                  tile_term_ptr: torch.Tensor, post_row: torch.Tensor, post_impact: torch.Tensor,
                  row_base: int = 0, head_slot: Optional[torch.Tensor] = None,
-                 head_imp: Optional[torch.Tensor] = None, fast_ok: bool = False) -> None:
+                 head_imp: Optional[torch.Tensor] = None, fast_ok: bool = False,
+                 post_pack: Optional[torch.Tensor] = None, head_max: Optional[torch.Tensor] = None,
+                 fx_shift: int = 0) -> None:
         if row_base + n_docs >= (1 << 32):
             # the (score, row) merge keys carry rows as 32-bit values (csrc/merge.cuh)
             raise ValueError(f"global rows up to {row_base + n_docs} do not fit the 32-bit row field of the BM25 merge")
@@ -100,6 +106,9 @@ class Bm25DeviceIndex:
         self.row_base = row_base
         self.head_slot = head_slot
         self.head_imp = head_imp
+        self.post_pack = post_pack
+        self.head_max = head_max
+        self.fx_shift = int(fx_shift)
         self.n_head = int(head_imp.shape[1]) if head_imp is not None else 0
         self.fast_ok = bool(fast_ok)
         self.fast_min_docs = self.FAST_MIN_DOCS
@@ -244,8 +253,21 @@ class Bm25DeviceIndex:
             finite = bool(torch.isfinite(post_impact).all().item())
             # float32 filter scores need positive impacts well inside the float32 range
             fast_ok = finite and float(lo) >= 2.0 ** -100 and float(hi) <= 2.0 ** 100
+        post_pack = head_max = None
+        fx_shift = 0
         if fast_ok:
-            n_head = min(int(head_terms), cls.MAX_HEAD, v)
+            # fixed-point scale of the filter's tail sums: 64 tokens of the largest impact stay below 2^30
+            fx_shift = 30 - int(np.ceil(np.log2(float(hi) * cls.FAST_MAX_QLEN)))
+            fast_ok = 8 <= fx_shift <= 60
+        if fast_ok:
+            post_pack = torch.empty(n_post, dtype=torch.int64, device=dev)
+            step = 64_000_000
+            for o in range(0, n_post, step):
+                e = min(n_post, o + step)
+                q_imp = torch.round(post_impact[o:e] * float(2.0 ** fx_shift)).to(torch.int64)
+                post_pack[o:e] = ((post_row[o:e].to(torch.int64) % tile_docs) << 32) | q_imp
+                del q_imp
+            n_head = min(int(head_terms), cls.MAX_HEAD, v, max(0, _lib.load().rr_bm25_fast_max_head(tile_docs)))
             order = torch.argsort(df_dev, descending=True, stable=True)[:n_head]
             order = order[df_dev[order] * 8 >= n]  # dense enough to pay for a column
             n_head = int(order.numel())
@@ -263,12 +285,18 @@ class Bm25DeviceIndex:
                     head_imp.view(-1)[pos] = post_impact[off:off + m][sel]
                     off += m
                     del slot, sel, r64, pos
+                hm64 = head_imp.amax(dim=(0, 2))
+                hm32 = hm64.to(torch.float32)
+                head_max = torch.where(hm32.to(torch.float64) < hm64,
+                                       torch.nextafter(hm32, torch.full_like(hm32, float("inf"))), hm32).contiguous()
             else:
                 head_imp = head_imp[:, :0, :].contiguous()
+                head_max = torch.zeros(1, dtype=torch.float32, device=dev)
         del term_c, tf_c, df_dev
         torch.cuda.current_stream().synchronize()  # temporaries die here
         return cls(dev, n, v, tile_docs, tile_term_ptr, post_row, post_impact, row_base,
-                   head_slot=head_slot, head_imp=head_imp, fast_ok=fast_ok)
+                   head_slot=head_slot, head_imp=head_imp, fast_ok=fast_ok, post_pack=post_pack,
+                   head_max=head_max, fx_shift=fx_shift)
 
     SMEM_BANKS64 = 16  # 8-byte accumulators: 16 bank pairs per half-warp
 
@@ -323,15 +351,17 @@ class Bm25DeviceIndex:
         ws_bytes = lib.rr_bm25_fast_workspace_bytes(self.n_tiles, self.tile_docs, self.n_docs, q, k)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         _lib.call("rr_bm25_topk_fast", self.tile_term_ptr.data_ptr(), self.post_row.data_ptr(),
-                  self.post_impact.data_ptr(), self.head_slot.data_ptr(),
-                  self.head_imp.data_ptr() if self.n_head else None, self.n_head, self.n_tiles,
+                  self.post_impact.data_ptr(), self.post_pack.data_ptr(), self.fx_shift,
+                  self.head_slot.data_ptr(), self.head_imp.data_ptr() if self.n_head else None,
+                  self.head_max.data_ptr(), self.n_head, self.n_tiles,
                   self.tile_docs, self.n_terms, self.n_docs, qt.data_ptr(), q, ql, k, self.row_base,
                   score.data_ptr(), idx.data_ptr(), count.data_ptr(), flags.data_ptr(), counter.data_ptr(),
                   ws.data_ptr(), ws_bytes, _stream())
         return idx, score, count, flags
 
-    def uses_fast_path(self, q: int, k: int) -> bool:
-        return bool(self.fast_ok and self.n_docs >= self.fast_min_docs and q >= 1 and k <= 1000)
+    def uses_fast_path(self, q: int, k: int, q_len: int = 8) -> bool:
+        return bool(self.fast_ok and self.n_docs >= self.fast_min_docs and q >= 1 and k <= 1000
+                    and q_len <= self.FAST_MAX_QLEN)
 
     def search_batch(self, q_terms, k: int, check: bool = True, exact: bool = False
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -351,7 +381,7 @@ class Bm25DeviceIndex:
         if qt.ndim == 1:
             qt = qt[None, :]
         q, ql = qt.shape
-        if exact or ql == 0 or self.n_docs == 0 or not self.uses_fast_path(q, k):
+        if exact or ql == 0 or self.n_docs == 0 or not self.uses_fast_path(q, k, ql):
             return self._search_exact(qt, k)
         if not check:
             if self._inexact is None:

@@ -39,12 +39,17 @@ def _obj_stale(src: Path, obj: Path) -> bool:
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    # kernel-variant experiments: RR_BUILD_TAG=x RR_NVCC_EXTRA="-DRR_BF_WARPS=32" builds
+    # librr_b200_x.so from its own object directory (load it with RR_B200_LIB=...)
     extra = os.environ.get("RR_NVCC_EXTRA", "").split()
-    OBJ_DIR.mkdir(parents=True, exist_ok=True)
+    tag = os.environ.get("RR_BUILD_TAG", "")
+    obj_dir = OBJ_DIR if not tag else OBJ_DIR.parent / f"obj_{tag}"
+    lib_path = LIB_PATH if not tag else PKG_DIR / f"librr_b200_{tag}.so"
+    obj_dir.mkdir(parents=True, exist_ok=True)
     jobs = []
     for s in SOURCES:
-        src, obj = CSRC / s, OBJ_DIR / (s[:-3] + ".o")
-        if force or extra or _obj_stale(src, obj):
+        src, obj = CSRC / s, obj_dir / (s[:-3] + ".o")
+        if force or _obj_stale(src, obj):
             cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
             if verbose:
                 cmd += ["-Xptxas", "-v"]
@@ -65,14 +70,14 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
                 sys.stderr.write(f"--- {name}\n{res.stderr}")
     if failed:
         raise RuntimeError("nvcc failed building librr_b200.so")
-    objs = [OBJ_DIR / (s[:-3] + ".o") for s in SOURCES]
-    if jobs or not LIB_PATH.exists() or any(o.stat().st_mtime > LIB_PATH.stat().st_mtime for o in objs):
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", str(LIB_PATH)] + [str(o) for o in objs]
+    objs = [obj_dir / (s[:-3] + ".o") for s in SOURCES]
+    if jobs or not lib_path.exists() or any(o.stat().st_mtime > lib_path.stat().st_mtime for o in objs):
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", str(lib_path)] + [str(o) for o in objs]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             sys.stderr.write(res.stdout + res.stderr)
             raise RuntimeError("nvcc failed linking librr_b200.so")
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

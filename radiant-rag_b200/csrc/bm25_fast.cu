@@ -11,8 +11,12 @@
 //            with the largest document frequency - most of the posting mass under Zipf) are
 //            staged ONCE per tile into shared memory as float32 columns and then read by every
 //            query that contains them; the sparse "tail" terms of a query are scattered into a
-//            per-warp float32 accumulator with shared-memory atomics.  One warp = one query;
+//            per-warp fixed-point accumulator with shared-memory atomics.  One warp = one query;
 //            the score of a document lives in a register and is only compared with a bound.
+//            When the head terms of a query cannot reach the bound on their own (uq < tau_q, the
+//            usual case: frequent terms carry little idf) the head columns are read only for the
+//            groups of documents whose tail sums come within uq of the bound (MaxScore-style
+//            pruning, but inside a filter whose survivors are verified exactly).
 //            pass 1 (SAMPLE) runs on every s-th tile and keeps one maximum per lane;
 //            tau_q = the k'-th largest of them is a score that >= k' documents reach;
 //            pass 2 (FILTER) keeps the documents with score >= tau_q (about s * k' per query).
@@ -20,31 +24,43 @@
 //            operation order (query-token order, __dadd_rn, impacts as rr_bm25_impacts built
 //            them), exact top-k by (score desc, row asc), score > 0.
 //
-// Exactness.  All impacts are positive, so |A - E| <= eps * E with eps = (q_len + 4) * 2^-24 for
-// the float32 score A and the reference's float64 score E of any document.  A document outside
-// the survivor list has A < tau, hence E < tau * (1 + eps).  If the k-th exact score among the
-// survivors exceeds that, no outside document can enter or tie the top-k and the result is the
-// reference's, bit for bit.  The refine kernel CHECKS this per query (and list overflow); a query
+// Exactness.  All impacts are positive.  Tail impacts enter the filter score as fixed-point integers
+// (round(impact * 2^s), accumulated with native integer shared-memory atomics), head impacts as
+// float32, so |A - E| <= eps * E + eps_abs with eps = (q_len + 4) * 2^-24 and
+// eps_abs = (q_len + 1) * 2^-(s+1) for the filter score A and the reference's float64 score E of any
+// document.  A document outside the survivor list has A < tau, hence E < tau * (1 + eps) + eps_abs.
+// If the k-th exact score among the survivors exceeds that, no outside document can enter or tie
+// the top-k and the result is the reference's, bit for bit.  The refine kernel CHECKS this per query (and list overflow); a query
 // that fails is flagged and counted, and the caller redoes it with rr_bm25_topk.  Impacts
 // outside [2^-100, 2^100] or non-positive disable this path at index build time (bm25_index.py).
 //
 // Algorithmic bytes per batch: one pass over the index (postings * 12 B + head columns); per
 // query without sharing: sum_t df(t) * 12 B (SURVEY.md 8d reports both).
+#include <math.h>
+
 #include "common.cuh"
 #include "select.cuh"
+#include "tau.cuh"
 
 namespace rr {
 
-constexpr int BF_WARPS = 16;
+#ifndef RR_BF_WARPS
+#define RR_BF_WARPS 24
+#endif
+constexpr int BF_WARPS = RR_BF_WARPS;  // one query per warp; more resident warps = more posting loads in flight
 constexpr int BF_THREADS = BF_WARPS * 32;
 constexpr int BF_MAX_HEAD = 32;
 constexpr int BF_MAX_TILE = 1024;
-constexpr int BF_ROWS4 = BF_MAX_TILE / 128;  // float4 groups a lane owns in a 1024-doc tile
+#ifndef RR_BF_INFLIGHT
+#define RR_BF_INFLIGHT 12
+#endif
+constexpr int BF_INFLIGHT = RR_BF_INFLIGHT;   // posting loads a lane issues before its first accumulate
 
 struct BfArgs {
   const long long* tile_term_ptr;  // [n_tiles][n_terms + 1]
-  const u32* post_row;
-  const double* post_impact;
+  const u64* post_pack;     // [P] row-in-tile << 32 | round(impact * 2^fx_shift) (same order as post_row)
+  const float* head_max;    // [n_head] largest float32 impact of the head term over all documents
+  float fx_inv;             // 2^-fx_shift
   const int* head_slot;    // [n_terms] slot of a head term, -1 for tail terms
   const double* head_imp;  // [n_tiles][n_head][tile_docs] dense float64 impacts, 0 = absent
   int n_head;
@@ -57,7 +73,7 @@ struct BfArgs {
   int q_len;
   int stride;        // this pass visits tiles 0, stride, 2*stride, ...
   int n_pass_tiles;
-  float* lane_max;   // SAMPLE out: [q][n_pass_tiles * 32]
+  u32* lane_max;     // SAMPLE out: [q][n_pass_tiles * 32] keys ~orderable(max), 0xFFFFFFFF = none
   const float* tau;  // FILTER in:  [q]
   u32* list_cnt;     // FILTER out: [q]
   u64* list;         // FILTER out: [q][cap]  float bits << 32 | local row
@@ -89,17 +105,25 @@ __device__ __forceinline__ TokenInfo bf_token_info(const BfArgs& a, const long l
   return ti;
 }
 
+__device__ __forceinline__ float bf_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 template <bool SAMPLE>
 __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a) {
   extern __shared__ __align__(16) unsigned char bf_smem[];
   const int T = a.tile_docs;
-  float* cols = reinterpret_cast<float*>(bf_smem);       // [n_head][T]
-  float* tacc_all = cols + (size_t)a.n_head * T;         // [BF_WARPS][T]
-  __shared__ int s_excl[BF_WARPS][33];
-  __shared__ long long s_lo[BF_WARPS][32];
+  float* cols = reinterpret_cast<float*>(bf_smem);                           // [n_head][T]
+  u32* tacc_all = reinterpret_cast<u32*>(cols + (size_t)a.n_head * T);       // [BF_WARPS][T] fixed-point tail sums
+  __shared__ int s_excl[BF_WARPS][34];         // compacted tail tokens: first flat index, then 2 sentinels
+  __shared__ long long s_base[BF_WARPS][32];   // first posting of the segment minus its first flat index
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* tacc = tacc_all + (size_t)warp * T;
-  const int t4 = T >> 2;  // float4 per column
+  u32* tacc = tacc_all + (size_t)warp * T;
+  const int t4 = T >> 2;  // 16-byte groups per column
+  const float inv = a.fx_inv;
+  const float hmax = (lane < a.n_head) ? __ldg(a.head_max + lane) : 0.0f;
 
   for (int pt = blockIdx.x; pt < a.n_pass_tiles; pt += gridDim.x) {
     const int tile = pt * a.stride;
@@ -143,9 +167,10 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
       float tau = 0.0f;
       if (!SAMPLE) tau = __ldg(a.tau + qi);
 
-      // zero the tail accumulator
-      for (int i = lane; i < t4; i += 32) reinterpret_cast<float4*>(tacc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = lane; i < t4; i += 32) reinterpret_cast<uint4*>(tacc)[i] = make_uint4(0u, 0u, 0u, 0u);
       int head_cnt = 0;  // lane h: multiplicity of head slot h in this query
+      bool sparse = false;
+      float uq = 0.0f;
       __syncwarp();
 
       for (int j0 = 0; j0 < a.q_len; j0 += 32) {
@@ -161,8 +186,21 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
           const int h = __shfl_sync(0xffffffffu, ti.hs, src);
           if (lane == h) ++head_cnt;
         }
-        // tail tokens: all their postings of this tile as ONE flat index space, so that the
-        // loads of different tokens are independent and in flight together
+        if (!SAMPLE && a.q_len <= 32) {
+          // The head terms of a query add at most uq to any document (their largest impact anywhere).
+          // When that alone cannot reach the bound (the usual case: frequent terms carry little
+          // idf), the head columns are only read for the 16-document groups whose tail sums come
+          // within uq of it.
+          uq = bf_warp_sum((float)head_cnt * hmax) * 1.000002f;
+          sparse = tau > 0.0f && uq < tau * 0.999998f;
+        }
+        // tail tokens: all their postings of this tile as ONE flat index space (balanced over the
+        // lanes whatever the segment lengths), walked with a per-lane segment cursor; up to BF_INFLIGHT
+        // independent 8-byte loads per lane are in flight before the first accumulate.  The sums are
+        // fixed-point integers, so the scatter is one native shared-memory atomic per posting.
+        // (Measured alternatives that were slower: float accumulators (a compare-and-swap loop per
+        // posting), atomic-free read-modify-write of one segment per instruction with a warp barrier
+        // in between, and scoring only the documents the tail touches - a third of a tile.)
         int incl = ti.len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -171,125 +209,121 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
         if (total > 0) {
-          s_excl[warp][lane] = incl - ti.len;
-          s_lo[warp][lane] = ti.lo;
+          const unsigned tm = __ballot_sync(0xffffffffu, ti.len > 0);
+          const int nt = __popc(tm);
+          if (ti.len > 0) {
+            const int r = __popc(tm & ((1u << lane) - 1u));
+            s_excl[warp][r] = incl - ti.len;
+            s_base[warp][r] = ti.lo - (long long)(incl - ti.len);
+          }
+          if (lane == 0) {
+            s_excl[warp][nt] = total;
+            s_excl[warp][nt + 1] = 0x7fffffff;
+          }
           __syncwarp();
-          for (int f0 = 0; f0 < total; f0 += 128) {
-            u32 row[4];
-            double imp[4];
+          int j = 0;
+          int nb = s_excl[warp][1];
+          long long base = s_base[warp][0];
+          for (int f0 = lane; f0 < total; f0 += 32 * BF_INFLIGHT) {
+            u64 pk[BF_INFLIGHT];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int f = f0 + u * 32 + lane;
-              row[u] = 0xFFFFFFFFu;
-              imp[u] = 0.0;
+            for (int u = 0; u < BF_INFLIGHT; ++u) {
+              const int f = f0 + 32 * u;
+              pk[u] = ~0ull;
               if (f < total) {
-                int j = 0;  // largest j with s_excl[j] <= f
-#pragma unroll
-                for (int step = 16; step >= 1; step >>= 1)
-                  if (s_excl[warp][j + step] <= f) j += step;
-                const long long p = s_lo[warp][j] + (f - s_excl[warp][j]);
-                row[u] = __ldg(a.post_row + p);
-                imp[u] = __ldg(a.post_impact + p);
+                while (f >= nb) {  // rare: a lane crosses a segment boundary every few postings
+                  ++j;
+                  nb = s_excl[warp][j + 1];
+                  base = s_base[warp][j];
+                }
+                pk[u] = __ldg(a.post_pack + base + f);
               }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (row[u] != 0xFFFFFFFFu) atomicAdd(tacc + (int)((long long)row[u] - tile_lo), (float)imp[u]);
+            for (int u = 0; u < BF_INFLIGHT; ++u)
+              if (pk[u] != ~0ull) atomicAdd(tacc + (int)(pk[u] >> 32), (u32)pk[u]);
           }
           __syncwarp();
         }
       }
       __syncwarp();
 
-      // scores of the 32 documents this lane owns: tail sum + head columns
-      float4 acc[BF_ROWS4];
+      // dense pass: scores of the documents this lane owns (tail sum + head columns), 16 documents
+      // at a time: four float4 accumulators keep the register count low enough for 24 resident warps
+      const unsigned hmask = __ballot_sync(0xffffffffu, head_cnt > 0);
+      float lmax = 0.0f;
+      for (int hb = 0; hb < t4; hb += 128) {
+        float4 acc[4];
 #pragma unroll
-      for (int i = 0; i < BF_ROWS4; ++i) {
-        const int v = i * 32 + lane;
-        acc[i] = (v < t4) ? reinterpret_cast<const float4*>(tacc)[v] : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      unsigned hm = __ballot_sync(0xffffffffu, head_cnt > 0);
-      while (hm) {
-        const int h = __ffs(hm) - 1;
-        hm &= hm - 1;
-        const float c = (float)__shfl_sync(0xffffffffu, head_cnt, h);
-        const float4* cp = reinterpret_cast<const float4*>(cols + (size_t)h * T);
+        for (int i = 0; i < 4; ++i) {
+          const int v = hb + i * 32 + lane;
+          const uint4 tv = (v < t4) ? reinterpret_cast<const uint4*>(tacc)[v] : make_uint4(0u, 0u, 0u, 0u);
+          acc[i] = make_float4(__uint2float_rn(tv.x) * inv, __uint2float_rn(tv.y) * inv, __uint2float_rn(tv.z) * inv,
+                               __uint2float_rn(tv.w) * inv);
+        }
+        unsigned hm = hmask;
+        if (!SAMPLE && sparse) {
+          float mx = 0.0f;
 #pragma unroll
-        for (int i = 0; i < BF_ROWS4; ++i) {
-          const int v = i * 32 + lane;
-          if (v < t4) {
-            const float4 x = cp[v];
-            acc[i].x = fmaf(c, x.x, acc[i].x);
-            acc[i].y = fmaf(c, x.y, acc[i].y);
-            acc[i].z = fmaf(c, x.z, acc[i].z);
-            acc[i].w = fmaf(c, x.w, acc[i].w);
+          for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fmaxf(acc[i].x, acc[i].y), fmaxf(acc[i].z, acc[i].w)));
+          if (!__any_sync(0xffffffffu, mx + uq >= tau * 0.999998f)) continue;  // no document of this group can survive
+        }
+        while (hm) {
+          const int h = __ffs(hm) - 1;
+          hm &= hm - 1;
+          const float c = (float)__shfl_sync(0xffffffffu, head_cnt, h);
+          const float4* cp = reinterpret_cast<const float4*>(cols + (size_t)h * T) + hb + lane;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (hb + i * 32 + lane < t4) {
+              const float4 x = cp[i * 32];
+              acc[i].x = fmaf(c, x.x, acc[i].x);
+              acc[i].y = fmaf(c, x.y, acc[i].y);
+              acc[i].z = fmaf(c, x.z, acc[i].z);
+              acc[i].w = fmaf(c, x.w, acc[i].w);
+            }
           }
         }
-      }
-
-      if (SAMPLE) {
-        float m = 0.0f;
+        if (SAMPLE) {
 #pragma unroll
-        for (int i = 0; i < BF_ROWS4; ++i) {
-          const int d = (i * 32 + lane) * 4;
-          if (d + 0 < rows_here) m = fmaxf(m, acc[i].x);
-          if (d + 1 < rows_here) m = fmaxf(m, acc[i].y);
-          if (d + 2 < rows_here) m = fmaxf(m, acc[i].z);
-          if (d + 3 < rows_here) m = fmaxf(m, acc[i].w);
-        }
-        a.lane_max[(size_t)qi * ((size_t)a.n_pass_tiles * 32) + (size_t)pt * 32 + lane] = m;
-      } else {
-        bool any = false;
+          for (int i = 0; i < 4; ++i) {
+            const int d = (hb + i * 32 + lane) * 4;
+            if (d + 0 < rows_here) lmax = fmaxf(lmax, acc[i].x);
+            if (d + 1 < rows_here) lmax = fmaxf(lmax, acc[i].y);
+            if (d + 2 < rows_here) lmax = fmaxf(lmax, acc[i].z);
+            if (d + 3 < rows_here) lmax = fmaxf(lmax, acc[i].w);
+          }
+        } else {
+          bool any = false;
 #pragma unroll
-        for (int i = 0; i < BF_ROWS4; ++i) {
-          const float mx = fmaxf(fmaxf(acc[i].x, acc[i].y), fmaxf(acc[i].z, acc[i].w));
-          any |= (mx >= tau) && (mx > 0.0f);
-        }
-        if (any) {  // rare: about s * k' survivors per query over the whole corpus
+          for (int i = 0; i < 4; ++i) {
+            const float mx = fmaxf(fmaxf(acc[i].x, acc[i].y), fmaxf(acc[i].z, acc[i].w));
+            any |= (mx >= tau) && (mx > 0.0f);
+          }
+          if (any) {  // rare: about s * k' survivors per query over the whole corpus
 #pragma unroll
-          for (int i = 0; i < BF_ROWS4; ++i) {
-            const int d = (i * 32 + lane) * 4;
-            const float v4[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+            for (int i = 0; i < 4; ++i) {
+              const int d = (hb + i * 32 + lane) * 4;
+              const float v4[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (v4[e] >= tau && v4[e] > 0.0f && d + e < rows_here) {
-                const u32 slot = atomicAdd(a.list_cnt + qi, 1u);
-                if (slot < (u32)a.cap)
-                  a.list[(size_t)qi * a.cap + slot] =
-                      ((u64)__float_as_uint(v4[e]) << 32) | (u64)(u32)(tile_lo + d + e);
+              for (int e = 0; e < 4; ++e) {
+                if (v4[e] >= tau && v4[e] > 0.0f && d + e < rows_here) {
+                  const u32 slot = atomicAdd(a.list_cnt + qi, 1u);
+                  if (slot < (u32)a.cap)
+                    a.list[(size_t)qi * a.cap + slot] =
+                        ((u64)__float_as_uint(v4[e]) << 32) | (u64)(u32)(tile_lo + d + e);
+                }
               }
             }
           }
         }
       }
-      __syncwarp();  // tacc is re-zeroed by the next query
+      if (SAMPLE)
+        a.lane_max[(size_t)qi * ((size_t)a.n_pass_tiles * 32) + (size_t)pt * 32 + lane] =
+            lmax > 0.0f ? ~f32_orderable(lmax) : 0xFFFFFFFFu;
+      __syncwarp();  // the accumulator is re-zeroed by the next query
     }
   }
-}
-
-// tau_q = the kp-th largest per-lane maximum of the sampled tiles (0 = no bound).
-struct BtArgs {
-  const float* lane_max;  // [q][m]
-  long long m;
-  int kp;
-  int cap;
-  float* tau;
-};
-
-__global__ void __launch_bounds__(256) bm25_tau_kernel(const BtArgs a) {
-  extern __shared__ __align__(16) unsigned char bt_smem[];
-  u64* s_k1 = reinterpret_cast<u64*>(bt_smem);
-  u32* s_k2 = reinterpret_cast<u32*>(s_k1 + a.cap);
-  __shared__ SelectScratch<256> sc;
-  const int q = blockIdx.x;
-  const float* v = a.lane_max + (size_t)q * a.m;
-  auto get = [&](long long i, u64& x, u32& y) {
-    const float s = v[i];
-    x = (s > 0.0f) ? (u64)(~f32_orderable(s)) : K1_INVALID;
-    y = (u32)i;
-  };
-  const int got = block_select_sorted<256, true>(get, a.m, a.kp, s_k1, s_k2, a.cap, sc);
-  if (threadIdx.x == 0) a.tau[q] = (got == a.kp) ? f32_from_orderable((u32)(~s_k1[a.kp - 1])) : 0.0f;
 }
 
 struct BrArgs {
@@ -307,11 +341,12 @@ struct BrArgs {
   const u64* list;
   int cap;
   const float* tau;
-  double* escore;  // [q][cap] workspace
   int k;
   int sel_cap;
+  int chunk;  // candidates whose per-token impacts are staged together
   long long row_base;
-  double eps;
+  double eps;      // relative error bound of a filter score
+  double eps_abs;  // absolute error bound (fixed-point tail sums)
   double* out_score;
   long long* out_idx;
   int* out_count;
@@ -319,17 +354,32 @@ struct BrArgs {
   u32* counter;
 };
 
-__global__ void __launch_bounds__(256) bm25_refine_kernel(const BrArgs a) {
+constexpr int BR_THREADS = 256;
+constexpr int BR_CAND_CAP = 2048;  // exact-scored candidates per query
+
+// Phase B.  The survivor list of a query holds every document with float32 score A >= tau_q
+// (about s * k' of them).  Only those that can still reach the top-k are scored exactly:
+//   A_k   = k-th largest A among the survivors;  candidates C = { A >= thr },
+//   thr   = A_k * (1 - 8 eps) - 4 eps_abs
+// (a survivor below thr has E < thr * (1 + eps) + eps_abs, while the k best-by-A survivors have
+// E >= A_k * (1 - eps) - eps_abs, so it cannot be among the k best exact scores).  Exact scores: one thread
+// per (candidate, query token) fetches the impact - dense head column or a binary search in the
+// (tile, term) segment - and one thread per candidate adds them in query-token order (__dadd_rn).
+__global__ void __launch_bounds__(BR_THREADS) bm25_refine_kernel(const BrArgs a) {
   extern __shared__ __align__(16) unsigned char br_smem[];
-  u64* s_k1 = reinterpret_cast<u64*>(br_smem);
-  u32* s_k2 = reinterpret_cast<u32*>(s_k1 + a.sel_cap);
-  int* s_term = reinterpret_cast<int*>(s_k2 + a.sel_cap);  // [q_len]
-  int* s_hs = s_term + a.q_len;                            // [q_len]
-  __shared__ SelectScratch<256> sc;
+  u64* s_k1 = reinterpret_cast<u64*>(br_smem);                    // [sel_cap]
+  double* s_es = reinterpret_cast<double*>(s_k1 + a.sel_cap);     // [BR_CAND_CAP] exact scores
+  double* s_imp = s_es + BR_CAND_CAP;                             // [chunk][q_len]
+  u32* s_k2 = reinterpret_cast<u32*>(s_imp + (size_t)a.chunk * a.q_len);  // [sel_cap]
+  u32* s_cand = s_k2 + a.sel_cap;                                 // [BR_CAND_CAP] rows
+  int* s_term = reinterpret_cast<int*>(s_cand + BR_CAND_CAP);     // [q_len]
+  int* s_hs = s_term + a.q_len;                                   // [q_len]
+  __shared__ SelectScratch<BR_THREADS> sc;
+  __shared__ int s_nc;
   const int q = blockIdx.x;
   const u32 cnt = a.list_cnt[q];
   const int n_s = (int)min(cnt, (u32)a.cap);
-  for (int j = threadIdx.x; j < a.q_len; j += 256) {
+  for (int j = threadIdx.x; j < a.q_len; j += BR_THREADS) {
     int t = a.q_terms[(size_t)q * a.q_len + j];
     int hs = -1;
     if (t >= 0 && t < a.n_terms) hs = a.head_slot[t];
@@ -337,49 +387,78 @@ __global__ void __launch_bounds__(256) bm25_refine_kernel(const BrArgs a) {
     s_term[j] = t;
     s_hs[j] = hs;
   }
-  __syncthreads();
+  if (threadIdx.x == 0) s_nc = 0;
   const u64* lst = a.list + (size_t)q * a.cap;
-  double* es = a.escore + (size_t)q * a.cap;
+  // ---- k-th largest float32 score among the survivors (positive floats order like their bits)
+  auto get_a = [&](long long i, u64& x, u32& y) {
+    const u64 e = lst[i];
+    x = (u64)(~(u32)(e >> 32));
+    y = (u32)e;
+  };
+  const int m1 = block_select_sorted<BR_THREADS, true>(get_a, n_s, a.k, s_k1, s_k2, a.sel_cap, sc);
+  double thr = 0.0;  // fewer than k survivors: all of them are candidates
+  if (m1 == a.k) {
+    thr = (double)__uint_as_float(~(u32)s_k1[a.k - 1]) * (1.0 - 8.0 * a.eps) - 4.0 * a.eps_abs;
+    if (thr < 0.0) thr = 0.0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_s; i += BR_THREADS) {
+    const u64 e = lst[i];
+    if ((double)__uint_as_float((u32)(e >> 32)) >= thr) {
+      const int slot = atomicAdd(&s_nc, 1);
+      if (slot < BR_CAND_CAP) s_cand[slot] = (u32)e;
+    }
+  }
+  __syncthreads();
+  const int n_c_all = s_nc;
+  const int n_c = min(n_c_all, BR_CAND_CAP);
+  // ---- exact float64 scores of the candidates, `chunk` candidates at a time
   const int T = a.tile_docs;
-  for (int i = threadIdx.x; i < n_s; i += 256) {
-    const u32 row = (u32)lst[i];
-    const int tile = (int)(row / (u32)T);
-    const int r = (int)(row - (u32)tile * (u32)T);
-    const long long* ptr = a.tile_term_ptr + (size_t)tile * (a.n_terms + 1);
-    const double* hcol = a.head_imp + (size_t)tile * a.n_head * T + r;
-    double acc = 0.0;
-    for (int j = 0; j < a.q_len; ++j) {  // query-token order, repeats included
+  for (int c0 = 0; c0 < n_c; c0 += a.chunk) {
+    const int nc = min(a.chunk, n_c - c0);
+    for (int w = threadIdx.x; w < nc * a.q_len; w += BR_THREADS) {
+      const int c = w / a.q_len, j = w - c * a.q_len;
       const int t = s_term[j];
-      if (t < 0) continue;
-      const int hs = s_hs[j];
-      double imp = 0.0;
-      if (hs >= 0) {
-        imp = __ldg(hcol + (size_t)hs * T);  // 0.0 where the document lacks the term: x + 0 = x
-      } else {
-        long long lo = __ldg(ptr + t), hi = __ldg(ptr + t + 1);
-        while (lo < hi) {  // rows ascend inside a (tile, term) segment
-          const long long mid = (lo + hi) >> 1;
-          const u32 rm = __ldg(a.post_row + mid);
-          if (rm < row) lo = mid + 1;
-          else if (rm > row) hi = mid;
-          else {
-            imp = __ldg(a.post_impact + mid);
-            break;
+      double imp = 0.0;  // absent term / unknown token: x + 0.0 == x exactly
+      if (t >= 0) {
+        const u32 row = s_cand[c0 + c];
+        const int tile = (int)(row / (u32)T);
+        const int r = (int)(row - (u32)tile * (u32)T);
+        const int hs = s_hs[j];
+        if (hs >= 0) {
+          imp = __ldg(a.head_imp + ((size_t)tile * a.n_head + hs) * T + r);
+        } else {
+          const long long* ptr = a.tile_term_ptr + (size_t)tile * (a.n_terms + 1);
+          long long lo = __ldg(ptr + t), hi = __ldg(ptr + t + 1);
+          while (lo < hi) {  // rows ascend inside a (tile, term) segment
+            const long long mid = (lo + hi) >> 1;
+            const u32 rm = __ldg(a.post_row + mid);
+            if (rm < row) lo = mid + 1;
+            else if (rm > row) hi = mid;
+            else {
+              imp = __ldg(a.post_impact + mid);
+              break;
+            }
           }
         }
       }
-      acc = __dadd_rn(acc, imp);
+      s_imp[w] = imp;
     }
-    es[i] = acc;
+    __syncthreads();
+    for (int c = threadIdx.x; c < nc; c += BR_THREADS) {
+      double acc = 0.0;
+      for (int j = 0; j < a.q_len; ++j) acc = __dadd_rn(acc, s_imp[c * a.q_len + j]);  // query-token order
+      s_es[c0 + c] = acc;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  auto get = [&](long long i, u64& x, u32& y) {
-    const double s = es[i];
+  auto get_e = [&](long long i, u64& x, u32& y) {
+    const double s = s_es[i];
     x = (s > 0.0) ? ~f64_orderable(s) : K1_INVALID;  // score <= 0 dropped (bm25_index.py:267)
-    y = (u32)lst[i];
+    y = s_cand[i];
   };
-  const int m = block_select_sorted<256, true>(get, n_s, a.k, s_k1, s_k2, a.sel_cap, sc);
-  for (int j = threadIdx.x; j < a.k; j += 256) {
+  const int m = block_select_sorted<BR_THREADS, true>(get_e, n_c, a.k, s_k1, s_k2, a.sel_cap, sc);
+  for (int j = threadIdx.x; j < a.k; j += BR_THREADS) {
     const size_t o = (size_t)q * a.k + j;
     if (j < m) {
       a.out_score[o] = f64_from_orderable(~s_k1[j]);
@@ -391,14 +470,16 @@ __global__ void __launch_bounds__(256) bm25_refine_kernel(const BrArgs a) {
   }
   if (threadIdx.x == 0) {
     if (a.out_count) a.out_count[q] = m;
+    // every document that was NOT scored exactly has E < bound * (1 + eps) + eps_abs
     const double tau = (double)a.tau[q];
-    bool ok = cnt <= (u32)a.cap;
-    if (tau > 0.0) {  // documents below tau were dropped: the k-th exact score must clear it
+    const double bound = thr > tau ? thr : tau;
+    bool ok = cnt <= (u32)a.cap && n_c_all <= BR_CAND_CAP;
+    if (bound > 0.0) {
       if (m < a.k) {
         ok = false;
       } else {
         const double theta = f64_from_orderable(~s_k1[a.k - 1]);
-        if (!(theta * (1.0 - 4.0 * a.eps) > tau)) ok = false;
+        if (!(theta > bound * (1.0 + 2.0 * a.eps) + 2.0 * a.eps_abs)) ok = false;
       }
     }
     if (a.flags) a.flags[q] = ok ? 0 : 1;
@@ -406,6 +487,13 @@ __global__ void __launch_bounds__(256) bm25_refine_kernel(const BrArgs a) {
   }
 }
 
+// head columns + one tail accumulator per warp + the static arrays must fit the 227 KB a CTA may use
+static inline int bf_max_head(int tile_docs) {
+  const long long avail = 232448LL - (long long)BF_WARPS * (34 * 4 + 32 * 8) - 1024 - (long long)BF_WARPS * tile_docs * 4;
+  long long h = avail / ((long long)tile_docs * 4);
+  if (h > BF_MAX_HEAD) h = BF_MAX_HEAD;
+  return h < 0 ? 0 : (int)h;
+}
 static inline int bf_kprime(int k) { return k + k / 4 + 16; }
 static inline int bf_list_cap(int k) {
   int c = 2048;
@@ -426,7 +514,7 @@ static inline int bf_stride(int n_tiles, int tile_docs, long long n_docs, int k)
 }
 
 struct BfLayout {
-  size_t lane_max, tau, list_cnt, list, escore, total;
+  size_t lane_max, tau, list_cnt, list, total;
 };
 static BfLayout bf_layout(int n_tiles, int tile_docs, long long n_docs, int q, int k) {
   BfLayout l;
@@ -441,8 +529,6 @@ static BfLayout bf_layout(int n_tiles, int tile_docs, long long n_docs, int q, i
   l.list_cnt = off;
   off += align_up((size_t)q * 4, 256);
   l.list = off;
-  off += align_up((size_t)q * cap * 8, 256);
-  l.escore = off;
   off += align_up((size_t)q * cap * 8, 256);
   l.total = off + 256;
   return l;
@@ -483,6 +569,11 @@ extern "C" int rr_bm25_last_timing_ms(float* out_ms) {
   return RR_OK;
 }
 
+extern "C" int rr_bm25_fast_max_head(int32_t tile_docs) {
+  if (tile_docs < 128 || tile_docs > BF_MAX_TILE || tile_docs % 128 != 0) return -1;  // tile unsupported
+  return bf_max_head(tile_docs);
+}
+
 extern "C" size_t rr_bm25_fast_workspace_bytes(int32_t n_tiles, int32_t tile_docs, int64_t n_docs,
                                                int32_t q, int32_t k) {
   if (n_tiles <= 0 || q <= 0 || k <= 0 || tile_docs <= 0) return 256;
@@ -490,8 +581,10 @@ extern "C" size_t rr_bm25_fast_workspace_bytes(int32_t n_tiles, int32_t tile_doc
 }
 
 extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* post_row,
-                                 const double* post_impact, const int32_t* head_slot,
-                                 const double* head_imp, int32_t n_head, int32_t n_tiles,
+                                 const double* post_impact, const uint64_t* post_pack,
+                                 int32_t fx_shift, const int32_t* head_slot,
+                                 const double* head_imp, const float* head_max, int32_t n_head,
+                                 int32_t n_tiles,
                                  int32_t tile_docs, int32_t n_terms, int64_t n_docs,
                                  const int32_t* q_terms, int32_t q, int32_t q_len, int32_t k,
                                  int64_t row_base, double* out_score, int64_t* out_idx,
@@ -501,12 +594,14 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   RR_CHECK_ARG(q >= 0 && n_docs > 0 && q_len > 0 && n_tiles > 0 && n_terms > 0, "bad size");
   if (q == 0) return RR_OK;
   RR_CHECK_ARG(out_score && out_idx, "null pointer");
-  RR_CHECK_ARG(tile_term_ptr && post_row && post_impact && head_slot && q_terms, "null pointer");
+  RR_CHECK_ARG(tile_term_ptr && post_row && post_impact && post_pack && head_slot && q_terms, "null pointer");
   RR_CHECK_ARG(k >= 1 && k <= RR_MAX_K, "k out of range");
   RR_CHECK_ARG(tile_docs >= 128 && tile_docs <= BF_MAX_TILE && tile_docs % 128 == 0,
                "tile_docs must be a multiple of 128 in [128, 1024]");
   RR_CHECK_ARG(n_head >= 0 && n_head <= BF_MAX_HEAD, "n_head must be in [0, 32]");
-  RR_CHECK_ARG(n_head == 0 || head_imp, "head_imp is null");
+  RR_CHECK_ARG(n_head == 0 || (head_imp && head_max), "head_imp / head_max is null");
+  RR_CHECK_ARG(fx_shift >= 0 && fx_shift <= 60, "fx_shift out of range");
+  RR_CHECK_ARG(q_len <= 64, "rr_bm25_topk_fast takes at most 64 tokens per query (fixed-point headroom)");
   RR_CHECK_ARG((long long)n_tiles * tile_docs >= n_docs, "tiles do not cover n_docs");
   RR_CHECK_ARG(n_docs < (1LL << 32), "n_docs must be < 2^32");
   const BfLayout l = bf_layout(n_tiles, tile_docs, n_docs, q, k);
@@ -521,8 +616,9 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   const int kp = bf_kprime(k);
   BfArgs a;
   a.tile_term_ptr = (const long long*)tile_term_ptr;
-  a.post_row = post_row;
-  a.post_impact = post_impact;
+  a.post_pack = (const u64*)post_pack;
+  a.head_max = head_max;
+  a.fx_inv = (float)ldexp(1.0, -fx_shift);
   a.head_slot = head_slot;
   a.head_imp = head_imp;
   a.n_head = n_head;
@@ -533,13 +629,13 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   a.q_terms = q_terms;
   a.q = q;
   a.q_len = q_len;
-  a.lane_max = (float*)(ws + l.lane_max);
+  a.lane_max = (u32*)(ws + l.lane_max);
   a.tau = (const float*)(ws + l.tau);
   a.list_cnt = (u32*)(ws + l.list_cnt);
   a.list = (u64*)(ws + l.list);
   a.cap = cap;
   const size_t smem = ((size_t)n_head + BF_WARPS) * tile_docs * 4;
-  RR_CHECK_ARG((int)smem + 8192 <= max_smem_optin(), "tile does not fit shared memory");
+  RR_CHECK_ARG(n_head <= bf_max_head(tile_docs), "too many head columns for this tile size (rr_bm25_fast_max_head)");
   int sms = sm_count();
   if (sms <= 0) sms = 148;
   RR_CUDA(cudaMemsetAsync(ws + l.list_cnt, 0, (size_t)q * 4, st));
@@ -552,16 +648,8 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
     bm25_fast_kernel<true><<<grid, BF_THREADS, smem, st>>>(a);
     RR_LAUNCH_CHECK();
     bf_mark(1, st);
-    BtArgs t;
-    t.lane_max = a.lane_max;
-    t.m = (long long)a.n_pass_tiles * 32;
-    t.kp = kp;
-    t.cap = 4096;
-    while (t.cap < 2 * kp) t.cap <<= 1;
-    t.tau = (float*)(ws + l.tau);
-    const size_t tsm = (size_t)t.cap * 12;
-    RR_CUDA(cudaFuncSetAttribute(bm25_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    bm25_tau_kernel<<<q, 256, tsm, st>>>(t);
+    tau_keys_kernel<true><<<q, TAU_THREADS, 0, st>>>(a.lane_max, (long long)a.n_pass_tiles * 32, kp,
+                                                      (void*)(ws + l.tau));
     RR_LAUNCH_CHECK();
   } else {
     bf_mark(1, st);
@@ -592,22 +680,26 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   r.list = a.list;
   r.cap = cap;
   r.tau = a.tau;
-  r.escore = (double*)(ws + l.escore);
   r.k = k;
   r.sel_cap = 64;
   while (r.sel_cap < 2 * k) r.sel_cap <<= 1;
   if (r.sel_cap > 2048) r.sel_cap = 2048;
   while (r.sel_cap < k) r.sel_cap <<= 1;
+  r.chunk = (int)((32 * 1024) / ((size_t)q_len * 8));
+  if (r.chunk > 256) r.chunk = 256;
+  if (r.chunk < 1) r.chunk = 1;
   r.row_base = row_base;
   r.eps = (double)(q_len + 4) * 5.9604644775390625e-08;  // (q_len + 4) * 2^-24
+  r.eps_abs = (double)(q_len + 1) * ldexp(1.0, -(fx_shift + 1));
   r.out_score = out_score;
   r.out_idx = (long long*)out_idx;
   r.out_count = out_count;
   r.flags = inexact_flags;
   r.counter = inexact_counter;
-  const size_t rsm = (size_t)r.sel_cap * 12 + (size_t)q_len * 8;
+  const size_t rsm = (size_t)r.sel_cap * 12 + (size_t)BR_CAND_CAP * 12 + (size_t)r.chunk * q_len * 8 +
+                     (size_t)q_len * 8 + 16;
   RR_CUDA(cudaFuncSetAttribute(bm25_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-  bm25_refine_kernel<<<q, 256, rsm, st>>>(r);
+  bm25_refine_kernel<<<q, BR_THREADS, rsm, st>>>(r);
   RR_LAUNCH_CHECK();
   bf_mark(4, st);
   g_bf_timed = g_bf_timing && g_bf_ev_ready;

@@ -104,65 +104,40 @@ def _capture(fn: Callable[[], Any], device: torch.device, warmup: int = 3) -> Tu
 
 
 class GraphedShardedSearch(_StagedInput):
-    """The row-sharded two-stage step (sharded.ShardedDenseSearch.search_quantized) with its
-    three compute segments captured as CUDA graphs and the NCCL exchanges issued eagerly
-    between them:
-
-        graph 1  quantise queries, local Hamming top-k', pack (dist, row) into int64 keys
-        NCCL     ONE all_gather of the packed lists
-        graph 2  merge to the global top-k', score the candidates this shard owns
-        NCCL     all_reduce(MAX) of the scores
-        graph 3  rank, cut, filter
-
-    Per step the host issues 3 graph launches and 2 collectives instead of ~25 calls, which
-    is what bounds a sharded step whose GPU time is ~100 us.  Results are identical to the
-    eager path (same kernels, same order)."""
+    """The row-sharded two-stage step (sharded.ShardedDenseSearch.search_quantized) as ONE CUDA graph:
+    quantise, local Hamming top-k', pack, all_gather, merge, score the owned candidates,
+    all_reduce(MAX), rank - kernels and collectives alike.  The collectives are NCCL calls issued on
+    the capturing stream (nccl.NcclComm); per step the host launches one graph instead of ~25 calls,
+    which is what bounds a sharded step whose GPU time is ~100 us.  Results are identical to the
+    eager path (same kernels, same order).  Every rank must replay in lock-step."""
 
     def __init__(self, search: Any, n_queries: int, dim: int, top_k: int, rescore_multiplier: float = 4.0,
                  min_similarity: float = 0.0, prefer_int8: bool = True, tag_mask: int = 0,
                  tag_value: int = 0) -> None:
         import torch.distributed as dist
 
-        ops = search.ops
+        from .nccl import NcclComm
+
+        self.search = search
         self.group = search.group
         self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if self.world < 2:
             raise ValueError("GraphedShardedSearch is for world_size >= 2; use GraphedSearch on one GPU")
-        self.device = torch.device(ops.device)
-        dev = self.device
-        nq = n_queries
-        cand_k = max(1, min(int(top_k * rescore_multiplier), _lib.RR_MAX_K))
-        self.static_in = torch.zeros((nq, dim), dtype=torch.float32, device=dev)
+        self.device = torch.device(search.ops.device)
+        if search.comm is None:
+            search.comm = NcclComm(self.device, self.group)
+        self.static_in = torch.zeros((n_queries, dim), dtype=torch.float32, device=self.device)
 
-        def seg1():
-            qf, qc = ops.quantize_queries(self.static_in)
-            d, i = ops.hamming_topk(qc, cand_k, tag_mask, tag_value, check_overflow=False)
-            return qf, ops.pack_hamming(d, i)  # (dist, row) as one int64 key per entry
+        def step():
+            return search.search_quantized(self.static_in, top_k, rescore_multiplier=rescore_multiplier,
+                                           min_similarity=min_similarity, tag_mask=tag_mask, tag_value=tag_value,
+                                           prefer_int8=prefer_int8, check_overflow=False)
 
-        self.g1, (qf, self.key_loc), k1 = _capture(seg1, dev)
-        self.key_buf = torch.full((self.world, nq, cand_k), -1, dtype=torch.int64, device=dev)
-
-        def seg2():
-            _d, cand = ops.merge_hamming_gathered(self.key_buf, cand_k)  # gathered layout, no transpose
-            return cand, ops.score_candidates(qf, cand, prefer_int8)
-
-        self.g2, (cand, self.scores), k2 = _capture(seg2, dev)
-
-        def seg3():
-            return ops.rank_scored(self.scores, cand, top_k, min_similarity)
-
-        self.g3, self.static_out, k3 = _capture(seg3, dev)
-        self.kernels_per_replay = k1 + k2 + k3
+        self.graph, self.static_out, self.kernels_per_replay = _capture(step, self.device)
         self._init_staging()
 
     def replay(self) -> Any:
-        import torch.distributed as dist
-
-        self.g1.replay()
-        dist.all_gather_into_tensor(self.key_buf, self.key_loc, group=self.group)
-        self.g2.replay()
-        dist.all_reduce(self.scores, op=dist.ReduceOp.MAX, group=self.group)
-        self.g3.replay()
+        self.graph.replay()
         _lib.launch_count += self.kernels_per_replay
         return self.static_out
 

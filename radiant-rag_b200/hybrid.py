@@ -64,7 +64,10 @@ class HybridSearch:
 
     def __init__(self, dense: DenseIndex, bm25: Any, group: Optional[Any] = None,
                  rescore_multiplier: float = 4.0, prefer_int8: bool = True,
-                 dense_mode: str = "quantized") -> None:
+                 dense_mode: str = "quantized", comm: Optional[Any] = None) -> None:
+        """comm: an ``nccl.NcclComm`` over the same ranks - the candidate exchanges are then issued on
+        the current stream, which lets ``GraphedHybridSearch`` capture the WHOLE sharded step (kernels
+        and collectives) into one CUDA graph."""
         if dense_mode not in ("quantized", "exact"):
             raise ValueError("dense_mode must be 'quantized' or 'exact'")
         self.dense_index = dense
@@ -74,9 +77,10 @@ class HybridSearch:
         self.rescore_multiplier = float(rescore_multiplier)
         self.prefer_int8 = bool(prefer_int8)
         self.dense_mode = dense_mode
+        self.comm = comm
         self.ops = GpuShardOps(dense)
-        self.dense = ShardedDenseSearch(self.ops, group)
-        self.sparse = ShardedBM25Search(bm25, self.ops, group)
+        self.dense = ShardedDenseSearch(self.ops, group, comm)
+        self.sparse = ShardedBM25Search(bm25, self.ops, group, comm)
 
     def search_batch(self, queries, q_terms, top_k: int = 10, dense_top_k: int = 100,
                      bm25_top_k: int = 100, rrf_k: float = 60, min_similarity: float = 0.0,
@@ -119,7 +123,9 @@ class HybridSearch:
 
 
 class GraphedHybridSearch:
-    """CUDA-graph replay of one fixed-shape hybrid step on ONE GPU.
+    """CUDA-graph replay of one fixed-shape hybrid step: on ONE GPU, or on a row-sharded corpus when
+    the ``HybridSearch`` was built with an ``NcclComm`` (the exchanges are then part of the graph;
+    every rank must replay in lock-step, as with any collective).
 
         g = GraphedHybridSearch(hybrid, n_queries, dim, q_len, top_k=10, ...)
         res = g(queries_host_pinned, q_terms_host_pinned)      # HybridResult of static tensors
@@ -132,6 +138,8 @@ class GraphedHybridSearch:
         self.hybrid = hybrid
         self.device = hybrid.device
         dev = self.device
+        if hybrid.dense.world() > 1 and hybrid.comm is None:
+            raise ValueError("capturing a sharded step needs HybridSearch(..., comm=NcclComm(...))")
         self.static_q = torch.zeros((n_queries, dim), dtype=torch.float32, device=dev)
         self.static_t = torch.full((n_queries, q_len), -1, dtype=torch.int32, device=dev)
         kwargs = dict(search_kwargs, check=False)

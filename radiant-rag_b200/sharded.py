@@ -113,38 +113,49 @@ class GpuShardOps:
         return out_i, out_s
 
 
-def _gather_raw(t: torch.Tensor, group: Optional[Any]) -> torch.Tensor:
-    """[Q, k] on every rank -> [G, Q, k] on every rank (the collective's native layout)."""
-    world = dist.get_world_size(group)
+def _world(group: Optional[Any]) -> int:
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def _gather_raw(t: torch.Tensor, group: Optional[Any], comm: Optional[Any] = None) -> torch.Tensor:
+    """[Q, k] on every rank -> [G, Q, k] on every rank (the collective's native layout).
+    comm: an ``nccl.NcclComm`` - the collective is then issued on the CURRENT stream (capturable
+    into a CUDA graph) instead of going through torch.distributed's process group."""
+    world = _world(group)
     t = t.contiguous()
     buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-    if t.is_cuda:
+    if comm is not None and t.is_cuda:
+        comm.all_gather(t, buf)
+    elif t.is_cuda:
         dist.all_gather_into_tensor(buf, t, group=group)
     else:  # gloo (CPU tests of the host logic)
         dist.all_gather(list(buf.unbind(0)), t, group=group)
     return buf
 
 
-def _gather_lists(t: torch.Tensor, group: Optional[Any]) -> torch.Tensor:
+def _gather_lists(t: torch.Tensor, group: Optional[Any], comm: Optional[Any] = None) -> torch.Tensor:
     """[Q, k] on every rank -> [Q, G*k] (rank-major within a query) on every rank."""
-    world = dist.get_world_size(group)
+    world = _world(group)
     if world == 1:
         return t
-    t = t.contiguous()
-    buf = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=t.device)
-    if t.is_cuda:
-        dist.all_gather_into_tensor(buf, t, group=group)
-    else:  # gloo (CPU tests of the host logic)
-        dist.all_gather(list(buf.unbind(0)), t, group=group)
+    buf = _gather_raw(t, group, comm)
     return buf.permute(1, 0, 2).reshape(t.shape[0], world * t.shape[1]).contiguous()
+
+
+def _all_reduce_max(t: torch.Tensor, group: Optional[Any], comm: Optional[Any] = None) -> None:
+    if comm is not None and t.is_cuda:
+        comm.all_reduce(t, "max")
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
 
 
 class ShardedDenseSearch:
     """Two-stage quantised retrieval over a row-sharded corpus with single-index results."""
 
-    def __init__(self, ops: Any, group: Optional[Any] = None) -> None:
+    def __init__(self, ops: Any, group: Optional[Any] = None, comm: Optional[Any] = None) -> None:
         self.ops = ops
         self.group = group
+        self.comm = comm  # nccl.NcclComm: collectives on the current stream (CUDA-graph capturable)
 
     def world(self) -> int:
         return dist.get_world_size(self.group) if dist.is_initialized() else 1
@@ -176,11 +187,11 @@ class ShardedDenseSearch:
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world > 1 and hasattr(ops, "pack_hamming"):
             # (dist, row) packed into one int64 key per entry: one collective, merged in place
-            keys_all = _gather_raw(ops.pack_hamming(d_loc, i_loc), self.group)
+            keys_all = _gather_raw(ops.pack_hamming(d_loc, i_loc), self.group, self.comm)
             _d, cand = ops.merge_hamming_gathered(keys_all, candidate_k)
         elif world > 1:
-            d_all = _gather_lists(d_loc, self.group)
-            i_all = _gather_lists(i_loc, self.group)
+            d_all = _gather_lists(d_loc, self.group, self.comm)
+            i_all = _gather_lists(i_loc, self.group, self.comm)
             _d, cand = ops.merge_hamming(d_all, i_all, candidate_k)
         else:
             cand = i_loc
@@ -193,7 +204,7 @@ class ShardedDenseSearch:
         #  which beats the fused one-CTA-per-query score+rank kernel: 0.315 vs 0.331 ms per config-2 step)
         s = ops.score_candidates(qf, cand, prefer_int8)
         if world > 1:
-            dist.all_reduce(s, op=dist.ReduceOp.MAX, group=self.group)
+            _all_reduce_max(s, self.group, self.comm)
         return ops.rank_scored(s, cand, top_k, min_similarity)
 
 
@@ -202,10 +213,11 @@ class ShardedBM25Search:
     double with the same ``search_batch``) built over this rank's documents with the
     GLOBAL idf / avgdl tables and ``row_base`` = first global row of the shard."""
 
-    def __init__(self, local: Any, ops: Any, group: Optional[Any] = None) -> None:
+    def __init__(self, local: Any, ops: Any, group: Optional[Any] = None, comm: Optional[Any] = None) -> None:
         self.local = local
         self.ops = ops
         self.group = group
+        self.comm = comm
 
     def search_batch(self, q_terms, k: int, check: bool = True
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
@@ -214,8 +226,8 @@ class ShardedBM25Search:
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
             return idx, score, count
-        s_all = _gather_lists(score, self.group)
-        i_all = _gather_lists(idx, self.group)
+        s_all = _gather_lists(score, self.group, self.comm)
+        i_all = _gather_lists(idx, self.group, self.comm)
         return self.ops.merge_scores_f64(s_all, i_all, k)
 
 
@@ -224,9 +236,10 @@ class ShardedInt8Search:
     Every rank searches its shard (tensor cores for batches), the per-shard top-k
     (score, global row) lists are all_gathered and merged by (score desc, row asc)."""
 
-    def __init__(self, ops: Any, group: Optional[Any] = None) -> None:
+    def __init__(self, ops: Any, group: Optional[Any] = None, comm: Optional[Any] = None) -> None:
         self.ops = ops
         self.group = group
+        self.comm = comm
 
     def search(self, queries_i8, top_k: int, tag_mask: int = 0, tag_value: int = 0
                ) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -235,6 +248,6 @@ class ShardedInt8Search:
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         if world == 1:
             return idx, score
-        s_all = _gather_lists(score, self.group)
-        i_all = _gather_lists(idx, self.group)
+        s_all = _gather_lists(score, self.group, self.comm)
+        i_all = _gather_lists(idx, self.group, self.comm)
         return self.ops.merge_scores_i32(s_all, i_all, top_k)

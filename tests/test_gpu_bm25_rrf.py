@@ -125,7 +125,7 @@ def test_bm25_long_queries_many_tiles(interleave):
 
 @pytest.mark.parametrize("n_docs,v,tile,k,qlen,mean_len", [
     (150_000, 5000, 1024, 100, 8, 60),   # the production shape of the batched path
-    (40_000, 3000, 256, 5, 70, 40),      # 70-token queries (three token chunks), small k
+    (40_000, 3000, 256, 5, 60, 40),      # 60-token queries (two token chunks), small k
     (40_000, 3000, 128, 300, 40, 40),    # smallest tile, k above many queries' match count
     (9_000, 300, 512, 50, 8, 30),        # tiny vocabulary: most terms are dense head columns
     (3_000, 200, 1024, 20, 6, 30),       # three tiles: the sample pass visits every tile

@@ -306,3 +306,108 @@ def test_wire_format_import_and_index_persistence(tmp_path):
     with pytest.raises(ValueError):
         imp_store.import_quantized_batch([{"doc_id": "d1", "content": "x", "meta": {}, "binary": codes[1].tobytes(),
                                            "int8": i8[1].tobytes(), "embedding": corpus[1]}])
+
+
+def test_upsert_batch_is_all_or_nothing():
+    """A bad document in the middle of a batch leaves the store exactly as it was (ids, rows,
+    documents); afterwards new rows still map to the right doc_ids."""
+    require_gpu()
+    corpus = synthetic.normal_unit_rows(40, 64, seed=6)
+    store = B200VectorStore()
+    store.upsert_batch([{"doc_id": f"d{r}", "content": f"c{r}", "embedding": corpus[r], "meta": {}} for r in range(10)])
+    bad = [{"doc_id": f"d{r}", "content": f"c{r}", "embedding": corpus[r], "meta": {}} for r in range(10, 20)]
+    bad[6]["embedding"] = corpus[16][:32]  # wrong dimension
+    with pytest.raises(ValueError):
+        store.upsert_batch(bad)
+    assert store.list_doc_ids_with_embeddings() == [f"d{r}" for r in range(10)]
+    assert store.index.n == 10 and store.count_documents() == 10 and store.get_doc("d12") is None
+    store.upsert_batch([{"doc_id": f"d{r}", "content": f"c{r}", "embedding": corpus[r], "meta": {}} for r in range(20, 30)])
+    for r in (3, 25):
+        assert store.retrieve_by_embedding(corpus[r].tolist(), 1)[0][0].doc_id == f"d{r}"
+    # the same id twice in one batch: the last one wins, one row
+    store.upsert_batch([{"doc_id": "dup", "content": "a", "embedding": corpus[30], "meta": {}},
+                        {"doc_id": "dup", "content": "b", "embedding": corpus[31], "meta": {}}])
+    assert store.index.n == 21 and store.get_doc("dup").content == "b"
+    assert store.retrieve_by_embedding(corpus[31].tolist(), 1)[0][0].doc_id == "dup"
+    with pytest.raises(ValueError):
+        store.retrieve_by_embedding(corpus[0].tolist(), 5000)  # beyond the per-query result limit: said, not clamped
+
+
+def test_unknown_doc_level_passes_neither_filter():
+    """The reference's filters compare the stored doc_level string (redis_store.py:684, 915-916):
+    a row stored with any other level is returned only without a level filter."""
+    require_gpu()
+    corpus = synthetic.normal_unit_rows(3, 32, seed=8)
+    store = B200VectorStore()
+    for r, level in enumerate(["child", "parent", "section"]):
+        store.upsert(f"d{r}", "x", corpus[r].tolist(), {"doc_level": level})
+    q = corpus[2].tolist()
+    assert [d.doc_id for d, _ in store.retrieve_by_embedding(q, 3, min_similarity=-1.0)][0] == "d2"
+    assert "d2" not in [d.doc_id for d, _ in store.retrieve_by_embedding(q, 3, min_similarity=-1.0, doc_level_filter="child")]
+    assert "d2" not in [d.doc_id for d, _ in store.retrieve_by_embedding(q, 3, min_similarity=-1.0, doc_level_filter="parents")]
+
+
+def test_import_pgvector_bytea_rows():
+    """the reference's pgvector side tables (BYTEA packed bits / int8 rows,
+    pgvector_store.py:322-355) loaded as they are; results equal an index built from the floats."""
+    require_gpu()
+    n, dim = 500, 128
+    corpus = synthetic.normal_unit_rows(n, dim, seed=12)
+    ranges = oracle.calculate_int8_ranges(corpus)
+    codes, i8 = oracle.quantize_ubinary(corpus), oracle.quantize_int8(corpus, ranges)
+    qcfg = QuantizationConfig(enabled=True, precision="both")
+    ref = B200VectorStore(quantization=qcfg, int8_ranges=ranges)
+    ref.upsert_batch([{"doc_id": f"p{r}", "content": f"c{r}", "embedding": corpus[r], "meta": {}} for r in range(n)])
+    store = B200VectorStore(quantization=qcfg, int8_ranges=ranges)
+    doc_rows = [(f"p{r}", f"c{r}", {"doc_level": "child"}, corpus[r].tolist()) for r in range(n)]
+    doc_rows.append(("orphan", "no quantised row", {}, corpus[0].tolist()))  # batch-path document: skipped
+    binary_rows = [(f"p{r}", memoryview(codes[r].tobytes())) for r in range(n)]
+    int8_rows = [(f"p{r}", i8[r].tobytes()) for r in range(n)]
+    assert store.import_pgvector_rows(doc_rows, binary_rows, int8_rows) == n
+    assert torch.equal(store.index.codes[:n], ref.index.codes[:n]) and torch.equal(store.index.int8[:n], ref.index.int8[:n])
+    for qi in (0, 77, 499):
+        a = store.retrieve_by_embedding_quantized(corpus[qi].tolist(), 5)
+        b = ref.retrieve_by_embedding_quantized(corpus[qi].tolist(), 5)
+        assert [(d.doc_id, s) for d, s in a] == [(d.doc_id, s) for d, s in b]
+    with pytest.raises(ValueError):  # a short payload is rejected before anything is stored
+        store.import_quantized_batch([{"doc_id": "x", "content": "", "binary": b"\x00" * 3, "int8": i8[0].tobytes(),
+                                       "embedding": corpus[0]}])
+    assert store.index.n == n and not store.has_embedding("x")
+
+
+def test_batched_retrieval_equals_per_query_agents():
+    """hybrid.BatchedRetrieval (one call per phase for a batch of query strings) == the per-query
+    agent chain, including the fall-through to the non-empty run (app.py:1234-1239) and the
+    orchestrator's first-occurrence merge over sub-queries (orchestrator.py:953-965)."""
+    require_gpu()
+    from radiant_rag_b200.hybrid import BatchedRetrieval
+
+    emb = HashEmbedder(64)
+    store = B200VectorStore()
+    for i, text in enumerate(CORPUS_TEXTS):
+        store.upsert(f"doc{i:03d}", text, emb.embed_single(text), {"doc_level": "parent" if i % 7 == 3 else "child"})
+    bm = PersistentBM25Index(BM25Config(index_path=os.path.join(tempfile.mkdtemp(), "bm25")), store)
+    bm.build_from_store()
+    rcfg = RetrievalConfig(dense_top_k=8, bm25_top_k=8, fused_top_k=6, rrf_k=60)
+    br = BatchedRetrieval(store, bm, emb, rcfg)
+    dense, sparse, rrf = DenseRetrievalAgent(store, emb, rcfg), BM25RetrievalAgent(bm, rcfg), RRFAgent(rcfg)
+    got = br.search_batch(QUERY_TEXTS, mode="hybrid", top_k=5)
+    for qi, query in enumerate(QUERY_TEXTS):
+        d = dense.run(query=query, top_k=5).data
+        s = sparse.run(query=query, top_k=5).data
+        want = rrf.run(runs=[d, s], top_k=5).data[:5] if d and s else (d if d else s)
+        assert [(x.doc_id, v) for x, v in got[qi]] == [(x.doc_id, v) for x, v in want], query
+    assert [[x.doc_id for x, _ in r] for r in br.search_batch(QUERY_TEXTS[:3], mode="bm25", top_k=4)] == \
+        [[x.doc_id for x, _ in sparse.run(query=q, top_k=4).data] for q in QUERY_TEXTS[:3]]
+    # one user query expanded into sub-queries
+    subs = QUERY_TEXTS[:4]
+    d_all, s_all, fused = br.run_retrieval(subs)
+    seen, want_d = set(), []
+    for q in subs:
+        for doc, score in dense.run(query=q).data:
+            if doc.doc_id not in seen:
+                seen.add(doc.doc_id)
+                want_d.append((doc.doc_id, score))
+    assert [(x.doc_id, v) for x, v in d_all] == want_d
+    want_f = rrf.run(runs=[d_all, s_all]).data
+    assert [(x.doc_id, v) for x, v in fused] == [(x.doc_id, v) for x, v in want_f]

@@ -1,0 +1,4 @@
+mkdir -p gpurun_out/r2
+timeout 300 python -m pytest tests/test_gpu_bm25_rrf.py -x -q -m gpu > gpurun_out/r2/t_bm25.log 2>&1; echo tests $?; tail -8 gpurun_out/r2/t_bm25.log
+timeout 200 python tools/bm25_probe.py > gpurun_out/r2/bm25_probe.log 2>&1; echo probe $?; tail -2 gpurun_out/r2/bm25_probe.log
+timeout 300 python -m pytest tests/test_gpu_at_size.py tests/test_gpu_flow.py -x -q -m gpu -k "config3 or flow" > gpurun_out/r2/t_size.log 2>&1; echo size $?; tail -5 gpurun_out/r2/t_size.log
