@@ -255,6 +255,7 @@ class Bench:
         self.windows = []
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
+        self.comm = None
         if self.world > 1:
             # NCCL prints its version banner to stdout on the first communicator; rank 0 must print ONE
             # JSON line, so stdout is pointed at stderr (fd level) until the first collective is done
@@ -266,17 +267,15 @@ class Bench:
                 warm = torch.zeros(1, device=self.dev)
                 dist.all_reduce(warm)
                 torch.cuda.synchronize()
+                # candidate exchanges are NCCL calls on the step's own stream, so that a sharded step
+                # (kernels + collectives) replays as ONE CUDA graph
+                from radiant_rag_b200.nccl import NcclComm
+                self.comm = NcclComm(self.dev)
             finally:
                 sys.stdout.flush()
                 os.dup2(saved, 1)
                 os.close(saved)
         self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
-        # candidate exchanges are NCCL calls on the step's own stream, so that a sharded step
-        # (kernels + collectives) replays as ONE CUDA graph
-        self.comm = None
-        if self.world > 1:
-            from radiant_rag_b200.nccl import NcclComm
-            self.comm = NcclComm(self.dev)
 
     def exchange_us(self, shapes, reps: int = 20) -> float:
         """Event-timed latency of one step's collectives alone (same payload shapes, this rank)."""
@@ -467,7 +466,7 @@ def _gather_obj(bx: Bench, obj):
     return out
 
 
-def run_config4(bx: Bench, steps: int) -> dict:
+def run_config4(bx: Bench, steps: int, n_total: int = 10_000_000) -> dict:
     """BASELINE config 4: 10M x 1024 int8 exact search on the tensor cores, batch 4096, top-10,
     row-sharded over the ranks (local exact top-k -> all_gather -> merge).  Parity: every rank
     scores a sample of the queries against ITS rows with the oracle (exact int32 through float32
@@ -478,7 +477,7 @@ def run_config4(bx: Bench, steps: int) -> dict:
     from radiant_rag_b200.index import DenseIndex, synth_query_rows_device, synth_rows_device
     from radiant_rag_b200.sharded import GpuShardOps, ShardedInt8Search, shard_range
 
-    n_total, nq, dim, seed, top_k = 10_000_000, 4096, 1024, 3, 10
+    nq, dim, seed, top_k = 4096, 1024, 3, 10
     lo, hi = shard_range(n_total, bx.rank, bx.world)
     bound = 131070.0 * 2.0 ** -synthetic.value_shift(dim)
     ranges = np.stack([np.full(dim, -bound, np.float32), np.full(dim, bound, np.float32)])
@@ -525,7 +524,7 @@ def run_config4(bx: Bench, steps: int) -> dict:
     return res
 
 
-def run_config5(bx: Bench) -> dict:
+def run_config5(bx: Bench, n_total: int = 100_000_000) -> dict:
     """BASELINE config 5: 100M x 1024 binary codes + int8 rescore (k' = 40) and BM25 over the same
     100M documents (50k vocabulary, ~200 tokens), fused by RRF, top-10, batch 8192, row-sharded
     over 8 GPUs: the hybrid product call with NCCL exchanges of the per-shard candidates.
@@ -542,7 +541,7 @@ def run_config5(bx: Bench) -> dict:
     from radiant_rag_b200.index import DenseIndex, synth_query_rows_device, synth_rows_device
     from radiant_rag_b200.sharded import shard_range
 
-    n_total, dim, nq, v, mean_len, q_len, seed = 100_000_000, 1024, 8192, 50_000, 200, 8, 4
+    dim, nq, v, mean_len, q_len, seed = 1024, 8192, 50_000, 200, 8, 4
     top_k, mult = 10, 4.0
     dev = bx.dev
     t0 = time.time()
@@ -651,7 +650,7 @@ def run_config5(bx: Bench) -> dict:
             if d:
                 idf[t] = np.log((n_glob - d + 0.5) / (d + 0.5) + 1.0)
         cdf = synthetic.zipf_cdf_u32(v)
-        sub = 1_000_000
+        sub = min(1_000_000, n_total)
         sub_ptr, sub_toks = synth_zipf_corpus_device(sub, v, seed, mean_len, device=bx.local_rank)
         orc_sub = BM25Oracle(sub_ptr.cpu().numpy(), sub_toks.cpu().numpy(), v, 1.5, 0.75, idf=idf, avgdl=avgdl,
                              only_terms=need)
@@ -758,6 +757,14 @@ def run_gpu_arm(args) -> None:
     launches_per_step = (_lib.launch_count - launches0) // (args.steps + args.warmup)
     e2e_ms = bx.timed(step_e2e, args.steps, args.warmup)
     bx.windows.append((w0, time.time()))
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": total_ms / args.steps,
+                              "e2e_ms_per_step": e2e_ms / args.steps, "gpu_launches_per_step": launches_per_step}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     bx.sustain(step_device, total_ms / args.steps)
     # every rank learns about inexact events on ANY rank before anyone decides to stop
     events = bx.sum_over_ranks(hybrid.unchecked_events())
@@ -850,9 +857,9 @@ def run_gpu_arm(args) -> None:
         tensor_peak = pk.get("i8_ts_tops") or 2.0 * pk["bf16_tflops"]
         qt_flat = qt_np.ravel()
         # algorithmic bytes of the BM25 filter pass: ONE pass over the shard's index per batch
-        # (postings 12 B + dense head columns 8 B/doc/term + the offsets the batch touches); without
-        # sharing every query would pull sum_t df(t) * 12 B on its own
-        index_bytes = bm.n_postings * 12 + (bm.head_imp.numel() * 8 if bm.n_head else 0)
+        # (packed postings 8 B + dense head columns 8 B/doc/term); without sharing every query would
+        # pull sum_t df(t) * 12 B on its own (SURVEY.md 8d's per-query figure)
+        index_bytes = bm.n_postings * 8 + (bm.head_imp.numel() * 8 if bm.n_head else 0)
         ttp = bm.tile_term_ptr
         df_local = (ttp[:, 1:] - ttp[:, :-1]).sum(dim=0)
         unshared_bytes = float(df_local[torch.from_numpy(qt_flat[qt_flat >= 0].astype(np.int64)).to(dev)].sum().item()) * 12.0
@@ -869,6 +876,8 @@ def run_gpu_arm(args) -> None:
             "kernel": "bm25_fast_kernel<FILTER> (batched float32 filter pass: dense head columns in shared memory + "
                       "tail postings scattered per query)",
             "bound": "hbm", "achieved": index_bytes / (b_filter * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "limiter": "instruction issue + shared-memory pipe (IPC 2.3 of 4, LSU wavefronts 51 %: "
+                       "profiles/r2_ncu_full_summary.md), not HBM: the batch shares one pass over the index",
             "frac": index_bytes / (b_filter * 1e-3) / 1e9 / pk["hbm_gbs"], "launch_ms": b_filter,
             "share_of_step": b_filter / ms_per_step,
             "traffic": _traffic("bm25_fast_kernel_filter", f"{n_local}x{v}x{nq}"),
@@ -884,7 +893,8 @@ def run_gpu_arm(args) -> None:
                 "achieved_TBs": float(nq) * n_local * (8.0 + 4.0 * 2.65) / (b_filter * 1e-3) / 1e12,
                 "peak_TBs": pk["smem_tbs"], "frac": float(nq) * n_local * (8.0 + 4.0 * 2.65) / (b_filter * 1e-3) / 1e12 / pk["smem_tbs"]}}
         c_bytes = float(nq) * cand_k * dim * 4 + nq * dim * 4
-        rs_roof = {"kernel": "rescore_f32_kernel (candidate row gather)", "bound": "hbm",
+        rs_roof = {"kernel": "rescore_ring_kernel (candidate rows bulk-copied into a shared-memory ring)", "bound": "hbm",
+                   "traffic": _traffic("rescore_ring_kernel_f32", f"{nq}x{cand_k}x{dim}"),
                    "achieved": c_bytes / (rescore_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                    "frac": c_bytes / (rescore_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "launch_ms": rescore_ms,
                    "share_of_step": rescore_ms / ms_per_step, "algorithmic_bytes_per_launch": c_bytes}
@@ -949,6 +959,10 @@ def main() -> None:
     ap.add_argument("--rows", type=int, default=0, help="debug only: override the corpus size")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra BASELINE configs")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling runs (ncu): build, warm up and run the timed steps only, print a short line")
+    ap.add_argument("--debug-extra", default="", help="debug only: run just this extra (config2 | config4 | config5)")
+    ap.add_argument("--debug-rows", type=int, default=0, help="debug only: total rows of the --debug-extra config")
     args = ap.parse_args()
     if args.rows:
         CFG["n"] = args.rows
@@ -956,6 +970,16 @@ def main() -> None:
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.debug_extra:
+        bx = Bench(args)
+        fn = {"config2": lambda: run_config2(bx, 5, 3), "config4": lambda: run_config4(bx, 3, args.debug_rows or 10_000_000),
+              "config5": lambda: run_config5(bx, args.debug_rows or 100_000_000)}[args.debug_extra]
+        res = fn()
+        if bx.rank == 0:
+            print(json.dumps(res), flush=True)
+        if bx.world > 1:
+            bx.dist.barrier()
+            bx.dist.destroy_process_group()
     else:
         run_gpu_arm(args)
 

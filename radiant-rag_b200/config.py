@@ -45,3 +45,38 @@ class RetrievalConfig:
     rrf_k: int = 60
     min_similarity: float = 0.0
     search_scope: str = "leaves"
+
+
+def quantization_from_yaml(source, backend: Optional[str] = None) -> QuantizationConfig:
+    """The ``quantization:`` section the reference's ``load_config`` never reads
+    (radiant/config.py:1179-1228 build Redis/Chroma/PgVector configs without it), as
+    laid out in the reference's ``config_quantization_example.yaml``: one section per backend
+    (``redis:`` / ``chroma:`` / ``pgvector:``), selected by ``storage.backend`` unless `backend` is
+    given.  `source`: a path to the YAML file or the already-parsed mapping.  Unknown keys are
+    ignored, missing ones keep the reference's defaults; ``RADIANT_QUANTIZATION_<KEY>`` environment
+    variables override, in the reference's convention (config.py: RADIANT_<SECTION>_<KEY>)."""
+    import os
+
+    if isinstance(source, (str, os.PathLike)):
+        import yaml
+
+        with open(source, "r", encoding="utf-8") as f:
+            data = yaml.safe_load(f) or {}
+    else:
+        data = dict(source or {})
+    name = backend or (data.get("storage") or {}).get("backend") or "redis"
+    section = ((data.get(name) or {}).get("quantization")) or data.get("quantization") or {}
+    fields = {"enabled": bool, "precision": str, "rescore_multiplier": float, "use_rescoring": bool,
+              "int8_ranges_file": str, "int8_on_disk_only": bool}
+    kwargs = {}
+    for key, typ in fields.items():
+        val = section.get(key)
+        env = os.environ.get(f"RADIANT_QUANTIZATION_{key.upper()}")
+        if env is not None:
+            val = env
+        if val is None:
+            continue
+        if typ is bool and isinstance(val, str):
+            val = val.strip().lower() in ("1", "true", "yes", "on")
+        kwargs[key] = typ(val)
+    return QuantizationConfig(**kwargs)

@@ -61,6 +61,7 @@ struct BfArgs {
   const u64* post_pack;     // [P] row-in-tile << 32 | round(impact * 2^fx_shift) (same order as post_row)
   const float* head_max;    // [n_head] largest float32 impact of the head term over all documents
   float fx_inv;             // 2^-fx_shift
+  float fx_scale;           // 2^fx_shift
   const int* head_slot;    // [n_terms] slot of a head term, -1 for tail terms
   const double* head_imp;  // [n_tiles][n_head][tile_docs] dense float64 impacts, 0 = absent
   int n_head;
@@ -141,6 +142,10 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
     }
     __syncthreads();
     const long long* ptr = a.tile_term_ptr + (size_t)tile * (a.n_terms + 1);
+    // the tail accumulator is zeroed once per tile; every query leaves it clean (its dense pass
+    // writes zeros back behind the values it reads)
+    for (int i = lane; i < t4; i += 32) reinterpret_cast<uint4*>(tacc)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
 
     // software pipeline over this warp's queries: token ids two queries ahead, their head
     // slots / segment bounds one query ahead (a chain of dependent loads otherwise)
@@ -167,11 +172,10 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
       float tau = 0.0f;
       if (!SAMPLE) tau = __ldg(a.tau + qi);
 
-      for (int i = lane; i < t4; i += 32) reinterpret_cast<uint4*>(tacc)[i] = make_uint4(0u, 0u, 0u, 0u);
       int head_cnt = 0;  // lane h: multiplicity of head slot h in this query
       bool sparse = false;
       float uq = 0.0f;
-      __syncwarp();
+      u32 thr_fx = 0u;  // fixed-point tail sum a document needs before its head terms can matter
 
       for (int j0 = 0; j0 < a.q_len; j0 += 32) {
         if (j0 > 0) {  // long queries: later chunks are not prefetched
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
           // within uq of it.
           uq = bf_warp_sum((float)head_cnt * hmax) * 1.000002f;
           sparse = tau > 0.0f && uq < tau * 0.999998f;
+          if (sparse) thr_fx = (u32)fminf((tau * 0.999998f - uq) * a.fx_scale * 0.99999f, 4.0e9f);
         }
         // tail tokens: all their postings of this tile as ONE flat index space (balanced over the
         // lanes whatever the segment lengths), walked with a per-lane segment cursor; up to BF_INFLIGHT
@@ -253,21 +258,30 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
       const unsigned hmask = __ballot_sync(0xffffffffu, head_cnt > 0);
       float lmax = 0.0f;
       for (int hb = 0; hb < t4; hb += 128) {
-        float4 acc[4];
+        uint4 tv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int v = hb + i * 32 + lane;
-          const uint4 tv = (v < t4) ? reinterpret_cast<const uint4*>(tacc)[v] : make_uint4(0u, 0u, 0u, 0u);
-          acc[i] = make_float4(__uint2float_rn(tv.x) * inv, __uint2float_rn(tv.y) * inv, __uint2float_rn(tv.z) * inv,
-                               __uint2float_rn(tv.w) * inv);
+          tv[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (v < t4) {
+            tv[i] = reinterpret_cast<const uint4*>(tacc)[v];
+            reinterpret_cast<uint4*>(tacc)[v] = make_uint4(0u, 0u, 0u, 0u);  // clean for the next query
+          }
         }
         unsigned hm = hmask;
         if (!SAMPLE && sparse) {
-          float mx = 0.0f;
+          // integer test on the raw sums: no document of this group can reach the bound
+          bool hit = false;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fmaxf(acc[i].x, acc[i].y), fmaxf(acc[i].z, acc[i].w)));
-          if (!__any_sync(0xffffffffu, mx + uq >= tau * 0.999998f)) continue;  // no document of this group can survive
+          for (int i = 0; i < 4; ++i)
+            hit |= (tv[i].x >= thr_fx) | (tv[i].y >= thr_fx) | (tv[i].z >= thr_fx) | (tv[i].w >= thr_fx);
+          if (!__any_sync(0xffffffffu, hit)) continue;
         }
+        float4 acc[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          acc[i] = make_float4(__uint2float_rn(tv[i].x) * inv, __uint2float_rn(tv[i].y) * inv,
+                               __uint2float_rn(tv[i].z) * inv, __uint2float_rn(tv[i].w) * inv);
         while (hm) {
           const int h = __ffs(hm) - 1;
           hm &= hm - 1;
@@ -321,7 +335,7 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
       if (SAMPLE)
         a.lane_max[(size_t)qi * ((size_t)a.n_pass_tiles * 32) + (size_t)pt * 32 + lane] =
             lmax > 0.0f ? ~f32_orderable(lmax) : 0xFFFFFFFFu;
-      __syncwarp();  // the accumulator is re-zeroed by the next query
+      __syncwarp();  // the zeros written above are visible to the next query's scatter
     }
   }
 }
@@ -619,6 +633,7 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   a.post_pack = (const u64*)post_pack;
   a.head_max = head_max;
   a.fx_inv = (float)ldexp(1.0, -fx_shift);
+  a.fx_scale = (float)ldexp(1.0, fx_shift);
   a.head_slot = head_slot;
   a.head_imp = head_imp;
   a.n_head = n_head;
@@ -649,7 +664,7 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
     RR_LAUNCH_CHECK();
     bf_mark(1, st);
     tau_keys_kernel<true><<<q, TAU_THREADS, 0, st>>>(a.lane_max, (long long)a.n_pass_tiles * 32, kp,
-                                                      (void*)(ws + l.tau));
+                                                      (void*)(ws + l.tau), 0);
     RR_LAUNCH_CHECK();
   } else {
     bf_mark(1, st);

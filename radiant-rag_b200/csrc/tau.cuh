@@ -22,7 +22,8 @@ __device__ __forceinline__ void tau_store(void* out, int q, u32 key, bool have) 
 // MSB-first byte radix select over the bytes that vary.
 constexpr int TAU_THREADS = 1024;
 template <bool FLOAT_OUT>
-__global__ void __launch_bounds__(TAU_THREADS) tau_keys_kernel(const u32* keys, long long n, int k, void* tau_out) {
+__global__ void __launch_bounds__(TAU_THREADS) tau_keys_kernel(const u32* keys, long long n, int k, void* tau_out,
+                                                                int allow_minima) {
   __shared__ SelectScratch<TAU_THREADS> sc;
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -75,7 +76,9 @@ __global__ void __launch_bounds__(TAU_THREADS) tau_keys_kernel(const u32* keys, 
   // k-th: the k-th smallest of the per-thread minimum keys is one (the k smallest minima
   // belong to k different rows) and costs one ranking of 1024 keys instead of the radix
   // passes; it lets ~10% more rows through the filter pass than the exact k-th would.
-  if (k <= TAU_THREADS / 4) {
+  // (allow_minima = 0: go straight to the exact k-th - cheaper when a thread holds only a few keys,
+  //  as for the BM25 sample: the single-warp bisection below costs more than the radix passes there)
+  if (allow_minima && k <= TAU_THREADS / 4) {
     const u64 bound = block_kth_smallest<TAU_THREADS>(tmin == 0xFFFFFFFFu ? K1_INVALID : (u64)tmin, k - 1, sc.tmin,
                                                        &sc.kth);
     if (bound != K1_INVALID) {

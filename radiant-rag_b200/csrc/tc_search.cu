@@ -863,7 +863,7 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   }
   const int kcap = merge_cap(k);
   tc_mark(1, st);
-  tau_keys_kernel<false><<<q, TAU_THREADS, 0, st>>>(a.dense_keys, p.keys_per_q, k, (void*)(w + p.off_tau));
+  tau_keys_kernel<false><<<q, TAU_THREADS, 0, st>>>(a.dense_keys, p.keys_per_q, k, (void*)(w + p.off_tau), 1);
   RR_LAUNCH_CHECK();
   tc_mark(2, st);
 

@@ -265,3 +265,22 @@ def test_oracle_helpers_for_full_size_checks():
     for i in range(5):
         r1, r2 = full.search(qt[i].tolist(), 20), part.search(qt[i].tolist(), 20)
         assert np.array_equal(r1[0], r2[0]) and np.array_equal(r1[1], r2[1])
+
+
+def test_quantization_section_from_yaml(tmp_path, monkeypatch):
+    """the YAML ``quantization:`` section the reference's loader drops."""
+    from radiant_rag_b200.config import QuantizationConfig, quantization_from_yaml
+
+    p = tmp_path / "config.yaml"
+    p.write_text("storage:\n  backend: chroma\nredis:\n  quantization:\n    enabled: false\n"
+                 "chroma:\n  quantization:\n    enabled: true\n    precision: binary\n    rescore_multiplier: 6.0\n"
+                 "    use_rescoring: false\n    bogus: 1\n")
+    q = quantization_from_yaml(p)
+    assert q == QuantizationConfig(enabled=True, precision="binary", rescore_multiplier=6.0, use_rescoring=False)
+    assert quantization_from_yaml(p, backend="redis").enabled is False
+    assert quantization_from_yaml({}).enabled is False and quantization_from_yaml({}).rescore_multiplier == 4.0
+    monkeypatch.setenv("RADIANT_QUANTIZATION_PRECISION", "int8")
+    assert quantization_from_yaml(p).precision == "int8"
+    import pytest
+    with pytest.raises(ValueError):
+        quantization_from_yaml({"redis": {"quantization": {"rescore_multiplier": 0.5}}})
