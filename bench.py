@@ -565,13 +565,19 @@ def run_config5(bx: Bench, n_total: int = 100_000_000) -> dict:
     kw = dict(top_k=top_k, dense_top_k=top_k, bm25_top_k=top_k, rrf_k=60)
     out = {}
 
-    def step():
-        out["r"] = hybrid.search_batch(queries, qt, check=False, **kw)
+    redone = [0, 0]
 
-    hybrid.reset_unchecked_events()
+    def step():
+        # CHECKED step: flagged BM25 queries / overflowed candidate lists are redone on the exact
+        # paths inside the timed region (one device sync per half), so every result is proven exact
+        out["r"] = hybrid.search_batch(queries, qt, check=True, **kw)
+        redone[0] += index.last_tc_redone
+        redone[1] += bm.last_flagged
+
+    index.last_tc_redone = 0
     total_ms = bx.timed(step, 3, 2)
     ms = total_ms / 3
-    events = bx.sum_over_ranks(hybrid.unchecked_events())
+    events = bx.sum_over_ranks(redone[0] + redone[1])
     res_g = out["r"]
     # per-half times on this rank (each half contains its own collectives)
     d_ms = bx.timed(lambda: hybrid.dense.search_quantized(queries, top_k, rescore_multiplier=mult, check_overflow=False), 2, 1) / 2
@@ -580,7 +586,7 @@ def run_config5(bx: Bench, n_total: int = 100_000_000) -> dict:
                        f"(50k vocab, ~200 tokens) fused by RRF, top-{top_k}, batch {nq}, row-sharded x{bx.world}",
            "ms_per_batch": ms, "value": nq / (ms * 1e-3), "unit": "hybrid queries/s", "rows_per_gpu": n_local,
            "postings_per_gpu": bm.n_postings, "index_build_s": round(build_s, 1),
-           "ms": {"dense_top10": d_ms, "bm25_top10": b_ms}, "unchecked_exactness_events": events,
+           "ms": {"dense_top10": d_ms, "bm25_top10": b_ms}, "queries_redone_on_exact_paths_in_5_steps_all_ranks": events,
            "dense_queries_per_s": nq / (d_ms * 1e-3), "bm25_queries_per_s": nq / (b_ms * 1e-3)}
 
     # ---- parity on a sample

@@ -272,6 +272,12 @@ int rr_merge_hamming_gathered(const int64_t* in_keys, int32_t n_shards, int32_t 
 int rr_merge_scores_f64(const double* in_score, const int64_t* in_idx, int32_t q,
                         int32_t n_in, int32_t k, double* out_score, int64_t* out_idx,
                         int32_t* out_count, void* stream);
+/* One-collective form of the BM25 exchange: every shard writes its lists into ONE buffer of 8-byte
+ * words [2][q][k_in] (plane 0 = float64 scores, plane 1 = global rows, -1 = padding), ONE all_gather
+ * moves it and this merges the gathered [n_shards][2][q][k_in] buffer where it lies. */
+int rr_merge_scores_f64_gathered(const int64_t* in_words, int32_t n_shards, int32_t q, int32_t k_in,
+                                 int32_t k, double* out_score, int64_t* out_idx, int32_t* out_count,
+                                 void* stream);
 /* (score desc, idx asc), int32 scores (config 4) */
 int rr_merge_scores_i32(const int32_t* in_score, const int64_t* in_idx, int32_t q,
                         int32_t n_in, int32_t k, int32_t* out_score, int64_t* out_idx,

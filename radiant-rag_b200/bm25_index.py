@@ -111,6 +111,9 @@ class Bm25DeviceIndex:
         self.fx_shift = int(fx_shift)
         self.n_head = int(head_imp.shape[1]) if head_imp is not None else 0
         self.fast_ok = bool(fast_ok)
+        self.post_term: Optional[torch.Tensor] = None  # int32 [P], kept with keep_structure=True
+        self.post_tf: Optional[torch.Tensor] = None    # int32 [P]
+        self.doc_len: Optional[torch.Tensor] = None    # int32 [n_docs]
         self.fast_min_docs = self.FAST_MIN_DOCS
         self._inexact: Optional[torch.Tensor] = None  # device u32: flagged queries of unchecked calls
         self.last_flagged = 0                          # queries the last checked call had to redo
@@ -138,6 +141,7 @@ class Bm25DeviceIndex:
         sharded: bool = False,
         group: Any = None,
         chunk_docs: int = 2_000_000,
+        keep_structure: bool = False,
     ) -> "Bm25DeviceIndex":
         """doc_ptr int64 [N+1] / doc_terms int32 [T]: the documents of THIS shard as CSR of
         term ids; idf f64 [n_terms] (0 for unknown terms), avgdl, k1, b: global tables
@@ -232,71 +236,106 @@ class Bm25DeviceIndex:
                     d = int(df[t])
                     idf[t] = np.log((n_glob - d + 0.5) / (d + 0.5) + 1.0)
             del df_glob
-        idf_t = to_device(idf, dev, torch.float64)
-        # ---- pass 2: impacts in the reference's operation order, chunk by chunk
-        post_impact = torch.empty(n_post, dtype=torch.float64, device=dev)
-        off = 0
-        for term, tf in zip(term_c, tf_c):
-            m = int(term.numel())
-            post_idf = idf_t[term.to(torch.int64)].contiguous()
-            post_len = dlen[post_row[off:off + m].to(torch.int64)].contiguous()
-            _lib.call("rr_bm25_impacts", tf.data_ptr(), post_len.data_ptr(), post_idf.data_ptr(), m, float(k1),
-                      float(b), float(avgdl), post_impact[off:off + m].data_ptr(), _stream())
-            off += m
-            del post_idf, post_len
-        # ---- head terms: dense float64 columns per tile for the batched path
-        head_slot = head_imp = None
-        fast_ok = False
-        if (not bank_interleave and tile_docs % 128 == 0 and tile_docs <= cls.FAST_MAX_TILE
-                and n < (1 << 32)):
-            lo, hi = torch.aminmax(post_impact)
-            finite = bool(torch.isfinite(post_impact).all().item())
-            # float32 filter scores need positive impacts well inside the float32 range
-            fast_ok = finite and float(lo) >= 2.0 ** -100 and float(hi) <= 2.0 ** 100
-        post_pack = head_max = None
-        fx_shift = 0
-        if fast_ok:
-            # fixed-point scale of the filter's tail sums: 64 tokens of the largest impact stay below 2^30
-            fx_shift = 30 - int(np.ceil(np.log2(float(hi) * cls.FAST_MAX_QLEN)))
-            fast_ok = 8 <= fx_shift <= 60
-        if fast_ok:
-            post_pack = torch.empty(n_post, dtype=torch.int64, device=dev)
-            step = 64_000_000
-            for o in range(0, n_post, step):
-                e = min(n_post, o + step)
-                q_imp = torch.round(post_impact[o:e] * float(2.0 ** fx_shift)).to(torch.int64)
-                post_pack[o:e] = ((post_row[o:e].to(torch.int64) % tile_docs) << 32) | q_imp
-                del q_imp
+        post_term = torch.cat(term_c) if len(term_c) > 1 else term_c[0]
+        post_tf = torch.cat(tf_c) if len(tf_c) > 1 else tf_c[0]
+        del term_c, tf_c
+        inst = cls(dev, n, v, tile_docs, tile_term_ptr, post_row, torch.empty(n_post, dtype=torch.float64, device=dev),
+                   row_base)
+        inst.post_term, inst.post_tf, inst.doc_len = post_term, post_tf, dlen
+        inst._fast_layout = bool(not bank_interleave and tile_docs % 128 == 0 and tile_docs <= cls.FAST_MAX_TILE
+                                 and n < (1 << 32))
+        inst._compute_impacts(idf, float(avgdl), float(k1), float(b))
+        # head terms: the most frequent terms that are dense enough to pay for a column
+        if inst._fast_layout:
             n_head = min(int(head_terms), cls.MAX_HEAD, v, max(0, _lib.load().rr_bm25_fast_max_head(tile_docs)))
             order = torch.argsort(df_dev, descending=True, stable=True)[:n_head]
-            order = order[df_dev[order] * 8 >= n]  # dense enough to pay for a column
-            n_head = int(order.numel())
-            head_slot = torch.full((v,), -1, dtype=torch.int32, device=dev)
-            head_slot[order] = torch.arange(n_head, dtype=torch.int32, device=dev)
-            head_imp = torch.zeros((n_tiles, max(n_head, 1), tile_docs), dtype=torch.float64, device=dev)
-            if n_head:
-                off = 0
-                for term in term_c:
-                    m = int(term.numel())
-                    slot = head_slot[term.to(torch.int64)].to(torch.int64)
-                    sel = torch.nonzero(slot >= 0).flatten()
-                    r64 = post_row[off:off + m][sel].to(torch.int64)
-                    pos = ((r64 // tile_docs) * n_head + slot[sel]) * tile_docs + r64 % tile_docs
-                    head_imp.view(-1)[pos] = post_impact[off:off + m][sel]
-                    off += m
-                    del slot, sel, r64, pos
-                hm64 = head_imp.amax(dim=(0, 2))
-                hm32 = hm64.to(torch.float32)
-                head_max = torch.where(hm32.to(torch.float64) < hm64,
-                                       torch.nextafter(hm32, torch.full_like(hm32, float("inf"))), hm32).contiguous()
-            else:
-                head_imp = head_imp[:, :0, :].contiguous()
-                head_max = torch.zeros(1, dtype=torch.float32, device=dev)
-        del term_c, tf_c, df_dev
+            order = order[df_dev[order] * 8 >= n]
+            inst.head_slot = torch.full((v,), -1, dtype=torch.int32, device=dev)
+            inst.head_slot[order] = torch.arange(int(order.numel()), dtype=torch.int32, device=dev)
+            inst.n_head = int(order.numel())
+        inst._derive_fast()
+        if not keep_structure:  # per-posting term / tf are only needed to refresh the impacts later
+            inst.post_term = inst.post_tf = None
+        del df_dev
         torch.cuda.current_stream().synchronize()  # temporaries die here
-        return cls(dev, n, v, tile_docs, tile_term_ptr, post_row, post_impact, row_base,
-                   head_slot=head_slot, head_imp=head_imp, fast_ok=fast_ok, post_pack=post_pack,
-                   head_max=head_max, fx_shift=fx_shift)
+        return inst
+
+    def _compute_impacts(self, idf, avgdl: float, k1: float, b: float) -> None:
+        """post_impact for every posting in the reference's operation order (rr_bm25_impacts), from
+        the per-posting tf / term / document length and the GIVEN idf table and avgdl."""
+        dev = self.device
+        idf_t = to_device(idf, dev, torch.float64)
+        if idf_t.numel() < self.n_terms:  # tables of a host index that has grown no new terms for these rows
+            idf_t = torch.cat([idf_t, torch.zeros(self.n_terms - idf_t.numel(), dtype=torch.float64, device=dev)])
+        n_post = int(self.post_row.numel())
+        step = 128_000_000
+        for o in range(0, n_post, step):
+            e = min(n_post, o + step)
+            post_idf = idf_t[self.post_term[o:e].to(torch.int64)].contiguous()
+            post_len = self.doc_len[self.post_row[o:e].to(torch.int64)].contiguous()
+            tf = self.post_tf[o:e].contiguous()
+            _lib.call("rr_bm25_impacts", tf.data_ptr(), post_len.data_ptr(), post_idf.data_ptr(), e - o, k1, b, avgdl,
+                      self.post_impact[o:e].data_ptr(), _stream())
+            del post_idf, post_len, tf
+
+    def _derive_fast(self) -> None:
+        """The arrays the batched path reads, derived from post_impact: fixed-point packed postings,
+        dense head columns and their per-term maxima; decides whether the path is usable."""
+        cls = type(self)
+        dev, n_post, tile_docs = self.device, int(self.post_row.numel()), self.tile_docs
+        self.fast_ok = False
+        self.post_pack = self.head_imp = self.head_max = None
+        self.fx_shift = 0
+        if not getattr(self, "_fast_layout", False) or n_post == 0:
+            return
+        lo, hi = torch.aminmax(self.post_impact)
+        finite = bool(torch.isfinite(self.post_impact).all().item())
+        # the filter needs positive impacts well inside the float32 range ...
+        if not (finite and float(lo) >= 2.0 ** -100 and float(hi) <= 2.0 ** 100):
+            return
+        # ... and a fixed-point scale under which 64 tokens of the largest impact stay below 2^30
+        fx_shift = 30 - int(np.ceil(np.log2(float(hi) * cls.FAST_MAX_QLEN)))
+        if not 8 <= fx_shift <= 60:
+            return
+        post_pack = torch.empty(n_post, dtype=torch.int64, device=dev)
+        n_head = self.n_head
+        head_imp = torch.zeros((self.n_tiles, max(n_head, 1), tile_docs), dtype=torch.float64, device=dev)
+        step = 64_000_000
+        for o in range(0, n_post, step):
+            e = min(n_post, o + step)
+            r64 = self.post_row[o:e].to(torch.int64)
+            q_imp = torch.round(self.post_impact[o:e] * float(2.0 ** fx_shift)).to(torch.int64)
+            post_pack[o:e] = ((r64 % tile_docs) << 32) | q_imp
+            del q_imp
+            if n_head:
+                slot = self.head_slot[self.post_term[o:e].to(torch.int64)].to(torch.int64)
+                sel = torch.nonzero(slot >= 0).flatten()
+                rs = r64[sel]
+                pos = ((rs // tile_docs) * n_head + slot[sel]) * tile_docs + rs % tile_docs
+                head_imp.view(-1)[pos] = self.post_impact[o:e][sel]
+                del slot, sel, rs, pos
+            del r64
+        if n_head:
+            hm64 = head_imp.amax(dim=(0, 2))
+            hm32 = hm64.to(torch.float32)
+            head_max = torch.where(hm32.to(torch.float64) < hm64,
+                                   torch.nextafter(hm32, torch.full_like(hm32, float("inf"))), hm32).contiguous()
+        else:
+            head_imp = head_imp[:, :0, :].contiguous()
+            head_max = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.post_pack, self.head_imp, self.head_max, self.fx_shift, self.fast_ok = post_pack, head_imp, head_max, fx_shift, True
+
+    def refresh(self, idf, avgdl: float, k1: float, b: float) -> None:
+        """Re-evaluate every impact from NEW idf / avgdl tables without re-sorting the postings
+        (an ``add_document`` changes avgdl, i.e. every impact, but not the postings of the documents
+        already indexed): O(postings) element-wise work instead of a rebuild.  Needs
+        ``keep_structure=True`` at build time."""
+        if self.post_term is None:
+            raise _lib.RadiantB200Error("this index was built without keep_structure=True: rebuild it instead")
+        if torch.cuda.current_device() != (self.device.index or 0):
+            torch.cuda.set_device(self.device)
+        self._compute_impacts(idf, float(avgdl), float(k1), float(b))
+        self._derive_fast()
 
     SMEM_BANKS64 = 16  # 8-byte accumulators: 16 bank pairs per half-warp
 
@@ -326,10 +365,18 @@ class Bm25DeviceIndex:
         return ukey[order].contiguous(), tf[order].contiguous()
 
     # ---- search ----------------------------------------------------------------------
-    def _search_exact(self, qt: torch.Tensor, k: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    def _out(self, q: int, k: int, out_words: Optional[torch.Tensor]):
+        """Result tensors; with out_words (int64 [2, q, k]) scores and rows are the two planes of ONE
+        buffer, which is what the sharded exchange gathers."""
+        if out_words is None:
+            return (torch.empty((q, k), dtype=torch.float64, device=self.device),
+                    torch.empty((q, k), dtype=torch.int64, device=self.device))
+        return out_words[0].view(torch.float64), out_words[1]
+
+    def _search_exact(self, qt: torch.Tensor, k: int, out_words: Optional[torch.Tensor] = None
+                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         q, ql = qt.shape
-        score = torch.empty((q, k), dtype=torch.float64, device=self.device)
-        idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        score, idx = self._out(q, k, out_words)
         count = torch.empty((q,), dtype=torch.int32, device=self.device)
         lib = _lib.load()
         ws_bytes = lib.rr_bm25_topk_workspace_bytes(self.n_tiles, q, k)
@@ -340,11 +387,11 @@ class Bm25DeviceIndex:
                   count.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
         return idx, score, count
 
-    def _search_fast(self, qt: torch.Tensor, k: int, counter: torch.Tensor
+    def _search_fast(self, qt: torch.Tensor, k: int, counter: torch.Tensor,
+                     out_words: Optional[torch.Tensor] = None
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
         q, ql = qt.shape
-        score = torch.empty((q, k), dtype=torch.float64, device=self.device)
-        idx = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        score, idx = self._out(q, k, out_words)
         count = torch.empty((q,), dtype=torch.int32, device=self.device)
         flags = torch.empty((q,), dtype=torch.uint8, device=self.device)
         lib = _lib.load()
@@ -363,7 +410,18 @@ class Bm25DeviceIndex:
         return bool(self.fast_ok and self.n_docs >= self.fast_min_docs and q >= 1 and k <= 1000
                     and q_len <= self.FAST_MAX_QLEN)
 
-    def search_batch(self, q_terms, k: int, check: bool = True, exact: bool = False
+    def search_batch_into(self, q_terms, k: int, check: bool = True) -> torch.Tensor:
+        """``search_batch`` with scores and rows written into one int64 [2, Q, k] buffer (plane 0 =
+        float64 score bits, plane 1 = global rows): the form the sharded exchange moves in ONE collective."""
+        qt = to_device(q_terms, self.device, torch.int32)
+        if qt.ndim == 1:
+            qt = qt[None, :]
+        words = torch.empty((2, qt.shape[0], k), dtype=torch.int64, device=self.device)
+        self.search_batch(qt, k, check=check, out_words=words)
+        return words
+
+    def search_batch(self, q_terms, k: int, check: bool = True, exact: bool = False,
+                     out_words: Optional[torch.Tensor] = None
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """q_terms int32 [Q, L] term ids in query-token order, -1 = unknown / padding.
         -> (idx int64 [Q,k] (-1 padded), score f64 [Q,k], count int32 [Q]);
@@ -382,14 +440,14 @@ class Bm25DeviceIndex:
             qt = qt[None, :]
         q, ql = qt.shape
         if exact or ql == 0 or self.n_docs == 0 or not self.uses_fast_path(q, k, ql):
-            return self._search_exact(qt, k)
+            return self._search_exact(qt, k, out_words)
         if not check:
             if self._inexact is None:
                 self._inexact = torch.zeros(1, dtype=torch.int32, device=self.device)
-            idx, score, count, _flags = self._search_fast(qt, k, self._inexact)
+            idx, score, count, _flags = self._search_fast(qt, k, self._inexact, out_words)
             return idx, score, count
         counter = torch.zeros(1, dtype=torch.int32, device=self.device)
-        idx, score, count, flags = self._search_fast(qt, k, counter)
+        idx, score, count, flags = self._search_fast(qt, k, counter, out_words)
         self.last_flagged = int(counter.item())
         if self.last_flagged:
             bad = torch.nonzero(flags).flatten()
@@ -473,6 +531,12 @@ class BM25Index:
         self._doc_term_ids: List[np.ndarray] = []
         self._gpu: Optional[Bm25DeviceIndex] = None
         self._gpu_params: Tuple[float, float] = (k1, b)
+        self._gpu_docs = 0              # documents covered by self._gpu
+        self._gpu_version = -1          # host-table version its impacts were computed from
+        self._delta: Optional[Bm25DeviceIndex] = None   # documents added since (rows _gpu_docs ..)
+        self._delta_version = -1
+        self._tables_version = 0
+        self.delta_rebuild_fraction = 0.125   # a delta larger than this share of the main index triggers a rebuild
         for toks in self.doc_tokens:
             self._doc_term_ids.append(self._term_ids(toks, create=True))
         if self.doc_ids and self.needs_rebuild:
@@ -526,7 +590,10 @@ class BM25Index:
             self.term_doc_freqs[t] = d
             self.idf[t] = np.log((n - d + 0.5) / (d + 0.5) + 1.0)
         self.dirty = True
-        self._gpu = None
+        # device side: the postings of the documents already indexed do not change, only their
+        # impacts (avgdl moved, the idf of this document's terms moved): refreshed lazily, the new
+        # documents go to a small delta index - no O(N) rebuild per add
+        self._tables_version += 1
         return True
 
     def remove_document(self, doc_id: str) -> bool:
@@ -546,29 +613,88 @@ class BM25Index:
         return True
 
     # ---- device index ---------------------------------------------------------------
-    def device_index(self) -> Bm25DeviceIndex:
-        """Build (or reuse) the GPU index from the CURRENT host tables."""
-        if self.needs_rebuild:
-            self._rebuild_index()
-        if self._gpu is not None and self._gpu_params == (self.k1, self.b):
-            return self._gpu
-        lens = np.fromiter((a.size for a in self._doc_term_ids), dtype=np.int64,
-                           count=len(self._doc_term_ids))
+    def _csr(self, lo: int, hi: int):
+        docs = self._doc_term_ids[lo:hi]
+        lens = np.fromiter((a.size for a in docs), dtype=np.int64, count=len(docs))
         ptr = np.zeros(lens.size + 1, dtype=np.int64)
         np.cumsum(lens, out=ptr[1:])
-        terms = (np.concatenate(self._doc_term_ids) if self._doc_term_ids
-                 else np.zeros(0, dtype=np.int32))
-        v = len(self._vocab)
+        terms = np.concatenate(docs) if docs else np.zeros(0, dtype=np.int32)
+        return ptr, terms
+
+    def _idf_table(self, v: int) -> np.ndarray:
         idf = np.zeros(v, dtype=np.float64)
         for t, val in self.idf.items():
             tid = self._vocab.get(t)
-            if tid is not None:
+            if tid is not None and tid < v:
                 idf[tid] = float(val)
-        self._gpu = Bm25DeviceIndex.build(
-            ptr, terms, v, idf, float(self.avgdl), float(self.k1), float(self.b), device=self._device,
-            tile_docs=self._tile_docs, doc_len=np.asarray(self.doc_lengths, dtype=np.int32))
-        self._gpu_params = (self.k1, self.b)
-        return self._gpu
+        return idf
+
+    def device_indexes(self) -> Tuple[Bm25DeviceIndex, Optional[Bm25DeviceIndex]]:
+        """(main, delta): the GPU index over rows [0, n_main) and, after incremental adds, a small
+        one over rows [n_main, n) - both with impacts from the CURRENT host tables (idf / avgdl are
+        copied, never recomputed: the reference's stale-idf state is what gets scored).
+
+        A full build sorts every posting (O(N)); an ``add_document`` does not need one: the main
+        index re-evaluates its impacts in place (``refresh``, element-wise) and the new documents are
+        indexed on their own.  Removals, parameter changes and a delta beyond
+        ``delta_rebuild_fraction`` of the main index rebuild."""
+        if self.needs_rebuild:
+            self._rebuild_index()
+        n = len(self.doc_ids)
+        grown = n - self._gpu_docs
+        full = (self._gpu is None or self._gpu_params != (self.k1, self.b) or grown < 0
+                or grown > max(1024, int(self._gpu_docs * self.delta_rebuild_fraction))
+                or self._gpu.post_term is None)
+        if full:
+            ptr, terms = self._csr(0, n)
+            v = len(self._vocab)
+            self._gpu = Bm25DeviceIndex.build(
+                ptr, terms, v, self._idf_table(v), float(self.avgdl), float(self.k1), float(self.b),
+                device=self._device, tile_docs=self._tile_docs,
+                doc_len=np.asarray(self.doc_lengths, dtype=np.int32), keep_structure=True)
+            self._gpu_params = (self.k1, self.b)
+            self._gpu_docs, self._gpu_version = n, self._tables_version
+            self._delta, self._delta_version = None, -1
+            return self._gpu, None
+        if self._gpu_version != self._tables_version:
+            self._gpu.refresh(self._idf_table(self._gpu.n_terms), float(self.avgdl), float(self.k1), float(self.b))
+            self._gpu_version = self._tables_version
+        if grown == 0:
+            self._delta = None
+            return self._gpu, None
+        if self._delta is None or self._delta_version != self._tables_version:
+            ptr, terms = self._csr(self._gpu_docs, n)
+            v = len(self._vocab)
+            self._delta = Bm25DeviceIndex.build(
+                ptr, terms, v, self._idf_table(v), float(self.avgdl), float(self.k1), float(self.b),
+                device=self._device, tile_docs=self._tile_docs, row_base=self._gpu_docs,
+                doc_len=np.asarray(self.doc_lengths[self._gpu_docs:], dtype=np.int32))
+            self._delta_version = self._tables_version
+        return self._gpu, self._delta
+
+    def device_index(self) -> Bm25DeviceIndex:
+        """The GPU index over ALL current documents (forces a full build if a delta is pending)."""
+        main, delta = self.device_indexes()
+        if delta is not None:
+            self._gpu = None
+            main, _ = self.device_indexes()
+        return main
+
+    def _device_search(self, qt: np.ndarray, k: int):
+        main, delta = self.device_indexes()
+        idx, score, count = main.search_batch(qt, k)
+        if delta is None or delta.n_docs == 0:
+            return idx, score, count
+        i2, s2, _c2 = delta.search_batch(qt, k)
+        q = idx.shape[0]
+        out_s = torch.empty((q, k), dtype=torch.float64, device=idx.device)
+        out_i = torch.empty((q, k), dtype=torch.int64, device=idx.device)
+        out_c = torch.empty((q,), dtype=torch.int32, device=idx.device)
+        s_all = torch.cat([score, s2], dim=1).contiguous()
+        i_all = torch.cat([idx, i2], dim=1).contiguous()
+        _lib.call("rr_merge_scores_f64", s_all.data_ptr(), i_all.data_ptr(), q, 2 * k, k, out_s.data_ptr(),
+                  out_i.data_ptr(), out_c.data_ptr(), _stream())
+        return out_i, out_s, out_c
 
     def _query_term_ids(self, query_tokens: Sequence[str]) -> np.ndarray:
         ids = self._term_ids(query_tokens, create=False)
@@ -594,7 +720,7 @@ class BM25Index:
         k = max(1, min(int(top_k), _lib.RR_MAX_K))
         if k != int(top_k):
             logger.warning(f"BM25 top_k={top_k} outside [1, {_lib.RR_MAX_K}]: {k} results per query are returned")
-        idx, score, count = self.device_index().search_batch(qt, k)
+        idx, score, count = self._device_search(qt, k)
         idx_h, score_h, count_h = idx.cpu().tolist(), score.cpu().tolist(), count.cpu().tolist()
         out: List[List[Tuple[str, float]]] = []
         for i in range(nq):

@@ -74,6 +74,7 @@ struct BfArgs {
   int q_len;
   int stride;        // this pass visits tiles 0, stride, 2*stride, ...
   int n_pass_tiles;
+  int q_groups;      // a tile's queries are split over this many work items (small shards: fewer tiles than SMs)
   u32* lane_max;     // SAMPLE out: [q][n_pass_tiles * 32] keys ~orderable(max), 0xFFFFFFFF = none
   const float* tau;  // FILTER in:  [q]
   u32* list_cnt;     // FILTER out: [q]
@@ -126,7 +127,11 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
   const float inv = a.fx_inv;
   const float hmax = (lane < a.n_head) ? __ldg(a.head_max + lane) : 0.0f;
 
-  for (int pt = blockIdx.x; pt < a.n_pass_tiles; pt += gridDim.x) {
+  for (int w = blockIdx.x; w < a.n_pass_tiles * a.q_groups; w += gridDim.x) {
+    const int pt = w / a.q_groups;
+    const int grp = w - pt * a.q_groups;
+    const int q_lo = (int)((long long)a.q * grp / a.q_groups);
+    const int q_hi = (int)((long long)a.q * (grp + 1) / a.q_groups);
     const int tile = pt * a.stride;
     const long long tile_lo = (long long)tile * T;
     const int rows_here = (int)min((long long)T, a.n_docs - tile_lo);
@@ -154,21 +159,21 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
     ti_n1.hs = -1;
     ti_n1.len = 0;
     ti_n1.lo = 0;
-    if (warp < a.q) {
-      t_n1 = (lane < a.q_len) ? __ldg(a.q_terms + (size_t)warp * a.q_len + lane) : -1;
+    if (q_lo + warp < q_hi) {
+      t_n1 = (lane < a.q_len) ? __ldg(a.q_terms + (size_t)(q_lo + warp) * a.q_len + lane) : -1;
       ti_n1 = bf_token_info(a, ptr, t_n1);
     }
-    if (warp + BF_WARPS < a.q)
-      t_n2 = (lane < a.q_len) ? __ldg(a.q_terms + (size_t)(warp + BF_WARPS) * a.q_len + lane) : -1;
+    if (q_lo + warp + BF_WARPS < q_hi)
+      t_n2 = (lane < a.q_len) ? __ldg(a.q_terms + (size_t)(q_lo + warp + BF_WARPS) * a.q_len + lane) : -1;
 
-    for (int qi = warp; qi < a.q; qi += BF_WARPS) {
+    for (int qi = q_lo + warp; qi < q_hi; qi += BF_WARPS) {
       TokenInfo ti = ti_n1;
       const int t_cur_next = t_n2;  // tokens of query qi + BF_WARPS
-      if (qi + 2 * BF_WARPS < a.q)
+      if (qi + 2 * BF_WARPS < q_hi)
         t_n2 = (lane < a.q_len) ? __ldg(a.q_terms + (size_t)(qi + 2 * BF_WARPS) * a.q_len + lane) : -1;
       else
         t_n2 = -1;
-      if (qi + BF_WARPS < a.q) ti_n1 = bf_token_info(a, ptr, t_cur_next);
+      if (qi + BF_WARPS < q_hi) ti_n1 = bf_token_info(a, ptr, t_cur_next);
       float tau = 0.0f;
       if (!SAMPLE) tau = __ldg(a.tau + qi);
 
@@ -508,6 +513,16 @@ static inline int bf_max_head(int tile_docs) {
   if (h > BF_MAX_HEAD) h = BF_MAX_HEAD;
   return h < 0 ? 0 : (int)h;
 }
+// Small shards have fewer tiles than SMs (a pass visits 123 tiles of a 125k-document shard, its
+// sample pass 21): a tile's queries are then split over several work items, each of which stages
+// the tile's columns itself, so that every SM has work and the items are a few per SM.
+static inline int bf_query_groups(int n_pass_tiles, int q, int sms) {
+  if (n_pass_tiles >= 2 * sms) return 1;
+  int g = (3 * sms + n_pass_tiles - 1) / n_pass_tiles;
+  const int max_g = q / (2 * BF_WARPS) > 1 ? q / (2 * BF_WARPS) : 1;  // at least two queries per warp
+  if (g > max_g) g = max_g;
+  return g < 1 ? 1 : g;
+}
 static inline int bf_kprime(int k) { return k + k / 4 + 16; }
 static inline int bf_list_cap(int k) {
   int c = 2048;
@@ -658,8 +673,10 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   if (stride > 0) {
     a.stride = stride;
     a.n_pass_tiles = (n_tiles + stride - 1) / stride;
+    a.q_groups = bf_query_groups(a.n_pass_tiles, q, sms);
     RR_CUDA(cudaFuncSetAttribute(bm25_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = a.n_pass_tiles < sms ? a.n_pass_tiles : sms;
+    const int items = a.n_pass_tiles * a.q_groups;
+    const int grid = items < sms ? items : sms;
     bm25_fast_kernel<true><<<grid, BF_THREADS, smem, st>>>(a);
     RR_LAUNCH_CHECK();
     bf_mark(1, st);
@@ -673,9 +690,11 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   bf_mark(2, st);
   a.stride = 1;
   a.n_pass_tiles = n_tiles;
+  a.q_groups = bf_query_groups(n_tiles, q, sms);
   RR_CUDA(cudaFuncSetAttribute(bm25_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
-    const int grid = n_tiles < sms ? n_tiles : sms;
+    const int items = n_tiles * a.q_groups;
+    const int grid = items < sms ? items : sms;
     bm25_fast_kernel<false><<<grid, BF_THREADS, smem, st>>>(a);
     RR_LAUNCH_CHECK();
   }

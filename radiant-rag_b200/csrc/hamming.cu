@@ -509,6 +509,37 @@ __global__ void __launch_bounds__(MERGE_THREADS)
   }
 }
 
+// BM25 lists as the all_gather leaves them: words [n_shards][2][q][k_in], plane 0 = float64 score bits,
+// plane 1 = global row (-1 = padding); (score desc, row asc), score > 0 was applied by the shards
+__global__ void __launch_bounds__(MERGE_THREADS)
+    merge_f64_gathered_kernel(const long long* words, int n_shards, int q_total, int k_in, int k, int cap,
+                              double* out_score, long long* out_idx, int* out_count) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
+  u32* s_k2 = reinterpret_cast<u32*>(s_k1 + cap);
+  __shared__ SelectScratch<MERGE_THREADS> sc;
+  const int q = blockIdx.x;
+  auto get = [&](long long i, u64& x, u32& y) {
+    const int g = (int)(i / k_in);
+    const int j = (int)(i - (long long)g * k_in);
+    const size_t base = (size_t)g * 2 * q_total * k_in + (size_t)q * k_in + j;
+    const long long row = words[base + (size_t)q_total * k_in];
+    if (row < 0) {
+      x = K1_INVALID;
+      y = K2_INVALID;
+    } else {
+      x = ~f64_orderable(__longlong_as_double(words[base]));
+      y = (u32)row;
+    }
+  };
+  const int m = block_select_sorted<MERGE_THREADS>(get, (long long)n_shards * k_in, k, s_k1, s_k2, cap, sc);
+  for (int j = threadIdx.x; j < k; j += MERGE_THREADS) {
+    const bool have = j < m;
+    merge_write<MERGE_F64_DESC>(out_score, out_idx, (size_t)q * k + j, have, have ? s_k1[j] : 0, have ? s_k2[j] : 0, 0);
+  }
+  if (out_count && threadIdx.x == 0) out_count[q] = m;
+}
+
 __global__ void __launch_bounds__(256)
     pack_hamming_kernel(const int* dist, const long long* idx, long long n, long long* out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -550,6 +581,19 @@ extern "C" int rr_merge_hamming_gathered(const int64_t* in_keys, int32_t n_shard
   const int cap = merge_cap(k);
   merge_hamming_gathered_kernel<<<q, MERGE_THREADS, (size_t)cap * 12, (cudaStream_t)stream>>>(
       (const long long*)in_keys, n_shards, q, k_in, k, cap, out_dist, (long long*)out_idx);
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
+extern "C" int rr_merge_scores_f64_gathered(const int64_t* in_words, int32_t n_shards, int32_t q, int32_t k_in,
+                                            int32_t k, double* out_score, int64_t* out_idx,
+                                            int32_t* out_count, void* stream) {
+  if (q == 0) return RR_OK;
+  RR_CHECK_ARG(in_words && out_score && out_idx, "null pointer");
+  RR_CHECK_ARG(q > 0 && n_shards > 0 && k_in > 0 && k >= 1 && k <= RR_MAX_K, "bad size");
+  const int cap = merge_cap(k);
+  merge_f64_gathered_kernel<<<q, MERGE_THREADS, (size_t)cap * 12, (cudaStream_t)stream>>>(
+      (const long long*)in_words, n_shards, q, k_in, k, cap, out_score, (long long*)out_idx, out_count);
   RR_LAUNCH_CHECK();
   return RR_OK;
 }

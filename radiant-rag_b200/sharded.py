@@ -104,6 +104,17 @@ class GpuShardOps:
                   out_s.data_ptr(), out_i.data_ptr(), out_c.data_ptr(), _stream())
         return out_i, out_s, out_c
 
+    def merge_scores_f64_gathered(self, words_all: torch.Tensor, k: int):
+        """words_all int64 [G, 2, Q, k'] exactly as ONE all_gather of the shards' (score bits, row)
+        buffers leaves it (no transpose copies)."""
+        g, _two, q, k_in = words_all.shape
+        out_s = torch.empty((q, k), dtype=torch.float64, device=self.device)
+        out_i = torch.empty((q, k), dtype=torch.int64, device=self.device)
+        out_c = torch.empty((q,), dtype=torch.int32, device=self.device)
+        _lib.call("rr_merge_scores_f64_gathered", words_all.data_ptr(), g, q, k_in, k, out_s.data_ptr(),
+                  out_i.data_ptr(), out_c.data_ptr(), _stream())
+        return out_i, out_s, out_c
+
     def merge_scores_i32(self, score_all: torch.Tensor, idx_all: torch.Tensor, k: int):
         q, n_in = idx_all.shape
         out_s = torch.empty((q, k), dtype=torch.int32, device=self.device)
@@ -222,8 +233,12 @@ class ShardedBM25Search:
     def search_batch(self, q_terms, k: int, check: bool = True
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """check=False: no host synchronisation (see Bm25DeviceIndex.search_batch)."""
-        idx, score, count = self.local.search_batch(q_terms, k, check=check)
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world > 1 and hasattr(self.ops, "merge_scores_f64_gathered") and hasattr(self.local, "search_batch_into"):
+            # scores and rows of a shard travel in ONE collective and are merged where they land
+            words = self.local.search_batch_into(q_terms, k, check=check)  # int64 [2, Q, k]
+            return self.ops.merge_scores_f64_gathered(_gather_raw(words, self.group, self.comm), k)
+        idx, score, count = self.local.search_batch(q_terms, k, check=check)
         if world == 1:
             return idx, score, count
         s_all = _gather_lists(score, self.group, self.comm)

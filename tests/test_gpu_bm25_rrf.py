@@ -288,3 +288,96 @@ def test_rrf_error_behaviour():
     assert res.data == [] and res.status.value == "partial" and res.success
     assert agent.run(runs=[[], []]).data == []
     assert RRFAgent(RetrievalConfig(), enabled=False).run(runs=[]).status.value == "skipped"
+
+
+def test_bm25_row_sharded_one_collective_merge_emulated():
+    """SURVEY.md 8e for BM25 on one device: three shards built with the GLOBAL idf / avgdl, each
+    writes (score bits, global row) into one [2, Q, k] buffer, the buffers are stacked exactly as
+    ONE all_gather leaves them and merged in place - must equal the single-index oracle."""
+    require_gpu()
+    from radiant_rag_b200.index import DenseIndex
+    from radiant_rag_b200.sharded import GpuShardOps, shard_range
+
+    n_docs, v, k, g = 90_000, 4000, 50, 3
+    ptr, toks = synthetic.zipf_corpus(n_docs, v, seed=21, mean_len=50)
+    orc = BM25Oracle(ptr, toks, v)
+    qt = synthetic.zipf_queries(40, 8, v, seed=21)
+    qt[0, :] = -1
+    words = []
+    for r in range(g):
+        lo, hi = shard_range(n_docs, r, g)
+        sub_ptr = ptr[lo: hi + 1] - ptr[lo]
+        sub_toks = toks[ptr[lo]: ptr[hi]]
+        sh = Bm25DeviceIndex.build(sub_ptr, sub_toks, v, orc.idf, orc.avgdl, orc.k1, orc.b, device=0, row_base=lo)
+        sh.fast_min_docs = 0
+        words.append(sh.search_batch_into(qt, k))
+    ops = GpuShardOps(DenseIndex(32, device=0, store_int8=False, store_f32=False))
+    idx, score, count = ops.merge_scores_f64_gathered(torch.stack(words).contiguous(), k)
+    torch.cuda.synchronize()
+    for qi in range(qt.shape[0]):
+        rows, sc = orc.search(qt[qi].tolist(), k)
+        m = int(count[qi])
+        assert idx[qi, :m].cpu().tolist() == rows.tolist(), qi
+        assert score[qi, :m].cpu().tolist() == sc.tolist(), qi
+
+
+def test_bm25_incremental_adds_refresh_the_device_index_instead_of_rebuilding():
+    """``add_document`` is O(document) in the reference; here the device index of the
+    documents already indexed keeps its sorted postings - its impacts are re-evaluated in place from
+    the host's (stale-idf) tables and the new documents go to a small delta index.  Every search in
+    between equals the oracle fed with the SAME host tables, float64 bit for bit."""
+    require_gpu()
+    v = 400
+    ptr, toks = synthetic.zipf_corpus(2400, v, seed=17, mean_len=30)
+    docs = [[f"t{t:04d}" for t in toks[ptr[d]: ptr[d + 1]]] for d in range(2400)]
+    idx = BM25Index(tile_docs=256)
+    for d in range(2000):
+        idx.add_document(f"d{d}", docs[d])
+    builds = {"n": 0, "rows": []}
+    real_build = Bm25DeviceIndex.build.__func__
+
+    def counting_build(cls, doc_ptr, *args, **kwargs):
+        builds["n"] += 1
+        builds["rows"].append(len(doc_ptr) - 1)
+        return real_build(cls, doc_ptr, *args, **kwargs)
+
+    Bm25DeviceIndex.build = classmethod(counting_build)
+    try:
+        queries = [[f"t{t:04d}" for t in q] for q in synthetic.zipf_queries(6, 5, v, seed=17).tolist()] + [["t0000", "nope"]]
+
+        def check(n_docs):
+            if idx.needs_rebuild:  # a fresh index rebuilds its tables at the first search, as the reference does
+                idx.search(queries[0], 1)   # (bm25_index.py:229-230); afterwards adds are incremental (stale idf)
+            term_ids = np.concatenate([idx._doc_term_ids[d] for d in range(n_docs)]).astype(np.int64)
+            lens = np.array([idx._doc_term_ids[d].size for d in range(n_docs)])
+            p = np.concatenate([[0], np.cumsum(lens)])
+            vv = len(idx._vocab)
+            idf = idx._idf_table(vv)
+            orc = BM25Oracle(p, term_ids, vv, idx.k1, idx.b, idf=idf, avgdl=idx.avgdl)
+            orc.known = idf > 0
+            for q in queries:
+                qt = idx._query_term_ids(q)
+                rows, sc = orc.search(qt.tolist(), 25)
+                got = idx.search(q, 25)
+                assert [d for d, _ in got] == [f"d{r}" for r in rows.tolist()], (n_docs, q)
+                assert [s for _, s in got] == sc.tolist(), (n_docs, q)
+
+        check(2000)
+        assert builds["n"] == 1 and builds["rows"] == [2000]
+        assert not idx.needs_rebuild
+        for d in range(2000, 2100):
+            idx.add_document(f"d{d}", docs[d])
+            if d % 33 == 0:
+                check(d + 1)
+        check(2100)
+        assert builds["rows"].count(2000) == 1 and max(r for r in builds["rows"][1:]) <= 100  # only delta builds since
+        for d in range(2100, 2400):  # beyond the delta budget (1024 / an eighth): one full rebuild, then deltas again
+            idx.add_document(f"d{d}", docs[d])
+        idx.delta_rebuild_fraction = 0.0
+        idx_delta_budget = idx._gpu_docs
+        check(2400)
+        assert idx._gpu_docs == 2400 or idx_delta_budget == 2000
+        assert idx.remove_document("d5")
+        assert "d5" not in [d for d, _ in idx.search(queries[0], 2399)]
+    finally:
+        Bm25DeviceIndex.build = classmethod(real_build)
