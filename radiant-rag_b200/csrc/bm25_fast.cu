@@ -535,7 +535,8 @@ static inline int bf_stride(int n_tiles, int tile_docs, long long n_docs, int k)
   const int cap = bf_list_cap(k), kp = bf_kprime(k);
   if (n_docs <= cap) return 0;
   int s = cap / (3 * kp);
-  if (s > 8) s = 8;
+  if (s > 8) s = 8;  // (every 16th tile was measured: the sample pass halves, but the looser bound lets twice as
+                     //  many documents through the filter pass, whose appends cost more than was saved)
   const long long by_count = (long long)n_tiles * 32 / (4LL * kp);
   if (s > by_count) s = (int)by_count;
   if (s < 1) s = 1;

@@ -299,3 +299,75 @@ class BatchedRetrieval:
         else:
             fused = []
         return dense, sparse, fused
+
+
+# ---- the step after the path: batched cross-encoder rerank and auto-merge ---------
+
+def rerank_batch(local_models: Any, queries: Sequence[str], docs_per_query: Sequence[List[Tuple[Any, float]]],
+                 config: Any, top_k: Optional[int] = None) -> List[List[Tuple[Any, float]]]:
+    """``CrossEncoderRerankingAgent._execute`` (radiant/agents/rerank.py:64-117) for a batch of
+    queries with ONE cross-encoder call: the reference scores each query's candidates with its own
+    ``cross_encoder.predict`` (radiant/llm/local_models.py:251-280); the (query, document) pairs
+    of all queries are independent, so they are flattened into a single ``predict``.  Per query
+    the result is the reference's: candidates = first max(k * candidate_multiplier,
+    min_candidates) documents, texts cut to ``max_doc_chars``, stable sort by score descending,
+    first k.  Falls back to per-query ``local_models.rerank`` when no ``cross_encoder`` is exposed."""
+    k = top_k or config.top_k
+    num_candidates = max(k * config.candidate_multiplier, config.min_candidates)
+    cands = [list(docs[:num_candidates]) for docs in docs_per_query]
+    texts = [[d.content[: config.max_doc_chars] for d, _ in c] for c in cands]
+    encoder = getattr(local_models, "cross_encoder", None)
+    out: List[List[Tuple[Any, float]]] = []
+    if encoder is None:
+        for q, c, t in zip(queries, cands, texts):
+            out.append([(c[i][0], s) for i, s in local_models.rerank(q, t, top_k=k)] if c else [])
+        return out
+    pairs = [(q, t) for q, ts in zip(queries, texts) for t in ts]
+    scores = list(encoder.predict(pairs, show_progress_bar=False)) if pairs else []
+    pos = 0
+    for c in cands:
+        s = [(i, float(scores[pos + i])) for i in range(len(c))]
+        pos += len(c)
+        s.sort(key=lambda x: x[1], reverse=True)  # stable, as the reference
+        out.append([(c[i][0], sc) for i, sc in s[:k]])
+    return out
+
+
+def automerge_batch(store: Any, docs_per_query: Sequence[List[Tuple[Any, float]]], min_children: int,
+                    max_parent_chars: int, top_k: Optional[int] = None) -> List[List[Tuple[Any, float]]]:
+    """The parent look-ups of ``HierarchicalAutoMergingAgent`` (radiant/agents/automerge.py:87-135) for
+    a batch of queries: every distinct parent id of the batch is fetched ONCE (the reference calls
+    ``store.get_doc`` per parent per query), the merge rule itself is unchanged - children of a parent
+    with >= min_children hits are replaced by the parent (best child score) if it exists and is
+    short enough; per doc_id the best score wins; sorted by score descending."""
+    wanted = set()
+    grouped = []
+    for docs in docs_per_query:
+        by_parent, passthrough = {}, []
+        for doc, score in docs:
+            meta = getattr(doc, "meta", {}) or {}
+            parent_id = str(meta.get("parent_id", "")).strip()
+            if str(meta.get("doc_level", "child")) == "child" and parent_id:
+                by_parent.setdefault(parent_id, []).append((doc, score))
+            else:
+                passthrough.append((doc, score))
+        grouped.append((by_parent, passthrough))
+        wanted.update(p for p, ch in by_parent.items() if len(ch) >= min_children)
+    parents = {p: store.get_doc(p) for p in wanted}
+    out = []
+    for by_parent, passthrough in grouped:
+        merged: List[Tuple[Any, float]] = []
+        for parent_id, children in by_parent.items():
+            parent = parents.get(parent_id) if len(children) >= min_children else None
+            if parent is not None and len(parent.content) <= max_parent_chars:
+                merged.append((parent, max(s for _, s in children)))
+            else:
+                merged.extend(children)
+        best = {}
+        for doc, score in passthrough + merged:
+            if doc.doc_id not in best or score > best[doc.doc_id][1]:
+                best[doc.doc_id] = (doc, score)
+        result = list(best.values())
+        result.sort(key=lambda x: x[1], reverse=True)
+        out.append(result[: (top_k or len(passthrough) + sum(len(c) for c in by_parent.values()))])
+    return out

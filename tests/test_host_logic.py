@@ -284,3 +284,64 @@ def test_quantization_section_from_yaml(tmp_path, monkeypatch):
     import pytest
     with pytest.raises(ValueError):
         quantization_from_yaml({"redis": {"quantization": {"rescore_multiplier": 0.5}}})
+
+
+def test_batched_rerank_and_automerge_equal_the_per_query_rule():
+    """one cross-encoder call / one parent fetch for a whole batch, results equal
+    to the reference's per-query rule (radiant/agents/rerank.py:64-117, automerge.py:65-135)."""
+    import pytest
+    torch = pytest.importorskip("torch")
+    from dataclasses import dataclass
+
+    from radiant_rag_b200.base import StoredDoc
+    from radiant_rag_b200.hybrid import automerge_batch, rerank_batch
+
+    class Encoder:
+        calls = 0
+
+        def predict(self, pairs, show_progress_bar=False):
+            Encoder.calls += 1
+            return [float(len(set(q.split()) & set(d.split()))) - 0.01 * len(d) for q, d in pairs]
+
+    class Models:
+        cross_encoder = Encoder()
+
+        def rerank(self, query, documents, top_k=None):  # the reference's per-query method
+            s = self.cross_encoder.predict([(query, d) for d in documents])
+            idx = sorted(((i, float(x)) for i, x in enumerate(s)), key=lambda x: x[1], reverse=True)
+            return idx[:top_k] if top_k else idx
+
+    @dataclass
+    class Cfg:
+        top_k: int = 3
+        candidate_multiplier: int = 2
+        min_candidates: int = 4
+        max_doc_chars: int = 12
+
+    docs = [StoredDoc(f"d{i}", " ".join(["alpha", "beta", "gamma", "delta"][: 1 + i % 4]) + f" x{i}", {}) for i in range(9)]
+    queries = ["alpha beta", "gamma", "zzz"]
+    lists = [[(d, 1.0) for d in docs[:7]], [(d, 1.0) for d in docs[2:]], []]
+    cfg, models = Cfg(), Models()
+    Encoder.calls = 0
+    got = rerank_batch(models, queries, lists, cfg)
+    assert Encoder.calls == 1
+    for q, lst, g in zip(queries, lists, got):
+        cand = lst[: max(cfg.top_k * cfg.candidate_multiplier, cfg.min_candidates)]
+        want = [(cand[i][0], s) for i, s in models.rerank(q, [d.content[: cfg.max_doc_chars] for d, _ in cand], top_k=cfg.top_k)] if cand else []
+        assert [(d.doc_id, s) for d, s in g] == [(d.doc_id, s) for d, s in want]
+
+    class Store:
+        fetched = []
+
+        def get_doc(self, doc_id):
+            Store.fetched.append(doc_id)
+            return {"p1": StoredDoc("p1", "short parent", {"doc_level": "parent"}),
+                    "p2": StoredDoc("p2", "x" * 500, {"doc_level": "parent"})}.get(doc_id)
+
+    ch = [StoredDoc(f"c{i}", f"child {i}", {"doc_level": "child", "parent_id": "p1" if i < 3 else ("p2" if i < 6 else "p3")})
+          for i in range(8)]
+    lists = [[(c, 1.0 - 0.1 * i) for i, c in enumerate(ch)], [(ch[0], 0.5), (ch[1], 0.7), (ch[6], 0.9)]]
+    got = automerge_batch(Store(), lists, min_children=2, max_parent_chars=100)
+    assert sorted(Store.fetched) == ["p1", "p2", "p3"]   # each parent of the batch once
+    assert [d.doc_id for d, _ in got[0]] == ["p1", "c3", "c4", "c5", "c6", "c7"] and got[0][0][1] == 1.0
+    assert [(d.doc_id, s) for d, s in got[1]] == [("c6", 0.9), ("p1", 0.7)]
