@@ -56,6 +56,7 @@ constexpr int BF_MAX_TILE = 1024;
 #endif
 constexpr int BF_INFLIGHT = RR_BF_INFLIGHT;   // posting loads a lane issues before its first accumulate
 
+
 struct BfArgs {
   const long long* tile_term_ptr;  // [n_tiles][n_terms + 1]
   const u64* post_pack;     // [P] row-in-tile << 32 | round(impact * 2^fx_shift) (same order as post_row)
@@ -210,7 +211,8 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
         // fixed-point integers, so the scatter is one native shared-memory atomic per posting.
         // (Measured alternatives that were slower: float accumulators (a compare-and-swap loop per
         // posting), atomic-free read-modify-write of one segment per instruction with a warp barrier
-        // in between, and scoring only the documents the tail touches - a third of a tile.)
+        // in between, scoring only the documents the tail touches - a third of a tile - and staging
+        // the postings through shared memory with cp.async, which leaves room for fewer warps.)
         int incl = ti.len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -523,9 +525,11 @@ static inline int bf_query_groups(int n_pass_tiles, int q, int sms) {
   if (g > max_g) g = max_g;
   return g < 1 ? 1 : g;
 }
-static inline int bf_kprime(int k) { return k + k / 4 + 16; }
+// the bound is a score that k' DISTINCT sampled documents reach (one per lane), so at least k' >= k
+// documents survive the filter; a few extra keep the k-th exact score clear of the bound
+static inline int bf_kprime(int k) { return k + 4; }
 static inline int bf_list_cap(int k) {
-  int c = 2048;
+  int c = 4096;
   while (c < 16 * bf_kprime(k)) c <<= 1;
   if (c > 32768) c = 32768;
   return c;
