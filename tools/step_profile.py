@@ -36,6 +36,21 @@ def main():
     for _ in range(steps):
         res = hybrid.search_batch(queries, qt, top_k=10, dense_top_k=100, bm25_top_k=100, rrf_k=60, check=False)
     torch.cuda.synchronize()
+    if len(sys.argv) > 2 and sys.argv[2] == "exchange":
+        # the merge kernels of the row-sharded exchange on buffers laid out as 8 ranks' all_gather would
+        # leave them (every "rank" contributes this GPU's local lists): for ncu -k regex:merge_|pack_
+        from radiant_rag_b200.sharded import GpuShardOps
+        ops = GpuShardOps(index)
+        qf, qc = index.quantize_queries(queries)
+        d, i = index.hamming_topk(qc, 400, check_overflow=False)
+        keys = ops.pack_hamming(d, i)
+        keys_all = keys.unsqueeze(0).repeat(8, 1, 1).contiguous()
+        words = bm.search_batch_into(qt, 100, check=False)
+        words_all = words.unsqueeze(0).repeat(8, 1, 1, 1).contiguous()
+        for _ in range(3):
+            ops.merge_hamming_gathered(keys_all, 400)
+            ops.merge_scores_f64_gathered(words_all, 100)
+        torch.cuda.synchronize()
     print(json.dumps({"rr_launches_in_build": build_launches, "rr_launches_per_step": (_lib.launch_count - build_launches) // steps,
                       "unchecked_events": hybrid.unchecked_events(), "fused_nonempty": int((res.count > 0).sum())}))
 
