@@ -726,7 +726,8 @@ def run_gpu_arm(args) -> None:
     qt_host = torch.from_numpy(qt_np).pin_memory()
     torch.cuda.synchronize()
     build_s = time.time() - t_build
-    hybrid = HybridSearch(index, bm, rescore_multiplier=mult, prefer_int8=False, comm=bx.comm)
+    hybrid = HybridSearch(index, bm, rescore_multiplier=mult, prefer_int8=False, comm=bx.comm,
+                          overlap=args.overlap)
     kw = dict(top_k=top_k, dense_top_k=dense_k, bm25_top_k=bm25_k, rrf_k=rrf_k)
 
     out_host = {"idx": torch.empty((nq, top_k), dtype=torch.int64).pin_memory(),
@@ -965,6 +966,8 @@ def main() -> None:
     ap.add_argument("--rows", type=int, default=0, help="debug only: override the corpus size")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra BASELINE configs")
+    ap.add_argument("--overlap", action="store_true",
+                    help="experiment: BM25 half on a second stream next to the dense half (single GPU)")
     ap.add_argument("--profile", action="store_true",
                     help="profiling runs (ncu): build, warm up and run the timed steps only, print a short line")
     ap.add_argument("--debug-extra", default="", help="debug only: run just this extra (config2 | config4 | config5)")

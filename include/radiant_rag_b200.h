@@ -164,6 +164,28 @@ int rr_exact_search_f32(const float* emb, int64_t n, int32_t dim, const uint8_t*
                         float* out_score, int64_t* out_idx, int32_t* out_count,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- R5 for BATCHES (csrc/tc_exact.cu): the results of rr_exact_search_f32, bit for bit, with the
+ * row x query products on the tensor cores.  TF32 cosines (tcgen05.mma kind::tf32 straight from the
+ * float32 rows, read from HBM once per 128 queries) against a sampled bound minus a rigorous error
+ * margin keep a few hundred rows per query; their exact scores are then recomputed in
+ * rr_exact_search_f32's own float64 operation order and selected (score desc, row asc).
+ * row_inv_norm f32 [n] = 1 / |row| (0 for zero rows) from rr_row_inv_norms_f32; it only steers the
+ * filter, the exact norms are recomputed for the rows that are kept.
+ * Needs dim % 32 == 0, 16-byte aligned rows and queries, 128 <= n < 2^31 and a corpus large enough
+ * for top_k (rr_exact_search_f32_tc_supported).  A query whose candidate list outgrew its
+ * workspace segment (clustered duplicates, selective tag filters) raises *overflow (accumulated,
+ * never reset here) and overflow_flags[query] (u8 [q], may be NULL; written for every query): its
+ * rows in the outputs are not guaranteed and the caller redoes it with rr_exact_search_f32. */
+int rr_row_inv_norms_f32(const float* emb, int64_t n, int32_t dim, float* out, void* stream);
+int rr_exact_search_f32_tc_supported(int64_t n, int32_t dim, int32_t q, int32_t top_k);
+size_t rr_exact_search_f32_tc_workspace_bytes(int64_t n, int32_t q, int32_t top_k);
+int rr_exact_search_f32_tc(const float* emb, const float* row_inv_norm, int64_t n, int32_t dim,
+                           const uint8_t* tags, uint8_t tag_mask, uint8_t tag_value,
+                           const float* queries, int32_t q, int32_t top_k, double min_similarity,
+                           int64_t row_base, float* out_score, int64_t* out_idx, int32_t* out_count,
+                           uint32_t* overflow, uint8_t* overflow_flags, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
 /* ---- BASELINE config 4: exact int8 x int8 -> int32 search, (score desc, row asc). */
 size_t rr_int8_search_topk_workspace_bytes(int64_t n, int32_t q, int32_t k);
 int rr_int8_search_topk(const int8_t* emb, int64_t n, int32_t dim, const uint8_t* tags,

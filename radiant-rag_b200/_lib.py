@@ -55,6 +55,10 @@ PROTOTYPES = {
     "rr_rescore_i8": (_i32, [_p, _i32, _i32, _p, _i64, _i64, _p, _i32, _i32, _p, _p, _p, _p]),
     "rr_exact_search_f32_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "rr_exact_search_f32": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _f64, _i64, _p, _p, _p, _p, _sz, _p]),
+    "rr_row_inv_norms_f32": (_i32, [_p, _i64, _i32, _p, _p]),
+    "rr_exact_search_f32_tc_supported": (_i32, [_i64, _i32, _i32, _i32]),
+    "rr_exact_search_f32_tc_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "rr_exact_search_f32_tc": (_i32, [_p, _p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _f64, _i64, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "rr_int8_search_topk_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "rr_int8_search_topk": (_i32, [_p, _i64, _i32, _p, _u8, _u8, _p, _i32, _i32, _i64, _p, _p, _p, _sz, _p]),
     "rr_bm25_topk_workspace_bytes": (_sz, [_i32, _i32, _i32]),
@@ -92,7 +96,7 @@ launch_count = 0
 _KERNELS_PER_CALL = {
     "rr_quantize_ubinary": 1, "rr_quantize_int8": 1, "rr_hamming_topk": 2, "rr_rescore_f32": 1,
     "rr_score_candidates_f32": 1, "rr_rank_scored_f32": 1, "rr_rescore_i8": 1,
-    "rr_exact_search_f32": 2, "rr_int8_search_topk": 2, "rr_bm25_topk": 2, "rr_bm25_topk_fast": 4, "rr_bm25_impacts": 1,
+    "rr_exact_search_f32": 2, "rr_exact_search_f32_tc": 6, "rr_row_inv_norms_f32": 1, "rr_int8_search_topk": 2, "rr_bm25_topk": 2, "rr_bm25_topk_fast": 4, "rr_bm25_impacts": 1,
     "rr_rrf_fuse": 1, "rr_rrf_fuse_runs": 1, "rr_merge_hamming": 1, "rr_merge_scores_f64": 1, "rr_merge_scores_f64_gathered": 1, "rr_merge_scores_i32": 1,
     "rr_pack_hamming": 1, "rr_merge_hamming_gathered": 1,
     "rr_unpack_codes_pm1": 1, "rr_tc_dense_keys": 1, "rr_hamming_topk_tc": 5, "rr_int8_search_topk_tc": 5,

@@ -17,7 +17,7 @@ CSRC = PKG_DIR / "csrc"
 OBJ_DIR = PKG_DIR.parent / "build" / "obj"
 LIB_PATH = PKG_DIR / "librr_b200.so"
 SOURCES = ["api.cu", "quantize.cu", "hamming.cu", "rescore.cu", "exact.cu", "bm25.cu", "bm25_fast.cu",
-           "rrf.cu", "synth.cu", "tc_search.cu", "probe.cu"]
+           "rrf.cu", "synth.cu", "tc_search.cu", "tc_exact.cu", "probe.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

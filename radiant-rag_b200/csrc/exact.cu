@@ -11,7 +11,8 @@
 // in flight per lane) against QT queries held in shared memory as float64, so a row is
 // read from HBM once per QT queries and the query operands are read from shared memory
 // once per R rows.  float32 rows accumulate in float64 (correctly rounded cosine, no
-// f32->f64 conversion of the query in the loop); int8 rows use DP4A (exact).  Scores go
+// f32->f64 conversion of the query in the loop; the fused multiply-adds are spelled out because
+// tc_exact.cu's refine kernel restates this exact operation order for its candidates); int8 rows use DP4A (exact).  Scores go
 // out as 32-bit order-preserving keys [q, n].
 // Selection is two-level: (chunk, query) CTAs take the top-k of <= SEL_CHUNK_MAX keys each
 // (block_select_sorted with the per-thread-minimum bound shortcut), then one CTA per
@@ -68,10 +69,10 @@ __global__ void __launch_bounds__(EX_THREADS) exact_f32_scores_vec_kernel(const 
     double s = 0.0;
     for (int v = lane; v < dim4; v += 32) {
       const double2 lo = sq_lo[j * dim4 + v], hi = sq_hi[j * dim4 + v];
-      s += lo.x * lo.x;
-      s += lo.y * lo.y;
-      s += hi.x * hi.x;
-      s += hi.y * hi.y;
+      s = __fma_rn(lo.x, lo.x, s);
+      s = __fma_rn(lo.y, lo.y, s);
+      s = __fma_rn(hi.x, hi.x, s);
+      s = __fma_rn(hi.y, hi.y, s);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -111,20 +112,20 @@ __global__ void __launch_bounds__(EX_THREADS) exact_f32_scores_vec_kernel(const 
         ey[r] = (double)e[r].y;
         ez[r] = (double)e[r].z;
         ew[r] = (double)e[r].w;
-        nn[r] += ex[r] * ex[r];
-        nn[r] += ey[r] * ey[r];
-        nn[r] += ez[r] * ez[r];
-        nn[r] += ew[r] * ew[r];
+        nn[r] = __fma_rn(ex[r], ex[r], nn[r]);
+        nn[r] = __fma_rn(ey[r], ey[r], nn[r]);
+        nn[r] = __fma_rn(ez[r], ez[r], nn[r]);
+        nn[r] = __fma_rn(ew[r], ew[r], nn[r]);
       }
 #pragma unroll
       for (int j = 0; j < QT; ++j) {
         const double2 lo = sq_lo[j * dim4 + v], hi = sq_hi[j * dim4 + v];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          acc[j][r] += lo.x * ex[r];
-          acc[j][r] += lo.y * ey[r];
-          acc[j][r] += hi.x * ez[r];
-          acc[j][r] += hi.y * ew[r];
+          acc[j][r] = __fma_rn(lo.x, ex[r], acc[j][r]);
+          acc[j][r] = __fma_rn(lo.y, ey[r], acc[j][r]);
+          acc[j][r] = __fma_rn(hi.x, ez[r], acc[j][r]);
+          acc[j][r] = __fma_rn(hi.y, ew[r], acc[j][r]);
         }
       }
     }

@@ -79,6 +79,16 @@ __device__ __forceinline__ void tc_mma_i8_ts_elect(u32 d_tmem, u32 a_tmem, u64 b
       "@pe tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, pa;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// kind::tf32: A and B are float32 words in shared memory (K-major, SWIZZLE_128B: 32 floats per row
+// of the swizzle atom, K = 8 per instruction); the low 13 mantissa bits are ignored, D is float32
+__device__ __forceinline__ void tc_mma_tf32_ss_elect(u32 d_tmem, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred pe, pa;\n\t"
+      "elect.sync _|pe, 0xffffffff;\n\t"
+      "setp.ne.b32 pa, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, pa;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
 __device__ __forceinline__ void tc_commit_elect(u32 bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
@@ -102,6 +112,10 @@ __device__ __forceinline__ u64 tc_smem_desc(u32 saddr) {
 }
 // cute::UMMA::InstrDescriptor for kind::i8: D = S32 (bits 4-5 = 2), A format at bit 7 and B format at
 // bit 10 (0 = unsigned int8, 1 = signed int8), both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+// kind::tf32: D = F32 (bits 4-5 = 1), A = B = TF32 (format 2), both K-major
+__host__ __device__ constexpr u32 tc_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((u32)(n >> 3) << 17) | ((u32)(m >> 4) << 24);
+}
 __host__ __device__ constexpr u32 tc_idesc_i8(int m, int n, bool a_signed, bool b_signed) {
   return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((u32)(n >> 3) << 17) |
          ((u32)(m >> 4) << 24);

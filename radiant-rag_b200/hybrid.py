@@ -64,10 +64,13 @@ class HybridSearch:
 
     def __init__(self, dense: DenseIndex, bm25: Any, group: Optional[Any] = None,
                  rescore_multiplier: float = 4.0, prefer_int8: bool = True,
-                 dense_mode: str = "quantized", comm: Optional[Any] = None) -> None:
+                 dense_mode: str = "quantized", comm: Optional[Any] = None, overlap: bool = False) -> None:
         """comm: an ``nccl.NcclComm`` over the same ranks - the candidate exchanges are then issued on
         the current stream, which lets ``GraphedHybridSearch`` capture the WHOLE sharded step (kernels
-        and collectives) into one CUDA graph."""
+        and collectives) into one CUDA graph.
+        overlap: unchecked single-GPU steps run the BM25 half on a second stream next to the dense
+        half (the two are independent until RRF); in a captured step they become parallel branches
+        of the graph.  Not used when sharded: one communicator must see its collectives in one order."""
         if dense_mode not in ("quantized", "exact"):
             raise ValueError("dense_mode must be 'quantized' or 'exact'")
         self.dense_index = dense
@@ -78,6 +81,8 @@ class HybridSearch:
         self.prefer_int8 = bool(prefer_int8)
         self.dense_mode = dense_mode
         self.comm = comm
+        self.overlap = bool(overlap)
+        self._side_stream: Optional[torch.cuda.Stream] = None
         self.ops = GpuShardOps(dense)
         self.dense = ShardedDenseSearch(self.ops, group, comm)
         self.sparse = ShardedBM25Search(bm25, self.ops, group, comm)
@@ -94,6 +99,19 @@ class HybridSearch:
         for name, kk in (("top_k", top_k), ("dense_top_k", dense_top_k), ("bm25_top_k", bm25_top_k)):
             if not 1 <= int(kk) <= _lib.RR_MAX_K:
                 raise ValueError(f"{name}={kk} outside [1, {_lib.RR_MAX_K}]")
+        side = None
+        if self.overlap and not check and self.dense.world() == 1:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream(device=self.device)
+            side = self._side_stream
+            main = torch.cuda.current_stream(self.device)
+            queries = to_device(queries, self.device, torch.float32)
+            q_terms = to_device(q_terms, self.device, torch.int32)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                b_idx, b_score, b_count = self.sparse.search_batch(q_terms, bm25_top_k, check=False)
+            for t in (b_idx, b_score, b_count):
+                t.record_stream(main)
         if self.dense_mode == "quantized":
             d_idx, d_score, d_count = self.dense.search_quantized(
                 queries, dense_top_k, rescore_multiplier=self.rescore_multiplier,
@@ -103,8 +121,11 @@ class HybridSearch:
             if self.dense.world() > 1:
                 raise ValueError("dense_mode='exact' is a single-GPU path")
             d_idx, d_score, d_count = self.dense_index.search_exact(queries, dense_top_k, min_similarity,
-                                                                    tag_mask, tag_value)
-        b_idx, b_score, b_count = self.sparse.search_batch(q_terms, bm25_top_k, check=check)
+                                                                    tag_mask, tag_value, check_overflow=check)
+        if side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(side)
+        else:
+            b_idx, b_score, b_count = self.sparse.search_batch(q_terms, bm25_top_k, check=check)
         f_idx, f_score, f_count = rrf_fuse_runs_device([d_idx, b_idx], top_k, rrf_k)
         return HybridResult(f_idx, f_score, f_count, d_idx, d_score, d_count, b_idx, b_score, b_count)
 

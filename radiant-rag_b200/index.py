@@ -128,6 +128,9 @@ class DenseIndex:
         self.tc_min_queries = 16       # below this the POPC scan (memory-bound) is the faster path
         self._tc_overflow: Optional[torch.Tensor] = None
         self.last_tc_redone = 0        # queries the last checked tensor-core call redid on the exact path
+        self.tc_exact_min_queries = 8  # exact float32 scan: batches from here on take the TF32 filter + float64 refine
+        self._inv_norm: Optional[torch.Tensor] = None  # 1/|row| of the float32 rows (steers the TF32 filter only)
+        self._inv_norm_n = 0
         self.ranges: Optional[torch.Tensor] = None
         if int8_ranges is not None:
             self.set_int8_ranges(int8_ranges)
@@ -280,6 +283,9 @@ class DenseIndex:
                       self.int8[row:row + 1].data_ptr(), _stream())
         if self.store_f32:
             self.f32[row].copy_(e[0])
+            if row < self._inv_norm_n:
+                _lib.call("rr_row_inv_norms_f32", self.f32[row:row + 1].data_ptr(), 1, self.dim,
+                          self._inv_norm[row:row + 1].data_ptr(), _stream())
         self.tags[row] = tag
         if tag != LEVEL_CHILD:
             self.tags_uniform = False
@@ -292,6 +298,25 @@ class DenseIndex:
     def clear(self) -> None:
         self.n = 0
         self.tags_uniform = True
+        self._inv_norm_n = 0
+
+    def invalidate_norms(self) -> None:
+        """Call after writing ``self.f32`` directly (bulk loaders that bypass add / set_row)."""
+        self._inv_norm_n = 0
+
+    def _row_inv_norms(self) -> torch.Tensor:
+        """1 / |row| for rows [0, n), computed once per row (rr_row_inv_norms_f32) and kept."""
+        if self._inv_norm is None or self._inv_norm.shape[0] < self.n:
+            new = torch.empty((max(self._cap, self.n),), dtype=torch.float32, device=self.device)
+            if self._inv_norm is not None and self._inv_norm_n:
+                new[: self._inv_norm_n].copy_(self._inv_norm[: self._inv_norm_n])
+            self._inv_norm = new
+        if self._inv_norm_n < self.n:
+            lo = self._inv_norm_n
+            _lib.call("rr_row_inv_norms_f32", self.f32[lo:self.n].data_ptr(), self.n - lo, self.dim,
+                      self._inv_norm[lo:self.n].data_ptr(), _stream())
+            self._inv_norm_n = self.n
+        return self._inv_norm
 
     # ---- kernels -----------------------------------------------------------------
     def quantize_queries(self, queries: ArrayLike) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -504,26 +529,74 @@ class DenseIndex:
         return out
 
     def search_exact(self, queries: ArrayLike, top_k: int, min_similarity: float = 0.0,
-                     tag_mask: int = 0, tag_value: int = 0
+                     tag_mask: int = 0, tag_value: int = 0, use_tc: Optional[bool] = None,
+                     check_overflow: bool = True
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Exact float32 cosine scan (reference redis_store.py:863-952), batched."""
+        """Exact float32 cosine scan (reference redis_store.py:863-952), batched.
+
+        Batches of >= ``tc_exact_min_queries`` run the filter on the tensor cores
+        (rr_exact_search_f32_tc: TF32 products, exact float64 refine of the survivors) with
+        results bit-identical to the CUDA-core scan; a checked call redoes the queries whose
+        candidate list overflowed with rr_exact_search_f32, an unchecked call (graph capture)
+        accumulates the counter (``tc_overflow_total``)."""
         self._activate()
         if self.f32 is None:
             raise _lib.RadiantB200Error("index has no float32 rows: exact search unavailable")
+        if not 1 <= int(top_k) <= _lib.RR_MAX_K:
+            raise ValueError(f"top_k={top_k} outside [1, {_lib.RR_MAX_K}]")
         qf = to_device(queries, self.device, torch.float32)
         if qf.ndim == 1:
             qf = qf[None, :]
         q = qf.shape[0]
+        lib = _lib.load()
+        tptr, tm, tv = self._tag_args(tag_mask, tag_value)
+
+        def cuda_cores(q_rows):
+            qn = q_rows.shape[0]
+            score = torch.empty((qn, top_k), dtype=torch.float32, device=self.device)
+            idx = torch.empty((qn, top_k), dtype=torch.int64, device=self.device)
+            count = torch.empty((qn,), dtype=torch.int32, device=self.device)
+            ws_bytes = lib.rr_exact_search_f32_workspace_bytes(self.n, qn, top_k)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            _lib.call("rr_exact_search_f32", self.f32.data_ptr(), self.n, self.dim, tptr, tm, tv,
+                      q_rows.data_ptr(), qn, top_k, float(min_similarity), self.row_base, score.data_ptr(),
+                      idx.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+            return idx, score, count
+
+        if use_tc is None:
+            use_tc = self.use_tensor_cores and q >= self.tc_exact_min_queries
+        if use_tc:
+            use_tc = bool(lib.rr_exact_search_f32_tc_supported(self.n, self.dim, q, top_k)) \
+                and qf.data_ptr() % 16 == 0
+        if not use_tc:
+            return cuda_cores(qf.contiguous())
+        qf = qf.contiguous()
         score = torch.empty((q, top_k), dtype=torch.float32, device=self.device)
         idx = torch.empty((q, top_k), dtype=torch.int64, device=self.device)
         count = torch.empty((q,), dtype=torch.int32, device=self.device)
-        lib = _lib.load()
-        ws_bytes = lib.rr_exact_search_f32_workspace_bytes(self.n, q, top_k)
+        flags = torch.empty((q,), dtype=torch.uint8, device=self.device)
+        if check_overflow:
+            ovf = torch.zeros(1, dtype=torch.int32, device=self.device)
+        else:
+            if self._tc_overflow is None:
+                self._tc_overflow = torch.zeros(1, dtype=torch.int32, device=self.device)
+            ovf = self._tc_overflow
+        inv = self._row_inv_norms()
+        ws_bytes = lib.rr_exact_search_f32_tc_workspace_bytes(self.n, q, top_k)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-        tptr, tm, tv = self._tag_args(tag_mask, tag_value)
-        _lib.call("rr_exact_search_f32", self.f32.data_ptr(), self.n, self.dim, tptr, tm, tv,
+        _lib.call("rr_exact_search_f32_tc", self.f32.data_ptr(), inv.data_ptr(), self.n, self.dim, tptr, tm, tv,
                   qf.data_ptr(), q, top_k, float(min_similarity), self.row_base, score.data_ptr(),
-                  idx.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
+                  idx.data_ptr(), count.data_ptr(), ovf.data_ptr(), flags.data_ptr(), ws.data_ptr(), ws_bytes,
+                  _stream())
+        if check_overflow and int(ovf.item()) != 0:
+            bad = torch.nonzero(flags).flatten()
+            self.last_tc_redone = int(bad.numel())
+            i2, s2, c2 = cuda_cores(qf[bad].contiguous())
+            idx[bad] = i2
+            score[bad] = s2
+            count[bad] = c2
+        elif check_overflow:
+            self.last_tc_redone = 0
         return idx, score, count
 
     def search_int8_exact(self, queries_i8: ArrayLike, top_k: int, tag_mask: int = 0,

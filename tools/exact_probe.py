@@ -32,9 +32,20 @@ for lo in range(0, n, 125_000):
     idx.add(synth_rows_device(lo, 125_000, dim, 1))
 for q in (1, 2, 4, 8, 64):
     qs = synth_query_rows_device(0, q, dim, 1, n)
-    ms = ev(lambda: idx.search_exact(qs, 10))
-    print(json.dumps({"op": "exact_f32", "rows": n, "dim": dim, "q": q, "ms": ms, "GBs": n * dim * 4 * ((q + 7) // 8) / ms / 1e6,
-                      "queries_per_s": q / ms * 1e3}), flush=True)
+    ms = ev(lambda: idx.search_exact(qs, 10, use_tc=False), reps=5 if q >= 8 else 20)
+    print(json.dumps({"op": "exact_f32_cuda_cores", "rows": n, "dim": dim, "q": q, "ms": ms,
+                      "GBs": n * dim * 4 * ((q + 7) // 8) / ms / 1e6, "queries_per_s": q / ms * 1e3}), flush=True)
+idx.search_exact(synth_query_rows_device(0, 8, dim, 1, n), 10, use_tc=True)  # row norms are computed once, here
+for q, k in ((8, 10), (64, 10), (128, 10), (256, 10), (1024, 10), (64, 100), (1024, 100)):
+    qs = synth_query_rows_device(0, q, dim, 1, n)
+    ms = ev(lambda: idx.search_exact(qs, k, use_tc=True, check_overflow=False))
+    print(json.dumps({"op": "exact_f32_tc", "rows": n, "dim": dim, "q": q, "k": k, "ms": ms,
+                      "GBs_per_query_block": n * dim * 4 * ((q + 127) // 128) / ms / 1e6,
+                      "tf32_TFLOPs": 2.0 * n * dim * q / ms / 1e9, "queries_per_s": q / ms * 1e3,
+                      "overflow_events": idx.tc_overflow_total()}), flush=True)
+    idx.tc_overflow_reset()
+if "--f32-only" in sys.argv:
+    sys.exit(0)
 del idx
 torch.cuda.empty_cache()
 # config 4 shape scaled to one GPU: 2.5M x 1024 int8, 4096 queries
