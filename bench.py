@@ -256,6 +256,7 @@ class Bench:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         self.comm = None
+        self.comm_sparse = None
         if self.world > 1:
             # NCCL prints its version banner to stdout on the first communicator; rank 0 must print ONE
             # JSON line, so stdout is pointed at stderr (fd level) until the first collective is done
@@ -271,6 +272,9 @@ class Bench:
                 # (kernels + collectives) replays as ONE CUDA graph
                 from radiant_rag_b200.nccl import NcclComm
                 self.comm = NcclComm(self.dev)
+                # the BM25 half of the hybrid step runs on its own stream next to the dense half: its
+                # exchanges need their own communicator (one communicator = one order of collectives)
+                self.comm_sparse = NcclComm(self.dev)
             finally:
                 sys.stdout.flush()
                 os.dup2(saved, 1)
@@ -727,7 +731,7 @@ def run_gpu_arm(args) -> None:
     torch.cuda.synchronize()
     build_s = time.time() - t_build
     hybrid = HybridSearch(index, bm, rescore_multiplier=mult, prefer_int8=False, comm=bx.comm,
-                          overlap=args.overlap)
+                          overlap=not args.no_overlap, comm_sparse=bx.comm_sparse)
     kw = dict(top_k=top_k, dense_top_k=dense_k, bm25_top_k=bm25_k, rrf_k=rrf_k)
 
     out_host = {"idx": torch.empty((nq, top_k), dtype=torch.int64).pin_memory(),
@@ -966,8 +970,8 @@ def main() -> None:
     ap.add_argument("--rows", type=int, default=0, help="debug only: override the corpus size")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra BASELINE configs")
-    ap.add_argument("--overlap", action="store_true",
-                    help="experiment: BM25 half on a second stream next to the dense half (single GPU)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="run the BM25 half after the dense half on one stream instead of next to it on a second one")
     ap.add_argument("--profile", action="store_true",
                     help="profiling runs (ncu): build, warm up and run the timed steps only, print a short line")
     ap.add_argument("--debug-extra", default="", help="debug only: run just this extra (config2 | config4 | config5)")

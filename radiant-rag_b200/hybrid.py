@@ -64,13 +64,16 @@ class HybridSearch:
 
     def __init__(self, dense: DenseIndex, bm25: Any, group: Optional[Any] = None,
                  rescore_multiplier: float = 4.0, prefer_int8: bool = True,
-                 dense_mode: str = "quantized", comm: Optional[Any] = None, overlap: bool = False) -> None:
+                 dense_mode: str = "quantized", comm: Optional[Any] = None, overlap: bool = False,
+                 comm_sparse: Optional[Any] = None) -> None:
         """comm: an ``nccl.NcclComm`` over the same ranks - the candidate exchanges are then issued on
         the current stream, which lets ``GraphedHybridSearch`` capture the WHOLE sharded step (kernels
         and collectives) into one CUDA graph.
-        overlap: unchecked single-GPU steps run the BM25 half on a second stream next to the dense
-        half (the two are independent until RRF); in a captured step they become parallel branches
-        of the graph.  Not used when sharded: one communicator must see its collectives in one order."""
+        overlap: unchecked steps run the BM25 half on a second stream next to the dense half (the two
+        are independent until RRF); in a captured step they become parallel branches of the graph.
+        When sharded this needs ``comm_sparse``, a SECOND communicator for the BM25 exchange: one
+        communicator must see its collectives in one order on every rank, and two branches of a
+        graph have none."""
         if dense_mode not in ("quantized", "exact"):
             raise ValueError("dense_mode must be 'quantized' or 'exact'")
         self.dense_index = dense
@@ -85,7 +88,8 @@ class HybridSearch:
         self._side_stream: Optional[torch.cuda.Stream] = None
         self.ops = GpuShardOps(dense)
         self.dense = ShardedDenseSearch(self.ops, group, comm)
-        self.sparse = ShardedBM25Search(bm25, self.ops, group, comm)
+        self.comm_sparse = comm_sparse
+        self.sparse = ShardedBM25Search(bm25, self.ops, group, comm_sparse if comm_sparse is not None else comm)
 
     def search_batch(self, queries, q_terms, top_k: int = 10, dense_top_k: int = 100,
                      bm25_top_k: int = 100, rrf_k: float = 60, min_similarity: float = 0.0,
@@ -100,7 +104,7 @@ class HybridSearch:
             if not 1 <= int(kk) <= _lib.RR_MAX_K:
                 raise ValueError(f"{name}={kk} outside [1, {_lib.RR_MAX_K}]")
         side = None
-        if self.overlap and not check and self.dense.world() == 1:
+        if self.overlap and not check and (self.dense.world() == 1 or self.comm_sparse is not None):
             if self._side_stream is None:
                 self._side_stream = torch.cuda.Stream(device=self.device)
             side = self._side_stream

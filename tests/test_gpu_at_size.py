@@ -126,6 +126,17 @@ def test_config3_hybrid_top10_vs_oracle(config3):
     torch.cuda.synchronize()
     assert torch.equal(out.idx, res.idx) and torch.equal(out.score, res.score) and torch.equal(out.count, res.count)
     assert hybrid.unchecked_events() == 0
+    # the BM25 half on a second stream next to the dense half (parallel graph branches): same bits
+    hybrid2 = HybridSearch(c["index"], c["bm"], rescore_multiplier=4.0, prefer_int8=False, overlap=True)
+    eager = hybrid2.search_batch(c["queries"], qt_d, top_k=10, dense_top_k=100, bm25_top_k=100, rrf_k=60, check=False)
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(eager.tensors(), res.tensors()))
+    g2 = GraphedHybridSearch(hybrid2, 1024, 768, 8, top_k=10, dense_top_k=100, bm25_top_k=100, rrf_k=60)
+    for _ in range(3):
+        out2 = g2(c["queries"].cpu().pin_memory(), torch.from_numpy(c["qt"]).pin_memory())
+    torch.cuda.synchronize()
+    assert all(torch.equal(x, y) for x, y in zip(out2.tensors(), res.tensors()))
+    assert hybrid2.unchecked_events() == 0
 
 
 def test_config4_int8_exact_at_size_vs_oracle():
