@@ -62,6 +62,7 @@ def _peaks() -> dict:
         d = json.loads(p2.read_text())
         out.update(i8_ts_tops=d.get("i8_mma_m128n128_ts_tops"), i8_ss_tops=d.get("i8_mma_m128n256_ss_tops"),
                    popc_tera=d.get("popc32_tera_per_s"), smem_tbs=d.get("smem_load_tb_per_s"),
+                   gather_tbs=d.get("gather_3kb_rows_1024x400_tb_per_s"),
                    probe_src="measured by tools/peak_probe.py (profiles/r2_peaks.json)")
     return out
 
@@ -909,6 +910,10 @@ def run_gpu_arm(args) -> None:
                    "achieved": c_bytes / (rescore_ms * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                    "frac": c_bytes / (rescore_ms * 1e-3) / 1e9 / pk["hbm_gbs"], "launch_ms": rescore_ms,
                    "share_of_step": rescore_ms / ms_per_step, "algorithmic_bytes_per_launch": c_bytes}
+        if pk.get("gather_tbs"):  # what the memory system delivers for this access pattern with the arithmetic left out
+            rs_roof["gather_view"] = {"peak_TBs": pk["gather_tbs"], "what": "rr_probe_gather: the same bulk-copy ring over "
+                                      "random 3 KB rows, rows released unread (profiles/r2_peaks.json)",
+                                      "frac": c_bytes / (rescore_ms * 1e-3) / 1e12 / pk["gather_tbs"]}
         dominant = max((tc_roof, bm_roof, rs_roof), key=lambda r: r["launch_ms"])
         roofline = dict(dominant)
         roofline["timing"] = ("CUDA events on the launching stream around the kernel (rr_tc_timing / rr_bm25_timing), "

@@ -320,11 +320,17 @@ int rr_synth_zipf_tokens(int32_t* out, int64_t pos_start, int64_t n, uint64_t se
  * Each call times its own kernel with CUDA events on `stream` (best of 5) and synchronises.
  *   rr_probe_popc    32-bit POPC instructions per second over a full grid;
  *   rr_probe_smem    bytes per second of 128-bit shared-memory loads over a full grid;
+ *   rr_probe_gather  bytes per second of a random-row gather (see below);
  *   rr_probe_i8_mma  int8 operations per second (2 per MAC) of back-to-back
  *                    tcgen05.mma.kind::i8 from resident operands, one CTA per SM:
  *                    mode 0 = M128 N256 K32, A and B in shared memory; 1 = M128 N128, both in shared
  *                    memory; 2 = M128 N128, A in tensor memory (the batched Hamming scan's form). */
 int rr_probe_popc(int32_t iters, double* out_popc32_per_s_host, void* stream);
+/* rr_probe_gather (csrc/rescore.cu): the candidate gather of rr_score_candidates_f32 with the
+ * arithmetic left out - bytes per second the memory system delivers for q * c random rows of this
+ * index through the same bulk-copy ring (best of 5).  scratch_scores f32 [q, c] is overwritten. */
+int rr_probe_gather(const void* emb, int32_t emb_dtype, int64_t n, int32_t dim, const int64_t* cand_idx,
+                    int32_t q, int32_t c, float* scratch_scores, double* out_bytes_per_s_host, void* stream);
 int rr_probe_smem(int32_t iters, double* out_bytes_per_s_host, void* stream);
 int rr_probe_i8_mma(int32_t mode, int32_t iters, double* out_ops_per_s_host, void* stream);
 

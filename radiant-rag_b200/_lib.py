@@ -79,6 +79,7 @@ PROTOTYPES = {
     "rr_merge_scores_f64": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p, _p]),
     "rr_merge_scores_i32": (_i32, [_p, _p, _i32, _i32, _i32, _p, _p, _p]),
     "rr_probe_popc": (_i32, [_i32, C.POINTER(_f64), _p]),
+    "rr_probe_gather": (_i32, [_p, _i32, _i64, _i32, _p, _i32, _i32, _p, C.POINTER(_f64), _p]),
     "rr_probe_smem": (_i32, [_i32, C.POINTER(_f64), _p]),
     "rr_probe_i8_mma": (_i32, [_i32, _i32, C.POINTER(_f64), _p]),
     "rr_synth_rows_f32": (_i32, [_p, _i64, _i64, _i32, _u64, _i32, _p]),

@@ -253,20 +253,29 @@ constexpr int RG_THREADS = 256;
 constexpr int RG_CONSUMERS = RG_THREADS / 32 - 1;
 constexpr int RG_MAX_STAGES = 32;
 
-template <int EMB>
-__global__ void __launch_bounds__(RG_THREADS) rescore_ring_kernel(const RescoreArgs a, int stages, int row_bytes, int per) {
+// The [q][c] candidate slots are cut into EQUAL contiguous ranges, one per CTA, regardless of query
+// boundaries (a CTA keeps the <= nqv query vectors its range touches in shared memory): with two
+// resident CTAs per SM and exactly 2 x SMs x m ranges there is no partial last wave.
+// COPY_ONLY (rr_probe_gather): the consumers release every row unread - the kernel then measures what
+// the memory system delivers for this access pattern (random rows of row_bytes).
+template <int EMB, bool COPY_ONLY>
+__global__ void __launch_bounds__(RG_THREADS) rescore_ring_kernel(const RescoreArgs a, int stages, int row_bytes, int per,
+                                                                   int nqv, long long total) {
   extern __shared__ __align__(128) unsigned char rg_smem[];
   unsigned char* ring = rg_smem;                                               // [stages][row_bytes]
-  float* sq = reinterpret_cast<float*>(ring + (size_t)stages * row_bytes);     // [dim]
-  long long* s_loc = reinterpret_cast<long long*>(sq + align_up_dev((size_t)a.dim, 4));  // [per]
-  int* s_ci = reinterpret_cast<int*>(s_loc + per);                             // [per]
+  float* sq = reinterpret_cast<float*>(ring + (size_t)stages * row_bytes);     // [nqv][dim4 * 4]
+  const int dimp = (int)align_up_dev((size_t)a.dim, 4);
+  long long* s_loc = reinterpret_cast<long long*>(sq + (size_t)nqv * dimp);    // [per]
+  int* s_slot = reinterpret_cast<int*>(s_loc + per);                           // [per] flattened slot q * c + ci
   __shared__ __align__(8) u64 full[RG_MAX_STAGES];
   __shared__ __align__(8) u64 empty[RG_MAX_STAGES];
   __shared__ int s_nvalid;
-  const int q = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int lo = blockIdx.y * per;
-  const int hi = min(a.c, lo + per);
+  const long long lo = (long long)blockIdx.x * per;
+  const long long hi = min(total, lo + per);
+  if (lo >= hi) return;
+  const int q_first = (int)(lo / a.c);
+  const int q_last = (int)((hi - 1) / a.c);
   if (threadIdx.x == 0) {
     s_nvalid = 0;
     for (int s = 0; s < stages; ++s) {
@@ -275,18 +284,20 @@ __global__ void __launch_bounds__(RG_THREADS) rescore_ring_kernel(const RescoreA
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int d = threadIdx.x; d < a.dim; d += RG_THREADS) sq[d] = a.queries[(size_t)q * a.dim + d];
+  for (int i = threadIdx.x; i < (q_last - q_first + 1) * a.dim; i += RG_THREADS) {
+    const int j = i / a.dim, d = i - j * a.dim;
+    sq[(size_t)j * dimp + d] = a.queries[(size_t)(q_first + j) * a.dim + d];
+  }
   __syncthreads();
-  const long long* cand = a.cand_idx + (size_t)q * a.c;
-  for (int ci = lo + threadIdx.x; ci < hi; ci += RG_THREADS) {
-    const long long idx = cand[ci];
+  for (long long sl = lo + threadIdx.x; sl < hi; sl += RG_THREADS) {
+    const long long idx = a.cand_idx[sl];
     const long long loc = idx - a.row_base;
     if (idx >= 0 && loc >= 0 && loc < a.n) {
       const int slot = atomicAdd(&s_nvalid, 1);  // rows are independent: their order is free
       s_loc[slot] = loc;
-      s_ci[slot] = ci;
+      s_slot[slot] = (int)sl;
     } else {
-      a.out_score[(size_t)q * a.c + ci] = -INFINITY;  // not owned by this shard / padding
+      a.out_score[sl] = -INFINITY;  // not owned by this shard / padding
     }
   }
   __syncthreads();
@@ -306,13 +317,16 @@ __global__ void __launch_bounds__(RG_THREADS) rescore_ring_kernel(const RescoreA
       }
     }
   } else {
-    const float4* q4 = reinterpret_cast<const float4*>(sq);
     const int nv4 = a.dim >> 2;
     for (int j = warp - 1; j < nv; j += RG_CONSUMERS) {
       const int s = j % stages;
+      const int slot = s_slot[j];
+      const float4* q4 = reinterpret_cast<const float4*>(sq + (size_t)(slot / a.c - q_first) * dimp);
       tc_mbar_wait(tc_smem(full + s), (u32)(j / stages) & 1u);
       double acc = 0.0;
-      if (EMB == RR_F32) {
+      if (COPY_ONLY) {
+        acc = (double)reinterpret_cast<const float*>(ring + (size_t)s * row_bytes)[lane];
+      } else if (EMB == RR_F32) {
         const float4* r4 = reinterpret_cast<const float4*>(ring + (size_t)s * row_bytes);
         for (int v = lane; v < nv4; v += 32) {
           const float4 e = r4[v];
@@ -336,7 +350,7 @@ __global__ void __launch_bounds__(RG_THREADS) rescore_ring_kernel(const RescoreA
       __syncwarp();  // every lane has read its part of the slot
       if (lane == 0) tc_mbar_arrive(tc_smem(empty + s));
       acc = warp_sum_f64(acc);
-      if (lane == 0) a.out_score[(size_t)q * a.c + s_ci[j]] = (float)acc;
+      if (lane == 0) a.out_score[slot] = (float)acc;
     }
   }
 }
@@ -467,6 +481,48 @@ extern "C" int rr_rescore_f32(const float* queries, int32_t q, int32_t dim, cons
   return RR_OK;
 }
 
+// ring launch shared by rr_score_candidates_f32 and rr_probe_gather; returns RR_OK, or -1 when the
+// shape does not fit the ring (the caller then uses the register-staged kernel)
+template <bool COPY_ONLY>
+static int launch_rescore_ring(const RescoreArgs& a, int q, int emb_dtype, cudaStream_t st) {
+  const int dim = a.dim, c = a.c;
+  const int row_bytes = emb_dtype == RR_F32 ? dim * 4 : dim;
+  if (!((dim & 3) == 0 && (row_bytes & 15) == 0 && ((size_t)a.emb & 15) == 0 && a.n > 0)) return -1;
+  // equal slot ranges, 2 x SMs x m of them (two CTAs per SM are resident): m is the smallest
+  // multiplier for which a range touches <= 8 queries and holds <= 2048 slots
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  const long long total = (long long)q * c;
+  const int dimp = (int)align_up((size_t)dim, 4);
+  int per = 0, nqv = 0;
+  for (int m = 1; m <= 64; ++m) {
+    const long long n_cta = 2LL * sms * m;
+    per = (int)((total + n_cta - 1) / n_cta);
+    if (per < 4 * RG_CONSUMERS) per = 4 * RG_CONSUMERS;  // tiny calls: fewer, fuller CTAs
+    nqv = (per - 1) / c + 2;
+    if (nqv > q) nqv = q;
+    if (nqv <= 8 && per <= 2048) break;
+  }
+  const long long n_cta = (total + per - 1) / per;
+  const size_t fixed = (size_t)nqv * dimp * 4 + (size_t)per * 12 + 16;
+  // a ring slot must always be consumed by the SAME warp (row j -> slot j % stages, warp j % 7):
+  // a parity wait is only meaningful for a waiter that has seen the previous phase complete,
+  // so the ring depth is a multiple of the consumer count
+  int stages = fixed < 100 * 1024 ? (int)((100 * 1024 - fixed) / row_bytes) : 0;
+  if (stages > RG_MAX_STAGES) stages = RG_MAX_STAGES;
+  stages = stages / RG_CONSUMERS * RG_CONSUMERS;
+  if (!(stages >= RG_CONSUMERS && nqv <= 8 && per <= 2048 && total < (1LL << 31))) return -1;
+  const size_t rsm = (size_t)stages * row_bytes + fixed;
+  if (emb_dtype == RR_F32) {
+    RR_CUDA(cudaFuncSetAttribute(rescore_ring_kernel<RR_F32, COPY_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+    rescore_ring_kernel<RR_F32, COPY_ONLY><<<(unsigned)n_cta, RG_THREADS, rsm, st>>>(a, stages, row_bytes, per, nqv, total);
+  } else {
+    RR_CUDA(cudaFuncSetAttribute(rescore_ring_kernel<RR_I8, COPY_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
+    rescore_ring_kernel<RR_I8, COPY_ONLY><<<(unsigned)n_cta, RG_THREADS, rsm, st>>>(a, stages, row_bytes, per, nqv, total);
+  }
+  RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
 extern "C" int rr_score_candidates_f32(const float* queries, int32_t q, int32_t dim, const void* emb,
                                        int32_t emb_dtype, int64_t n, int64_t row_base,
                                        const int64_t* cand_idx, int32_t c, float* out_score,
@@ -480,40 +536,10 @@ extern "C" int rr_score_candidates_f32(const float* queries, int32_t q, int32_t 
   RescoreArgs a{queries, dim, emb, n, row_base, (const long long*)cand_idx, c, 1,
                 0.0, out_score, nullptr, nullptr};
   cudaStream_t st = (cudaStream_t)stream;
-  {
-    // rows staged through shared memory by the bulk-copy engine when they are 16-byte multiples
-    // (float32: dim % 4 == 0, int8: dim % 16 == 0) at 16-byte aligned addresses
-    const int row_bytes = emb_dtype == RR_F32 ? dim * 4 : dim;
-    if ((dim & 3) == 0 && (row_bytes & 15) == 0 && ((size_t)emb & 15) == 0 && n > 0) {
-      int split = (2 * 148 + q - 1) / q;  // two CTAs per SM are resident
-      const int max_split = (c + 4 * RG_CONSUMERS - 1) / (4 * RG_CONSUMERS);
-      if (split > max_split) split = max_split;
-      if (split > 16) split = 16;
-      if (split < 1) split = 1;
-      const int per = (c + split - 1) / split;
-      const size_t fixed = align_up((size_t)dim * 4, 16) + (size_t)per * 12 + 16;
-      // a ring slot must always be consumed by the SAME warp (row j -> slot j % stages, warp j % 7):
-      // a parity wait is only meaningful for a waiter that has seen the previous phase complete,
-      // so the ring depth is a multiple of the consumer count
-      int stages = (int)((100 * 1024 - fixed) / row_bytes);
-      if (stages > RG_MAX_STAGES) stages = RG_MAX_STAGES;
-      stages = stages / RG_CONSUMERS * RG_CONSUMERS;
-      if (stages >= RG_CONSUMERS && per <= 65535) {
-        const size_t rsm = (size_t)stages * row_bytes + fixed;
-        dim3 grid(q, split);
-        RescoreArgs ar = a;
-        if (emb_dtype == RR_F32) {
-          RR_CUDA(cudaFuncSetAttribute(rescore_ring_kernel<RR_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-          rescore_ring_kernel<RR_F32><<<grid, RG_THREADS, rsm, st>>>(ar, stages, row_bytes, per);
-        } else {
-          RR_CUDA(cudaFuncSetAttribute(rescore_ring_kernel<RR_I8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rsm));
-          rescore_ring_kernel<RR_I8><<<grid, RG_THREADS, rsm, st>>>(ar, stages, row_bytes, per);
-        }
-        RR_LAUNCH_CHECK();
-        return RR_OK;
-      }
-    }
-  }
+  // rows staged through shared memory by the bulk-copy engine when they are 16-byte multiples
+  // (float32: dim % 4 == 0, int8: dim % 16 == 0) at 16-byte aligned addresses
+  rc = launch_rescore_ring<false>(a, q, emb_dtype, st);
+  if (rc != -1) return rc;
   const size_t smem = align_up((size_t)dim * 4, 16) + 8;
   // enough CTAs for ~4 per SM, at least one warp iteration of work each
   int split = (4 * 148 + q - 1) / q;
@@ -560,5 +586,41 @@ extern "C" int rr_rescore_i8(const int8_t* queries_i8, int32_t q, int32_t dim, c
       queries_i8, dim, emb, n, row_base, (const long long*)cand_idx, c, p, top_k, out_score,
       (long long*)out_idx, out_count);
   RR_LAUNCH_CHECK();
+  return RR_OK;
+}
+
+// Measurement aid (tools/peak_probe.py): the gather of rr_score_candidates_f32 with the arithmetic
+// left out - bytes per second the memory system delivers for q * c random rows of this index.
+extern "C" int rr_probe_gather(const void* emb, int32_t emb_dtype, int64_t n, int32_t dim, const int64_t* cand_idx,
+                               int32_t q, int32_t c, float* scratch_scores, double* out_bytes_per_s, void* stream) {
+  RR_CHECK_ARG(emb && cand_idx && scratch_scores && out_bytes_per_s && q > 0 && c > 0 && n > 0, "bad argument");
+  RR_CHECK_ARG(emb_dtype == RR_F32 || emb_dtype == RR_I8, "emb_dtype must be RR_F32 or RR_I8");
+  cudaStream_t st = (cudaStream_t)stream;
+  // the query vectors are loaded but never used: any readable buffer of q * dim floats will do
+  RescoreArgs a{reinterpret_cast<const float*>(emb), dim, emb, n, 0, (const long long*)cand_idx, c, 1,
+                0.0, scratch_scores, nullptr, nullptr};
+  RR_CHECK_ARG((long long)q * dim <= n * (long long)(emb_dtype == RR_F32 ? dim : dim / 4), "index too small to stand in for the queries");
+  cudaEvent_t e0, e1;
+  RR_CUDA(cudaEventCreate(&e0));
+  RR_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 6; ++rep) {
+    RR_CUDA(cudaEventRecord(e0, st));
+    int rc = launch_rescore_ring<true>(a, q, emb_dtype, st);
+    if (rc != RR_OK) {
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      if (rc == -1) set_error("rr_probe_gather: shape does not fit the ring kernel");
+      return rc == -1 ? RR_ERR_INVALID : rc;
+    }
+    RR_CUDA(cudaEventRecord(e1, st));
+    RR_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    RR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *out_bytes_per_s = (double)q * c * (emb_dtype == RR_F32 ? dim * 4.0 : (double)dim) / (best * 1e-3);
   return RR_OK;
 }

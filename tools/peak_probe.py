@@ -55,6 +55,20 @@ def measure() -> dict:
     if rc != 0:
         raise SystemExit("rr_probe_smem: " + _lib.last_error())
     out["smem_load_tb_per_s"] = v.value / 1e12
+    # random-row gather through the rescoring kernel's bulk-copy ring, arithmetic left out:
+    # config 3's shape (1024 x 400 rows of 3 KB out of 1M) and config 2's (256 x 200)
+    n, dim = 1_000_000, 768
+    rows = torch.empty((n, dim), dtype=torch.float32, device="cuda")
+    rows.normal_()
+    for name, q, c in (("gather_3kb_rows_1024x400", 1024, 400), ("gather_3kb_rows_256x200", 256, 200)):
+        cand = torch.randint(0, n, (q, c), dtype=torch.int64, device="cuda")
+        scratch = torch.empty((q, c), dtype=torch.float32, device="cuda")
+        rc = lib.rr_probe_gather(rows.data_ptr(), _lib.RR_F32, n, dim, cand.data_ptr(), q, c, scratch.data_ptr(),
+                                 C.byref(v), st)
+        if rc != 0:
+            raise SystemExit("rr_probe_gather: " + _lib.last_error())
+        out[name + "_tb_per_s"] = v.value / 1e12
+    del rows
     sms = lib.rr_sm_count()
     out["sm_count"] = sms
     out["sm_mhz_after_probe"] = clk
