@@ -869,9 +869,11 @@ def run_gpu_arm(args) -> None:
         tensor_peak = pk.get("i8_ts_tops") or 2.0 * pk["bf16_tflops"]
         qt_flat = qt_np.ravel()
         # algorithmic bytes of the BM25 filter pass: ONE pass over the shard's index per batch
-        # (packed postings 8 B + dense head columns 8 B/doc/term); without sharing every query would
-        # pull sum_t df(t) * 12 B on its own (SURVEY.md 8d's per-query figure)
-        index_bytes = bm.n_postings * 8 + (bm.head_imp.numel() * 8 if bm.n_head else 0)
+        # (packed postings 8 B + dense float16 head columns 2 B/doc/term); without sharing every query
+        # would pull sum_t df(t) * 12 B on its own (SURVEY.md 8d's per-query figure)
+        index_bytes = bm.n_postings * 8 + (bm.head_imp.numel() * 2 if bm.n_head else 0)
+        qt_valid = torch.from_numpy(qt_flat[qt_flat >= 0].astype(np.int64)).to(dev)
+        head_tok = float((bm.head_slot[qt_valid] >= 0).sum().item()) / nq if bm.n_head else 0.0  # head tokens per query
         ttp = bm.tile_term_ptr
         df_local = (ttp[:, 1:] - ttp[:, :-1]).sum(dim=0)
         unshared_bytes = float(df_local[torch.from_numpy(qt_flat[qt_flat >= 0].astype(np.int64)).to(dev)].sum().item()) * 12.0
@@ -898,12 +900,12 @@ def run_gpu_arm(args) -> None:
             "algorithmic_bytes_without_batch_sharing": unshared_bytes,
             "achieved_without_batch_sharing_GBs": unshared_bytes / (b_filter * 1e-3) / 1e9,
             "note": "one pass over the index serves the whole batch (SURVEY.md 8d asks for both accountings); the "
-                    "kernel's own limiter is shared-memory bandwidth: per (query, document) 4 B of tail accumulator "
-                    "zeroed + 4 B read + 4 B per head token",
+                    "kernel's own limiter is latency at 6 warps per scheduler, then shared memory: per (query, document) "
+                    "4 B of tail accumulator zeroed + 4 B read + 2 B per head token",
             "smem_view": None if not pk.get("smem_tbs") else {
-                "bytes_per_launch": float(nq) * n_local * (8.0 + 4.0 * 2.65),
-                "achieved_TBs": float(nq) * n_local * (8.0 + 4.0 * 2.65) / (b_filter * 1e-3) / 1e12,
-                "peak_TBs": pk["smem_tbs"], "frac": float(nq) * n_local * (8.0 + 4.0 * 2.65) / (b_filter * 1e-3) / 1e12 / pk["smem_tbs"]}}
+                "bytes_per_launch": float(nq) * n_local * (8.0 + 2.0 * head_tok),
+                "achieved_TBs": float(nq) * n_local * (8.0 + 2.0 * head_tok) / (b_filter * 1e-3) / 1e12,
+                "peak_TBs": pk["smem_tbs"], "frac": float(nq) * n_local * (8.0 + 2.0 * head_tok) / (b_filter * 1e-3) / 1e12 / pk["smem_tbs"]}}
         c_bytes = float(nq) * cand_k * dim * 4 + nq * dim * 4
         rs_roof = {"kernel": "rescore_ring_kernel (candidate rows bulk-copied into a shared-memory ring)", "bound": "hbm",
                    "traffic": _traffic("rescore_ring_kernel_f32", f"{nq}x{cand_k}x{dim}"),

@@ -217,15 +217,18 @@ int rr_bm25_topk(const int64_t* tile_term_ptr, const uint32_t* post_row,
  * document) against a sampled bound keep a few hundred candidates per query, whose float64
  * scores are then recomputed in the reference's operation order.  Needs, on top of the
  * rr_bm25_topk index: rows ASCENDING inside every (tile, term) segment, tile_docs a multiple of
- * 128 and <= 1024, every impact finite and in [2^-100, 2^100], and for the n_head <= 32 terms
+ * 128 and <= 1024, every impact finite and in [2^-100, 2^100], and for the n_head <= 64 terms
  * chosen as "head" terms
  *   post_pack u64 [P]                        per posting, in post_row order: row-in-tile << 32 |
  *                                            round(impact * 2^fx_shift) as u32; fx_shift chosen so
  *                                            that 64 * max impact * 2^fx_shift <= 2^30
- *   head_max  f32 [n_head]                   upper bound of the term's float32 impact over all docs
+ *   head_max  f32 [n_head]                   upper bound of the term's FLOAT16-rounded impact over all docs
  *   head_slot i32 [n_terms]                  slot of the term, -1 for all other terms
  *   head_imp  f64 [n_tiles, n_head, tile_docs] the term's impact per document of the tile,
- *                                            0.0 where the document lacks the term
+ *                                            0.0 where the document lacks the term (read by the refine)
+ *   head_imp_f16 f16 [n_tiles, n_head, tile_docs] the same values rounded to float16 (every value
+ *                                            finite, i.e. < 65504; 16-byte aligned): what the filter
+ *                                            stages into shared memory
  * (head terms keep their sparse postings too).
  * inexact_flags u8 [q] or NULL: 1 for a query whose exactness check failed (candidate list
  * overflow, or the k-th candidate score does not clear the bound) - its output row is NOT
@@ -238,8 +241,8 @@ size_t rr_bm25_fast_workspace_bytes(int32_t n_tiles, int32_t tile_docs, int64_t 
 int rr_bm25_fast_max_head(int32_t tile_docs);
 int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* post_row,
                       const double* post_impact, const uint64_t* post_pack, int32_t fx_shift,
-                      const int32_t* head_slot, const double* head_imp, const float* head_max,
-                      int32_t n_head, int32_t n_tiles, int32_t tile_docs, int32_t n_terms,
+                      const int32_t* head_slot, const double* head_imp, const void* head_imp_f16,
+                      const float* head_max, int32_t n_head, int32_t n_tiles, int32_t tile_docs, int32_t n_terms,
                       int64_t n_docs, const int32_t* q_terms, int32_t q, int32_t q_len, int32_t k,
                       int64_t row_base, double* out_score, int64_t* out_idx, int32_t* out_count,
                       uint8_t* inexact_flags, uint32_t* inexact_counter, void* workspace,

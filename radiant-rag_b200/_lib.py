@@ -65,7 +65,7 @@ PROTOTYPES = {
     "rr_bm25_topk": (_i32, [_p, _p, _p, _i32, _i32, _i32, _i64, _p, _i32, _i32, _i32, _i64, _p, _p, _p, _p, _sz, _p]),
     "rr_bm25_fast_workspace_bytes": (_sz, [_i32, _i32, _i64, _i32, _i32]),
     "rr_bm25_fast_max_head": (_i32, [_i32]),
-    "rr_bm25_topk_fast": (_i32, [_p, _p, _p, _p, _i32, _p, _p, _p, _i32, _i32, _i32, _i32, _i64, _p, _i32, _i32, _i32, _i64,
+    "rr_bm25_topk_fast": (_i32, [_p, _p, _p, _p, _i32, _p, _p, _p, _p, _i32, _i32, _i32, _i32, _i64, _p, _i32, _i32, _i32, _i64,
                                  _p, _p, _p, _p, _p, _p, _sz, _p]),
     "rr_bm25_timing": (_i32, [_i32]),
     "rr_bm25_last_timing_ms": (_i32, [_p]),

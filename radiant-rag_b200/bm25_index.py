@@ -83,7 +83,7 @@ class Bm25DeviceIndex:
     FAST_MIN_DOCS = 65_536   # below this the exact kernel alone is as fast (few tiles)
     FAST_MAX_TILE = 1024
     FAST_MAX_QLEN = 64       # tokens per query the fixed-point filter sums have headroom for
-    MAX_HEAD = 32
+    MAX_HEAD = 64
     MAX_TABLE_BYTES = 8 << 30  # [n_tiles, n_terms+1] int64 offset table
 
     def __init__(self, device: torch.device, n_docs: int, n_terms: int, tile_docs: int,
@@ -106,6 +106,8 @@ class Bm25DeviceIndex:
         self.row_base = row_base
         self.head_slot = head_slot
         self.head_imp = head_imp
+        self.head_imp_h = (head_imp.to(torch.float16).contiguous()
+                           if head_imp is not None and head_imp.numel() else None)
         self.post_pack = post_pack
         self.head_max = head_max
         self.fx_shift = int(fx_shift)
@@ -137,7 +139,7 @@ class Bm25DeviceIndex:
         row_base: int = 0,
         doc_len=None,
         bank_interleave: bool = False,
-        head_terms: int = 32,
+        head_terms: int = 64,
         sharded: bool = False,
         group: Any = None,
         chunk_docs: int = 2_000_000,
@@ -284,7 +286,7 @@ class Bm25DeviceIndex:
         cls = type(self)
         dev, n_post, tile_docs = self.device, int(self.post_row.numel()), self.tile_docs
         self.fast_ok = False
-        self.post_pack = self.head_imp = self.head_max = None
+        self.post_pack = self.head_imp = self.head_max = self.head_imp_h = None
         self.fx_shift = 0
         if not getattr(self, "_fast_layout", False) or n_post == 0:
             return
@@ -316,13 +318,17 @@ class Bm25DeviceIndex:
                 del slot, sel, rs, pos
             del r64
         if n_head:
-            hm64 = head_imp.amax(dim=(0, 2))
-            hm32 = hm64.to(torch.float32)
-            head_max = torch.where(hm32.to(torch.float64) < hm64,
-                                   torch.nextafter(hm32, torch.full_like(hm32, float("inf"))), hm32).contiguous()
+            # the filter reads the head impacts as float16 (half the shared memory per column, so
+            # twice the head terms); the refine reads the float64 ones
+            if float(head_imp.max()) >= 60000.0:
+                return
+            head_imp_h = head_imp.to(torch.float16).contiguous()
+            head_max = head_imp_h.amax(dim=(0, 2)).to(torch.float32).contiguous()  # bounds what the filter adds
         else:
             head_imp = head_imp[:, :0, :].contiguous()
+            head_imp_h = torch.zeros(8, dtype=torch.float16, device=dev)
             head_max = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.head_imp_h = head_imp_h
         self.post_pack, self.head_imp, self.head_max, self.fx_shift, self.fast_ok = post_pack, head_imp, head_max, fx_shift, True
 
     def refresh(self, idf, avgdl: float, k1: float, b: float) -> None:
@@ -400,6 +406,7 @@ class Bm25DeviceIndex:
         _lib.call("rr_bm25_topk_fast", self.tile_term_ptr.data_ptr(), self.post_row.data_ptr(),
                   self.post_impact.data_ptr(), self.post_pack.data_ptr(), self.fx_shift,
                   self.head_slot.data_ptr(), self.head_imp.data_ptr() if self.n_head else None,
+                  self.head_imp_h.data_ptr() if self.n_head else None,
                   self.head_max.data_ptr(), self.n_head, self.n_tiles,
                   self.tile_docs, self.n_terms, self.n_docs, qt.data_ptr(), q, ql, k, self.row_base,
                   score.data_ptr(), idx.data_ptr(), count.data_ptr(), flags.data_ptr(), counter.data_ptr(),

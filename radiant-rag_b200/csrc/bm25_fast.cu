@@ -26,9 +26,10 @@
 //
 // Exactness.  All impacts are positive.  Tail impacts enter the filter score as fixed-point integers
 // (round(impact * 2^s), accumulated with native integer shared-memory atomics), head impacts as
-// float32, so |A - E| <= eps * E + eps_abs with eps = (q_len + 4) * 2^-24 and
-// eps_abs = (q_len + 1) * 2^-(s+1) for the filter score A and the reference's float64 score E of any
-// document.  A document outside the survivor list has A < tau, hence E < tau * (1 + eps) + eps_abs.
+// FLOAT16 (twice as many head columns fit in shared memory, and the 30 terms that follow the first 30
+// carry half of the remaining postings under Zipf), summed in float32, so |A - E| <= eps * E + eps_abs
+// with eps = (q_len + 4) * 2^-24 + 2^-10 and eps_abs = (q_len + 1) * 2^-(s+1) + q_len * 2^-24 for the
+// filter score A and the reference's float64 score E of any document.  A document outside the survivor list has A < tau, hence E < tau * (1 + eps) + eps_abs.
 // If the k-th exact score among the survivors exceeds that, no outside document can enter or tie
 // the top-k and the result is the reference's, bit for bit.  The refine kernel CHECKS this per query (and list overflow); a query
 // that fails is flagged and counted, and the caller redoes it with rr_bm25_topk.  Impacts
@@ -38,6 +39,8 @@
 // query without sharing: sum_t df(t) * 12 B (SURVEY.md 8d reports both).
 #include <math.h>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "select.cuh"
 #include "tau.cuh"
@@ -45,11 +48,11 @@
 namespace rr {
 
 #ifndef RR_BF_WARPS
-#define RR_BF_WARPS 24
+#define RR_BF_WARPS 32
 #endif
 constexpr int BF_WARPS = RR_BF_WARPS;  // one query per warp; more resident warps = more posting loads in flight
 constexpr int BF_THREADS = BF_WARPS * 32;
-constexpr int BF_MAX_HEAD = 32;
+constexpr int BF_MAX_HEAD = 64;   // head slot h lives on lane h & 31 (two counters per lane)
 constexpr int BF_MAX_TILE = 1024;
 #ifndef RR_BF_INFLIGHT
 #define RR_BF_INFLIGHT 12
@@ -64,7 +67,8 @@ struct BfArgs {
   float fx_inv;             // 2^-fx_shift
   float fx_scale;           // 2^fx_shift
   const int* head_slot;    // [n_terms] slot of a head term, -1 for tail terms
-  const double* head_imp;  // [n_tiles][n_head][tile_docs] dense float64 impacts, 0 = absent
+  const double* head_imp;  // [n_tiles][n_head][tile_docs] dense float64 impacts, 0 = absent (refine)
+  const __half* head_imp_h;  // the same rounded to float16: what the filter stages into shared memory
   int n_head;
   int n_tiles;
   int tile_docs;
@@ -118,7 +122,7 @@ template <bool SAMPLE>
 __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a) {
   extern __shared__ __align__(16) unsigned char bf_smem[];
   const int T = a.tile_docs;
-  float* cols = reinterpret_cast<float*>(bf_smem);                           // [n_head][T]
+  __half* cols = reinterpret_cast<__half*>(bf_smem);                         // [n_head][T] float16 head impacts
   u32* tacc_all = reinterpret_cast<u32*>(cols + (size_t)a.n_head * T);       // [BF_WARPS][T] fixed-point tail sums
   __shared__ int s_excl[BF_WARPS][34];         // compacted tail tokens: first flat index, then 2 sentinels
   __shared__ long long s_base[BF_WARPS][32];   // first posting of the segment minus its first flat index
@@ -126,7 +130,8 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
   u32* tacc = tacc_all + (size_t)warp * T;
   const int t4 = T >> 2;  // 16-byte groups per column
   const float inv = a.fx_inv;
-  const float hmax = (lane < a.n_head) ? __ldg(a.head_max + lane) : 0.0f;
+  const float hmax = (lane < a.n_head) ? __ldg(a.head_max + lane) : 0.0f;            // slot lane
+  const float hmax_hi = (32 + lane < a.n_head) ? __ldg(a.head_max + 32 + lane) : 0.0f;  // slot 32 + lane
 
   for (int w = blockIdx.x; w < a.n_pass_tiles * a.q_groups; w += gridDim.x) {
     const int pt = w / a.q_groups;
@@ -138,13 +143,10 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
     const int rows_here = (int)min((long long)T, a.n_docs - tile_lo);
     __syncthreads();  // every warp is done with the previous tile's columns
     {
-      const double2* src = reinterpret_cast<const double2*>(a.head_imp + (size_t)tile * a.n_head * T);
-      float2* dst = reinterpret_cast<float2*>(cols);
-      const int n2 = (a.n_head * T) >> 1;
-      for (int i = threadIdx.x; i < n2; i += BF_THREADS) {
-        const double2 v = __ldg(src + i);
-        dst[i] = make_float2((float)v.x, (float)v.y);
-      }
+      const uint4* src = reinterpret_cast<const uint4*>(a.head_imp_h + (size_t)tile * a.n_head * T);
+      uint4* dst = reinterpret_cast<uint4*>(cols);
+      const int n16 = (a.n_head * T) >> 3;  // T is a multiple of 128
+      for (int i = threadIdx.x; i < n16; i += BF_THREADS) dst[i] = __ldg(src + i);
     }
     __syncthreads();
     const long long* ptr = a.tile_term_ptr + (size_t)tile * (a.n_terms + 1);
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
       float tau = 0.0f;
       if (!SAMPLE) tau = __ldg(a.tau + qi);
 
-      int head_cnt = 0;  // lane h: multiplicity of head slot h in this query
+      int head_cnt = 0, head_cnt_hi = 0;  // lane l: multiplicity of head slots l and 32 + l in this query
       bool sparse = false;
       float uq = 0.0f;
       u32 thr_fx = 0u;  // fixed-point tail sum a document needs before its head terms can matter
@@ -194,14 +196,19 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
           const int src = __ffs(hm) - 1;
           hm &= hm - 1;
           const int h = __shfl_sync(0xffffffffu, ti.hs, src);
-          if (lane == h) ++head_cnt;
+          if (lane == (h & 31)) {
+            if (h < 32)
+              ++head_cnt;
+            else
+              ++head_cnt_hi;
+          }
         }
         if (!SAMPLE && a.q_len <= 32) {
           // The head terms of a query add at most uq to any document (their largest impact anywhere).
           // When that alone cannot reach the bound (the usual case: frequent terms carry little
           // idf), the head columns are only read for the 16-document groups whose tail sums come
           // within uq of it.
-          uq = bf_warp_sum((float)head_cnt * hmax) * 1.000002f;
+          uq = bf_warp_sum(fmaf((float)head_cnt_hi, hmax_hi, (float)head_cnt * hmax)) * 1.000002f;
           sparse = tau > 0.0f && uq < tau * 0.999998f;
           if (sparse) thr_fx = (u32)fminf((tau * 0.999998f - uq) * a.fx_scale * 0.99999f, 4.0e9f);
         }
@@ -261,8 +268,9 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
       __syncwarp();
 
       // dense pass: scores of the documents this lane owns (tail sum + head columns), 16 documents
-      // at a time: four float4 accumulators keep the register count low enough for 24 resident warps
+      // at a time: four float4 accumulators keep the register count low enough for 32 resident warps (<= 64 registers)
       const unsigned hmask = __ballot_sync(0xffffffffu, head_cnt > 0);
+      const unsigned hmask_hi = __ballot_sync(0xffffffffu, head_cnt_hi > 0);
       float lmax = 0.0f;
       for (int hb = 0; hb < t4; hb += 128) {
         uint4 tv[4];
@@ -275,7 +283,6 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
             reinterpret_cast<uint4*>(tacc)[v] = make_uint4(0u, 0u, 0u, 0u);  // clean for the next query
           }
         }
-        unsigned hm = hmask;
         if (!SAMPLE && sparse) {
           // integer test on the raw sums: no document of this group can reach the bound
           bool hit = false;
@@ -289,19 +296,25 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
         for (int i = 0; i < 4; ++i)
           acc[i] = make_float4(__uint2float_rn(tv[i].x) * inv, __uint2float_rn(tv[i].y) * inv,
                                __uint2float_rn(tv[i].z) * inv, __uint2float_rn(tv[i].w) * inv);
-        while (hm) {
-          const int h = __ffs(hm) - 1;
-          hm &= hm - 1;
-          const float c = (float)__shfl_sync(0xffffffffu, head_cnt, h);
-          const float4* cp = reinterpret_cast<const float4*>(cols + (size_t)h * T) + hb + lane;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (hb + i * 32 + lane < t4) {
-              const float4 x = cp[i * 32];
-              acc[i].x = fmaf(c, x.x, acc[i].x);
-              acc[i].y = fmaf(c, x.y, acc[i].y);
-              acc[i].z = fmaf(c, x.z, acc[i].z);
-              acc[i].w = fmaf(c, x.w, acc[i].w);
+        for (int part = 0; part < 2; ++part) {
+          unsigned hm = part ? hmask_hi : hmask;
+          while (hm) {
+            const int hl = __ffs(hm) - 1;
+            hm &= hm - 1;
+            const float c = (float)__shfl_sync(0xffffffffu, part ? head_cnt_hi : head_cnt, hl);
+            const uint2* cp = reinterpret_cast<const uint2*>(cols + (size_t)(32 * part + hl) * T) + hb + lane;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (hb + i * 32 + lane < t4) {
+                const uint2 xx = cp[i * 32];  // four float16 impacts: documents 4v .. 4v + 3
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&xx.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&xx.y));
+                acc[i].x = fmaf(c, lo.x, acc[i].x);
+                acc[i].y = fmaf(c, lo.y, acc[i].y);
+                acc[i].z = fmaf(c, hi.x, acc[i].z);
+                acc[i].w = fmaf(c, hi.y, acc[i].w);
+              }
             }
           }
         }
@@ -511,7 +524,7 @@ __global__ void __launch_bounds__(BR_THREADS) bm25_refine_kernel(const BrArgs a)
 // head columns + one tail accumulator per warp + the static arrays must fit the 227 KB a CTA may use
 static inline int bf_max_head(int tile_docs) {
   const long long avail = 232448LL - (long long)BF_WARPS * (34 * 4 + 32 * 8) - 1024 - (long long)BF_WARPS * tile_docs * 4;
-  long long h = avail / ((long long)tile_docs * 4);
+  long long h = avail / ((long long)tile_docs * 2);  // float16 columns
   if (h > BF_MAX_HEAD) h = BF_MAX_HEAD;
   return h < 0 ? 0 : (int)h;
 }
@@ -617,8 +630,8 @@ extern "C" size_t rr_bm25_fast_workspace_bytes(int32_t n_tiles, int32_t tile_doc
 extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* post_row,
                                  const double* post_impact, const uint64_t* post_pack,
                                  int32_t fx_shift, const int32_t* head_slot,
-                                 const double* head_imp, const float* head_max, int32_t n_head,
-                                 int32_t n_tiles,
+                                 const double* head_imp, const void* head_imp_f16, const float* head_max,
+                                 int32_t n_head, int32_t n_tiles,
                                  int32_t tile_docs, int32_t n_terms, int64_t n_docs,
                                  const int32_t* q_terms, int32_t q, int32_t q_len, int32_t k,
                                  int64_t row_base, double* out_score, int64_t* out_idx,
@@ -632,8 +645,9 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   RR_CHECK_ARG(k >= 1 && k <= RR_MAX_K, "k out of range");
   RR_CHECK_ARG(tile_docs >= 128 && tile_docs <= BF_MAX_TILE && tile_docs % 128 == 0,
                "tile_docs must be a multiple of 128 in [128, 1024]");
-  RR_CHECK_ARG(n_head >= 0 && n_head <= BF_MAX_HEAD, "n_head must be in [0, 32]");
-  RR_CHECK_ARG(n_head == 0 || (head_imp && head_max), "head_imp / head_max is null");
+  RR_CHECK_ARG(n_head >= 0 && n_head <= BF_MAX_HEAD, "n_head must be in [0, 64]");
+  RR_CHECK_ARG(n_head == 0 || (head_imp && head_imp_f16 && head_max), "head_imp / head_imp_f16 / head_max is null");
+  RR_CHECK_ARG(((uintptr_t)head_imp_f16 & 15) == 0, "head_imp_f16 must be 16-byte aligned");
   RR_CHECK_ARG(fx_shift >= 0 && fx_shift <= 60, "fx_shift out of range");
   RR_CHECK_ARG(q_len <= 64, "rr_bm25_topk_fast takes at most 64 tokens per query (fixed-point headroom)");
   RR_CHECK_ARG((long long)n_tiles * tile_docs >= n_docs, "tiles do not cover n_docs");
@@ -656,6 +670,7 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   a.fx_scale = (float)ldexp(1.0, fx_shift);
   a.head_slot = head_slot;
   a.head_imp = head_imp;
+  a.head_imp_h = reinterpret_cast<const __half*>(head_imp_f16);
   a.n_head = n_head;
   a.n_tiles = n_tiles;
   a.tile_docs = tile_docs;
@@ -669,7 +684,7 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   a.list_cnt = (u32*)(ws + l.list_cnt);
   a.list = (u64*)(ws + l.list);
   a.cap = cap;
-  const size_t smem = ((size_t)n_head + BF_WARPS) * tile_docs * 4;
+  const size_t smem = (size_t)n_head * tile_docs * 2 + (size_t)BF_WARPS * tile_docs * 4;
   RR_CHECK_ARG(n_head <= bf_max_head(tile_docs), "too many head columns for this tile size (rr_bm25_fast_max_head)");
   int sms = sm_count();
   if (sms <= 0) sms = 148;
@@ -728,8 +743,10 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   if (r.chunk > 256) r.chunk = 256;
   if (r.chunk < 1) r.chunk = 1;
   r.row_base = row_base;
-  r.eps = (double)(q_len + 4) * 5.9604644775390625e-08;  // (q_len + 4) * 2^-24
-  r.eps_abs = (double)(q_len + 1) * ldexp(1.0, -(fx_shift + 1));
+  // float32 arithmetic: (q_len + 4) * 2^-24; float16 head impacts: each within 2^-11 (1 + 2^-12) of
+  // the float64 value, or within 2^-25 absolutely when subnormal - 2^-10 relative bounds the sum
+  r.eps = (double)(q_len + 4) * 5.9604644775390625e-08 + (n_head > 0 ? 9.765625e-04 : 0.0);
+  r.eps_abs = (double)(q_len + 1) * ldexp(1.0, -(fx_shift + 1)) + (n_head > 0 ? (double)q_len * ldexp(1.0, -24) : 0.0);
   r.out_score = out_score;
   r.out_idx = (long long*)out_idx;
   r.out_count = out_count;

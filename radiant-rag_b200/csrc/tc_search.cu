@@ -20,9 +20,8 @@
 //                 double-buffered against the epilogue.
 //   warps 2-5,    epilogue, two warps per TMEM lane quarter (64 query columns each):
 //   10-13         tcgen05.ld 32x32b.x32 brings a thread's row of 32 query scores to registers.
-//                 Filter mode: a hit is a clear sign bit of score - tau_q; hits are appended to
-//                 the query's list.  (What paces the kernel is tensor-memory load/store bandwidth:
-//                 the unpackers' A-operand stores plus these accumulator reads.)
+//                 Filter mode: the accumulators start at -tau_q (written by these warps), so a
+//                 hit is a clear sign bit; hits are appended to the query's list.
 // Exact top-k without materialising Q x N scores (164 GB in config 4):
 //   pass 0  (EPI_COLMAX) the same kernel over a strided sample of row tiles keeps the best score
 //           per (CTA, row slot, query); tc_tau_kernel takes a score tau_q that at least k of
@@ -182,8 +181,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp >= 2 && warp < 6) {
     const int t = threadIdx.x - 64;  // 0..127
     const int qq = q0 + t;
-    // tau_eff per query column (0 in the dense / sample modes, unreachable for padding columns)
-    thr[t] = EPI != EPI_FILTER ? 0 : (qq < a.q ? tc_tau_eff(a.tau[qq]) : (1 << 30));
+    // bias = -tau_eff: 0 in dense mode (plain scores), far negative for padding columns
+    thr[t] = EPI != EPI_FILTER ? 0 : (qq < a.q ? -tc_tau_eff(a.tau[qq]) : -(1 << 30));
     s_cnt[t] = 0;
   }
   tc_fence_before();
@@ -236,7 +235,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     u32 stage = 0, phase = 0, tcount = 0;
     for (long long i = blockIdx.x; i < a.n_tiles; i += gridDim.x, ++tcount) {
       const u32 as = tcount & 1u;
-      tc_mbar_wait(tc_smem(tmem_empty + as), ((tcount >> 1) & 1u) ^ 1u);  // the epilogue has read this accumulator
+      tc_mbar_wait(tc_smem(tmem_empty + as), (tcount >> 1) & 1u);  // read by the epilogue and re-biased
       tc_fence_after();
       const u32 d_tmem = tmem_base + as * TC_BN;
       if (a.packed) {
@@ -251,7 +250,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             for (int j = 0; j < TC_KBPS; ++j) {
               if (kb + j < a.kb) {
                 const u64 bdj = bd + (u64)(j * (TC_TILE_BYTES >> 4));
-                tc_mma_i8_ts_elect(d_tmem, a_tmem + 32 * j, bdj, TC_IDESC_UA, (kb + j) > 0 ? 1u : 0u);  // the tile's first MMA overwrites
+                tc_mma_i8_ts_elect(d_tmem, a_tmem + 32 * j, bdj, TC_IDESC_UA, 1u);
                 tc_mma_i8_ts_elect(d_tmem, a_tmem + 32 * j + 8, bdj + 2, TC_IDESC_UA, 1u);
                 tc_mma_i8_ts_elect(d_tmem, a_tmem + 32 * j + 16, bdj + 4, TC_IDESC_UA, 1u);
                 tc_mma_i8_ts_elect(d_tmem, a_tmem + 32 * j + 24, bdj + 6, TC_IDESC_UA, 1u);
@@ -270,7 +269,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           tc_fence_after();
           const u64 ad = adesc0 + (u64)(stage * (TC_TILE_BYTES >> 4));
           const u64 bd = bdesc0 + (u64)(kb * (TC_TILE_BYTES >> 4));
-          tc_mma_i8_ss_elect(d_tmem, ad, bd, TC_IDESC, kb > 0 ? 1u : 0u);  // the tile's first MMA overwrites
+          tc_mma_i8_ss_elect(d_tmem, ad, bd, TC_IDESC, 1u);
           tc_mma_i8_ss_elect(d_tmem, ad + 2, bd + 2, TC_IDESC, 1u);
           tc_mma_i8_ss_elect(d_tmem, ad + 4, bd + 4, TC_IDESC, 1u);
           tc_mma_i8_ss_elect(d_tmem, ad + 6, bd + 6, TC_IDESC, 1u);
@@ -287,14 +286,50 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // ===================== epilogue (warps 2..5 and the last four) =====================
     // Two warps share a TMEM lane quarter and split the 128 query columns between them: a
     // single warp's dependent-issue latency is what paces this role.
-    // Filter mode: "score >= tau" is the sign bit of score - tau_j (thresholds read from shared
-    // memory as int4, a subtract and a funnel shift per column collect the hit mask).  An earlier
-    // version pre-loaded the accumulators with -tau_j through tcgen05.st to save the subtract: that
-    // cost 64 KB of tensor-memory stores per tile, and tensor-memory load/store bandwidth - the A
-    // operand stores of the unpackers plus these reads - is what paces this kernel, not the MMAs.
+    // Filter mode keeps the compare out of the instruction stream: the accumulator of query
+    // column j starts at -tau_j instead of 0 (the epilogue warps write that bias into tensor
+    // memory with tcgen05.st right after they have read a tile, the MMAs always accumulate),
+    // so "score >= tau" is the sign bit of the accumulator and a funnel shift per column
+    // collects the hit mask.
+    // (Measured alternative: no bias stores, the first MMA of a tile overwrites and the epilogue
+    // subtracts tau_j from every score - 64 KB of tensor-memory stores per tile less, but 5 % slower.
+    // What paces the kernel is the accumulator read-out)
     const int lq = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) .. +31
     const int half = warp < 6 ? 0 : 1 + (warp - (6 + 4 * TC_UNPACK_GROUPS)) / 4;
     const int c0 = half * TC_EPI_CHUNKS;  // first column chunk of this warp
+    // (the biases are re-read from shared memory for every store: this role has slack, and
+    // keeping them out of registers lets the kernel run more unpack warps)
+    auto store_bias = [&](u32 as) {
+#pragma unroll
+      for (int cc = 0; cc < TC_EPI_CHUNKS; ++cc) {
+        const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + as * TC_BN + (c0 + cc) * 32;
+        u32 o[32];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int4 tv = reinterpret_cast<const int4*>(thr + (c0 + cc) * 32)[j4];  // thr[] holds the biases
+          o[4 * j4 + 0] = (u32)tv.x;
+          o[4 * j4 + 1] = (u32)tv.y;
+          o[4 * j4 + 2] = (u32)tv.z;
+          o[4 * j4 + 3] = (u32)tv.w;
+        }
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+            "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+            "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+            ::"r"(taddr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]),
+              "r"(o[8]), "r"(o[9]), "r"(o[10]), "r"(o[11]), "r"(o[12]), "r"(o[13]), "r"(o[14]), "r"(o[15]),
+              "r"(o[16]), "r"(o[17]), "r"(o[18]), "r"(o[19]), "r"(o[20]), "r"(o[21]), "r"(o[22]), "r"(o[23]),
+              "r"(o[24]), "r"(o[25]), "r"(o[26]), "r"(o[27]), "r"(o[28]), "r"(o[29]), "r"(o[30]), "r"(o[31])
+            : "memory");
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    };
+    // both accumulators start biased; each arrival below is "read and re-biased"
+    for (u32 as = 0; as < 2; ++as) {
+      store_bias(as);
+      tc_fence_before();
+      tc_mbar_arrive(tc_smem(tmem_empty + as));
+    }
     // sample pass: best score seen by this thread's row slot, per query column (a slot sees one
     // row of every tile the CTA takes, so the slots partition the sampled rows)
     int colmax[EPI == EPI_COLMAX ? TC_EPI_CHUNKS * 32 : 1];
@@ -313,7 +348,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (!(a.debug & 4)) {
 #pragma unroll
         for (int cc = 0; cc < TC_EPI_CHUNKS; ++cc) {
-          if ((a.debug & 8) && cc > 0) break;  // timing experiment: read half of the accumulator
           const int c = c0 + cc;
           u32 v[32];
           const u32 taddr = tmem_base + ((u32)(lq * 32) << 16) + as * TC_BN + c * 32;
@@ -344,19 +378,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             // quarter alone, so dependent-issue latency, not throughput, is what it pays):
             // bit 7-i of m[g] = sign of column 8g+i (1 = below the bound)
             u32 m[4] = {0, 0, 0, 0};
-            int tj[32];
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const int4 tv = reinterpret_cast<const int4*>(thr + c * 32)[j4];
-              tj[4 * j4 + 0] = tv.x;
-              tj[4 * j4 + 1] = tv.y;
-              tj[4 * j4 + 2] = tv.z;
-              tj[4 * j4 + 3] = tv.w;
-            }
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) m[g] = __funnelshift_l(v[8 * g + jj] - (u32)tj[8 * g + jj], m[g], 1);
+              for (int g = 0; g < 4; ++g) m[g] = __funnelshift_l(v[8 * g + jj], m[g], 1);
             }
             // byte g of `miss` = m[g]; hit bit 8g + (7-i) <-> column 8g + i
             const u32 miss = m[0] | (m[1] << 8) | (m[2] << 16) | (m[3] << 24);
@@ -375,7 +400,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
               for (int x = 0; x < 4; ++x) t4[x] = (j & 4) ? t8[2 * x + 1] : t8[2 * x];
 #pragma unroll
               for (int x = 0; x < 2; ++x) t2[x] = (j & 8) ? t4[2 * x + 1] : t4[2 * x];
-              const int s = (int)((j & 16) ? t2[1] : t2[0]) - thr[c * 32 + j];
+              const int s = (int)((j & 16) ? t2[1] : t2[0]);
               const u32 slot = atomicAdd(s_cnt + c * 32 + j, 1u);  // shared-memory counter
               if (slot < (u32)a.cap_cta) {
                 const size_t o = ((size_t)(q0 + c * 32 + j) * gridDim.x + blockIdx.x) * a.cap_cta + slot;
@@ -386,6 +411,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           }
         }
       }
+      store_bias(as);
       tc_fence_before();
       tc_mbar_arrive(tc_smem(tmem_empty + as));
     }

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BM25 at BASELINE config 3 (1M docs, 1024 queries x 8 tokens, top-100) on one GPU: per-kernel
 CUDA-event times of the batched path, the exact kernel's time on a sub-batch, for profiling runs
-(ncu -k regex:bm25_) and tuning.  usage: bm25_probe.py [n_docs] [n_queries] [reps] [tile_docs]"""
+(ncu -k regex:bm25_) and tuning.  usage: bm25_probe.py [n_docs] [n_queries] [reps] [tile_docs] [head_terms]"""
 import ctypes as C
 import json
 import sys
@@ -20,9 +20,10 @@ def main():
     nq = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
     tile = int(sys.argv[4]) if len(sys.argv) > 4 else 1024
+    head_terms = int(sys.argv[5]) if len(sys.argv) > 5 else 64
     v, seed = 50_000, 2
     ptr, toks = synth_zipf_corpus_device(n_docs, v, seed, 200, device=0)
-    bm = Bm25DeviceIndex.build(ptr, toks, v, None, None, 1.5, 0.75, device=0, tile_docs=tile)
+    bm = Bm25DeviceIndex.build(ptr, toks, v, None, None, 1.5, 0.75, device=0, tile_docs=tile, head_terms=head_terms)
     bm.fast_min_docs = 0
     del ptr, toks
     qt = torch.from_numpy(synthetic.zipf_queries(nq, 8, v, seed)).cuda()
