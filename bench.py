@@ -900,7 +900,7 @@ def run_gpu_arm(args) -> None:
             "algorithmic_bytes_without_batch_sharing": unshared_bytes,
             "achieved_without_batch_sharing_GBs": unshared_bytes / (b_filter * 1e-3) / 1e9,
             "note": "one pass over the index serves the whole batch (SURVEY.md 8d asks for both accountings); the "
-                    "kernel's own limiter is latency at 6 warps per scheduler, then shared memory: per (query, document) "
+                    "kernel's own limiter is the latency of each warp's dependent chain at 8 warps per scheduler, then shared memory: per (query, document) "
                     "4 B of tail accumulator zeroed + 4 B read + 2 B per head token",
             "smem_view": None if not pk.get("smem_tbs") else {
                 "bytes_per_launch": float(nq) * n_local * (8.0 + 2.0 * head_tok),

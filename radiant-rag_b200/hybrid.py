@@ -64,7 +64,7 @@ class HybridSearch:
 
     def __init__(self, dense: DenseIndex, bm25: Any, group: Optional[Any] = None,
                  rescore_multiplier: float = 4.0, prefer_int8: bool = True,
-                 dense_mode: str = "quantized", comm: Optional[Any] = None, overlap: bool = False,
+                 dense_mode: str = "quantized", comm: Optional[Any] = None, overlap: bool = True,
                  comm_sparse: Optional[Any] = None) -> None:
         """comm: an ``nccl.NcclComm`` over the same ranks - the candidate exchanges are then issued on
         the current stream, which lets ``GraphedHybridSearch`` capture the WHOLE sharded step (kernels

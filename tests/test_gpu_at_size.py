@@ -102,7 +102,7 @@ def test_config3_hybrid_top10_vs_oracle(config3):
     c = config3
     if "orc" not in c:
         pytest.skip("needs the oracle built by the BM25 test")
-    hybrid = HybridSearch(c["index"], c["bm"], rescore_multiplier=4.0, prefer_int8=False)
+    hybrid = HybridSearch(c["index"], c["bm"], rescore_multiplier=4.0, prefer_int8=False, overlap=False)
     qt_d = torch.from_numpy(c["qt"]).cuda()
     res = hybrid.search_batch(c["queries"], qt_d, top_k=10, dense_top_k=100, bm25_top_k=100, rrf_k=60)
     torch.cuda.synchronize()
