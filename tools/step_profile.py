@@ -30,7 +30,7 @@ def main():
     del ptr, toks
     queries = synth_query_rows_device(0, nq, dim, seed, n)
     qt = torch.from_numpy(synthetic.zipf_queries(nq, 8, v, seed)).cuda()
-    hybrid = HybridSearch(index, bm, rescore_multiplier=4.0, prefer_int8=False)
+    hybrid = HybridSearch(index, bm, rescore_multiplier=4.0, prefer_int8=False, overlap=False)  # one stream: a stable launch order for --launch-skip
     torch.cuda.synchronize()
     build_launches = _lib.launch_count
     for _ in range(steps):
