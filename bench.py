@@ -890,8 +890,7 @@ def run_gpu_arm(args) -> None:
             "kernel": "bm25_fast_kernel<FILTER> (batched float32 filter pass: dense head columns in shared memory + "
                       "tail postings scattered per query)",
             "bound": "hbm", "achieved": index_bytes / (b_filter * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-            "limiter": "instruction issue + shared-memory pipe (IPC 2.3 of 4, LSU wavefronts 51 %: "
-                       "profiles/r2_ncu_full_summary.md), not HBM: the batch shares one pass over the index",
+            "limiter": "the latency of each warp's dependent chain at 8 warps per scheduler (ncu: IPC 2.7, issue active 68 %, LSU wavefronts 52 %: profiles/r2_ncu_full_summary.md), not HBM: the batch shares one pass over the index",
             "frac": index_bytes / (b_filter * 1e-3) / 1e9 / pk["hbm_gbs"], "launch_ms": b_filter,
             "share_of_step": b_filter / ms_per_step,
             "traffic": _traffic("bm25_fast_kernel_filter", f"{n_local}x{v}x{nq}"),

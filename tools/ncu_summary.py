@@ -13,7 +13,7 @@ import sys
 SHAPES = {  # kernel substring -> (traffic key, shape key) at BASELINE config 3 on one GPU
     "tc_i8_search_kernel<0>": ("tc_i8_search_kernel_filter", "1000000x768x1024"),
     "bm25_fast_kernel<0>": ("bm25_fast_kernel_filter", "1000000x50000x1024"),
-    "rescore_ring_kernel<0>": ("rescore_ring_kernel_f32", "1024x400x768"),
+    "rescore_ring_kernel<0, 0>": ("rescore_ring_kernel_f32", "1024x400x768"),
 }
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
