@@ -79,7 +79,10 @@ struct BfArgs {
   int q_len;
   int stride;        // this pass visits tiles 0, stride, 2*stride, ...
   int n_pass_tiles;
-  int q_groups;      // a tile's queries are split over this many work items (small shards: fewer tiles than SMs)
+  int n_full;        // the first n_full tiles of the pass (a multiple of the grid) are one work item each;
+  int q_groups;      // the queries of each remaining tile are split over q_groups work items, so that the last,
+                     // partial round of tiles keeps every SM busy (and small shards with fewer tiles than SMs too)
+  int n_items;       // n_full + (n_pass_tiles - n_full) * q_groups
   u32* lane_max;     // SAMPLE out: [q][n_pass_tiles * 32] keys ~orderable(max), 0xFFFFFFFF = none
   const float* tau;  // FILTER in:  [q]
   u32* list_cnt;     // FILTER out: [q]
@@ -133,11 +136,16 @@ __global__ void __launch_bounds__(BF_THREADS, 1) bm25_fast_kernel(const BfArgs a
   const float hmax = (lane < a.n_head) ? __ldg(a.head_max + lane) : 0.0f;            // slot lane
   const float hmax_hi = (32 + lane < a.n_head) ? __ldg(a.head_max + 32 + lane) : 0.0f;  // slot 32 + lane
 
-  for (int w = blockIdx.x; w < a.n_pass_tiles * a.q_groups; w += gridDim.x) {
-    const int pt = w / a.q_groups;
-    const int grp = w - pt * a.q_groups;
-    const int q_lo = (int)((long long)a.q * grp / a.q_groups);
-    const int q_hi = (int)((long long)a.q * (grp + 1) / a.q_groups);
+  for (int w = blockIdx.x; w < a.n_items; w += gridDim.x) {
+    int pt = w, grp = 0, ng = 1;
+    if (w >= a.n_full) {
+      const int r = w - a.n_full;
+      pt = a.n_full + r / a.q_groups;
+      grp = r - (pt - a.n_full) * a.q_groups;
+      ng = a.q_groups;
+    }
+    const int q_lo = (int)((long long)a.q * grp / ng);
+    const int q_hi = (int)((long long)a.q * (grp + 1) / ng);
     const int tile = pt * a.stride;
     const long long tile_lo = (long long)tile * T;
     const int rows_here = (int)min((long long)T, a.n_docs - tile_lo);
@@ -393,7 +401,13 @@ struct BrArgs {
 };
 
 constexpr int BR_THREADS = 256;
-constexpr int BR_CAND_CAP = 2048;  // exact-scored candidates per query
+#ifndef RR_BR_CAND_CAP
+#define RR_BR_CAND_CAP 2048
+#endif
+#ifndef RR_BR_CHUNK
+#define RR_BR_CHUNK 256
+#endif
+constexpr int BR_CAND_CAP = RR_BR_CAND_CAP;  // exact-scored candidates per query
 
 // Phase B.  The survivor list of a query holds every document with float32 score A >= tau_q
 // (about s * k' of them).  Only those that can still reach the top-k are scored exactly:
@@ -532,15 +546,33 @@ static inline int bf_max_head(int tile_docs) {
   if (h > BF_MAX_HEAD) h = BF_MAX_HEAD;
   return h < 0 ? 0 : (int)h;
 }
-// Small shards have fewer tiles than SMs (a pass visits 123 tiles of a 125k-document shard, its
-// sample pass 21): a tile's queries are then split over several work items, each of which stages
-// the tile's columns itself, so that every SM has work and the items are a few per SM.
-static inline int bf_query_groups(int n_pass_tiles, int q, int sms) {
-  if (n_pass_tiles >= 2 * sms) return 1;
-  int g = (3 * sms + n_pass_tiles - 1) / n_pass_tiles;
-  const int max_g = q / (2 * BF_WARPS) > 1 ? q / (2 * BF_WARPS) : 1;  // at least two queries per warp
-  if (g > max_g) g = max_g;
-  return g < 1 ? 1 : g;
+// Work items of a pass: whole tiles while they fill complete rounds of the grid; the tiles of the last,
+// partial round (all tiles of a small shard) are split by queries into g items each, g minimising
+//   rounds of items per CTA x (query rounds per item + staging of the tile's columns ~ half a query round).
+// (Measured before: 977 tiles on 148 SMs cost exactly what 1036 tiles cost - 7 rounds - and 888 tiles 6/7 of it.)
+struct BfItems {
+  int n_full, groups, n_items;
+};
+static inline BfItems bf_plan_items(int n_pass_tiles, int q, int sms) {
+  BfItems it;
+  it.n_full = (n_pass_tiles / sms) * sms;
+  const int rem = n_pass_tiles - it.n_full;
+  it.groups = 1;
+  if (rem > 0) {
+    const int max_g = q / (2 * BF_WARPS) > 1 ? q / (2 * BF_WARPS) : 1;  // at least two queries per warp
+    double best = 1e30;
+    for (int g = 1; g <= max_g && g <= 64; ++g) {
+      const int rounds = (rem * g + sms - 1) / sms;
+      const int qr = ((q + g - 1) / g + BF_WARPS - 1) / BF_WARPS;
+      const double cost = (double)rounds * ((double)qr + 0.5);
+      if (cost < best - 1e-9) {
+        best = cost;
+        it.groups = g;
+      }
+    }
+  }
+  it.n_items = it.n_full + rem * it.groups;
+  return it;
 }
 // the bound is a score that k' DISTINCT sampled documents reach (one per lane), so at least k' >= k
 // documents survive the filter; a few extra keep the k-th exact score clear of the bound
@@ -697,10 +729,12 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   if (stride > 0) {
     a.stride = stride;
     a.n_pass_tiles = (n_tiles + stride - 1) / stride;
-    a.q_groups = bf_query_groups(a.n_pass_tiles, q, sms);
+    const BfItems it = bf_plan_items(a.n_pass_tiles, q, sms);
+    a.n_full = it.n_full;
+    a.q_groups = it.groups;
+    a.n_items = it.n_items;
     RR_CUDA(cudaFuncSetAttribute(bm25_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int items = a.n_pass_tiles * a.q_groups;
-    const int grid = items < sms ? items : sms;
+    const int grid = it.n_items < sms ? it.n_items : sms;
     bm25_fast_kernel<true><<<grid, BF_THREADS, smem, st>>>(a);
     RR_LAUNCH_CHECK();
     bf_mark(1, st);
@@ -714,11 +748,13 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   bf_mark(2, st);
   a.stride = 1;
   a.n_pass_tiles = n_tiles;
-  a.q_groups = bf_query_groups(n_tiles, q, sms);
   RR_CUDA(cudaFuncSetAttribute(bm25_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
-    const int items = n_tiles * a.q_groups;
-    const int grid = items < sms ? items : sms;
+    const BfItems it = bf_plan_items(n_tiles, q, sms);
+    a.n_full = it.n_full;
+    a.q_groups = it.groups;
+    a.n_items = it.n_items;
+    const int grid = it.n_items < sms ? it.n_items : sms;
     bm25_fast_kernel<false><<<grid, BF_THREADS, smem, st>>>(a);
     RR_LAUNCH_CHECK();
   }
@@ -744,7 +780,7 @@ extern "C" int rr_bm25_topk_fast(const int64_t* tile_term_ptr, const uint32_t* p
   if (r.sel_cap > 2048) r.sel_cap = 2048;
   while (r.sel_cap < k) r.sel_cap <<= 1;
   r.chunk = (int)((32 * 1024) / ((size_t)q_len * 8));
-  if (r.chunk > 256) r.chunk = 256;
+  if (r.chunk > RR_BR_CHUNK) r.chunk = RR_BR_CHUNK;
   if (r.chunk < 1) r.chunk = 1;
   r.row_base = row_base;
   // float32 arithmetic: (q_len + 4) * 2^-24; float16 head impacts: each within 2^-11 (1 + 2^-12) of

@@ -1,4 +1,6 @@
 #!/bin/bash
-O=gpurun_out/r2/final; mkdir -p $O
-timeout -k 10 400 ncu --set full --clock-control none --import-source on -k "regex:tc_tf32_scan_kernel" --launch-skip 4 -c 2 -f -o $O/exact_tc_scan python tools/exact_tc_profile.py > $O/ncu_exact2.log 2>&1; echo "ncu-exact $?"
-tail -3 $O/ncu_exact2.log
+timeout -k 10 300 python -m pytest tests/test_gpu_bm25_rrf.py -x -q 2>&1 | tail -3
+for v in "" _rf; do
+  echo "variant '$v'"; RR_B200_LIB=$PWD/radiant-rag_b200/librr_b200$v.so timeout -k 10 200 python tools/bm25_probe.py 1000000 1024 5 2>&1 | tail -1 | cut -c120-420
+done
+RR_B200_LIB=$PWD/radiant-rag_b200/librr_b200.so timeout -k 10 200 python tools/bm25_probe.py 125000 1024 5 2>&1 | tail -1 | cut -c120-420
