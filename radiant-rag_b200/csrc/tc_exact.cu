@@ -551,7 +551,7 @@ extern "C" int rr_exact_search_f32_tc(const float* emb, const float* row_inv_nor
                                (int)list_smem));
   tc_select_lists_kernel<MERGE_F32_DESC><<<q, LIST_THREADS, list_smem, st>>>(
       a.cnt, (const int*)(w + p.off_key), a.list_row, p.ctas_x, p.cap_cta, top_k, kcap, dim, nullptr, nullptr, row_base,
-      out_score, (long long*)out_idx, out_count, overflow, overflow_flags);
+      out_score, (long long*)out_idx, out_count, overflow, overflow_flags, 1);
   RR_LAUNCH_CHECK();
   return RR_OK;
 }

@@ -15,13 +15,13 @@ constexpr int TC_PACKED_SCALE = 255;  // packed-mode score = 255 * (popc(q) - ha
 // exact top-k of each query's filtered list segments, (score desc, row asc)
 constexpr int LIST_THREADS = 512;
 constexpr int LIST_STAGE_CAP = 6144;  // list entries of one query staged in shared memory (48 KB)
-template <int MODE>  // MERGE_I32_DESC: scores as is; MERGE_HAMMING: dist = popc(q) - score / 255;
+template <int MODE>  // MERGE_I32_DESC: scores as is; MERGE_HAMMING: dist = popc(q) - score / hamming_scale;
                      // MERGE_F32_DESC: list_score holds ~orderable(float32) keys (0xFFFFFFFF = dropped by the refine)
 __global__ void __launch_bounds__(LIST_THREADS, 2)
     tc_select_lists_kernel(const u32* cnt, const int* list_score, const u32* list_row, int n_cta, int cap_cta,
                            int k, int kcap, int dim, const int8_t* q_pm1, const int* tau, long long row_base,
                            void* out_a, long long* out_idx, int* out_count, unsigned* overflow,
-                           unsigned char* overflow_flags) {
+                           unsigned char* overflow_flags, int hamming_scale) {
   extern __shared__ __align__(16) unsigned char merge_smem[];
   u64* s_k1 = reinterpret_cast<u64*>(merge_smem);
   u32* s_k2 = reinterpret_cast<u32*>(s_k1 + kcap);
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(LIST_THREADS, 2)
       out_idx[o] = j < m ? (long long)s_k2[j] + row_base : -1;
     } else if (j < m) {
       const int s = i32_from_orderable((u32)(~s_k1[j])) + tc_tau_eff(tau[q]);  // lists hold score - tau_eff
-      reinterpret_cast<int*>(out_a)[o] = (MODE == MERGE_HAMMING) ? s_qpop - s / TC_PACKED_SCALE : s;
+      reinterpret_cast<int*>(out_a)[o] = (MODE == MERGE_HAMMING) ? s_qpop - s / hamming_scale : s;
       out_idx[o] = (long long)s_k2[j] + row_base;
     } else {
       reinterpret_cast<int*>(out_a)[o] = (MODE == MERGE_HAMMING) ? 0x7fffffff : (int)0x80000000;

@@ -776,11 +776,11 @@ static int tc_search(const int8_t* emb, const uint8_t* packed_codes, long long n
   if (hamming)
     tc_select_lists_kernel<MERGE_HAMMING><<<q, LIST_THREADS, list_smem, st>>>(
         a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, queries, (const int*)(w + p.off_tau), row_base, out_a,
-        out_idx, nullptr, overflow_out, overflow_flags);
+        out_idx, nullptr, overflow_out, overflow_flags, TC_PACKED_SCALE);
   else
     tc_select_lists_kernel<MERGE_I32_DESC><<<q, LIST_THREADS, list_smem, st>>>(
         a.cnt, a.list_score, a.list_row, ctas_x, p.cap_cta, k, kcap, dim, queries, (const int*)(w + p.off_tau), row_base, out_a,
-        out_idx, nullptr, overflow_out, overflow_flags);
+        out_idx, nullptr, overflow_out, overflow_flags, TC_PACKED_SCALE);
   RR_LAUNCH_CHECK();
   tc_mark(4, st);
   g_tc_timed = g_tc_timing && g_tc_ev_ready;
