@@ -290,6 +290,33 @@ class DenseIndex:
         if tag != LEVEL_CHILD:
             self.tags_uniform = False
 
+    def delete_row(self, row: int) -> Optional[int]:
+        """Remove one row by moving the LAST row into its slot (the arrays stay dense).  Returns the old
+        index of the row that moved (``n - 1`` before the call), or None when the last row itself was
+        removed.  Keeps the cached row norms of the exact tensor-core scan consistent."""
+        self._activate()
+        if not 0 <= row < self.n:
+            raise IndexError(f"row {row} outside [0, {self.n})")
+        last = self.n - 1
+        moved = None
+        if row != last:
+            self.codes[row].copy_(self.codes[last])
+            self.tags[row] = self.tags[last]
+            if self.int8 is not None:
+                self.int8[row].copy_(self.int8[last])
+            if self.f32 is not None:
+                self.f32[row].copy_(self.f32[last])
+            if self._inv_norm is not None and row < self._inv_norm_n:
+                if last < self._inv_norm_n:
+                    self._inv_norm[row] = self._inv_norm[last]
+                else:  # the moved row's norm was not cached yet
+                    _lib.call("rr_row_inv_norms_f32", self.f32[row:row + 1].data_ptr(), 1, self.dim,
+                              self._inv_norm[row:row + 1].data_ptr(), _stream())
+            moved = last
+        self.n = last
+        self._inv_norm_n = min(self._inv_norm_n, self.n)
+        return moved
+
     def set_tag(self, row: int, tag: int) -> None:
         self.tags[row] = tag
         if tag != LEVEL_CHILD:

@@ -282,20 +282,12 @@ class B200VectorStore(BaseVectorStore):
             self._docs.pop(doc_id, None)
             row = self._row_of.pop(doc_id, None)
             if row is not None:
-                idx = self._index
-                last = idx.n - 1
-                if row != last:  # swap-with-last keeps the arrays dense
-                    idx.codes[row].copy_(idx.codes[last])
-                    idx.tags[row] = idx.tags[last]
-                    if idx.int8 is not None:
-                        idx.int8[row].copy_(idx.int8[last])
-                    if idx.f32 is not None:
-                        idx.f32[row].copy_(idx.f32[last])
-                    moved = self._id_of[last]
+                moved_from = self._index.delete_row(row)  # swap-with-last keeps the arrays dense
+                if moved_from is not None:
+                    moved = self._id_of[moved_from]
                     self._id_of[row] = moved
                     self._row_of[moved] = row
                 self._id_of.pop()
-                idx.n = last
             return found
 
     # ---- reads -------------------------------------------------------------------------

@@ -116,6 +116,26 @@ def test_exact_tc_row_updates_refresh_the_cached_norms():
     assert not torch.equal(before[0], after[0])
 
 
+def test_exact_tc_row_deletes_keep_the_cached_norms_consistent():
+    """delete_row moves the last row into the hole; a later add reuses the freed slot at the end.  The cached
+    1/|row| values must follow (a stale one would silently steer the filter wrong)."""
+    require_gpu()
+    n, dim, nq = 20_000, 128, 9
+    corpus = synthetic.hash_rows_f32(0, n, dim, seed=23)
+    corpus[n - 1] *= np.float32(1e3)   # the row that will move has a very different norm from the one it replaces
+    queries = synthetic.hash_query_rows_f32(0, nq, dim, seed=23, n_corpus=n)
+    idx, _ = build_index(corpus, int8=False, f32=True)
+    idx.search_exact(queries, 5, 0.0, use_tc=True)          # norms cached for all n rows
+    assert idx.delete_row(77) == n - 1 and idx.n == n - 1
+    got = idx.search_exact(queries, 5, 0.0, use_tc=True)
+    assert _same(got, idx.search_exact(queries, 5, 0.0, use_tc=False))
+    idx.add(queries[4:5] * np.float32(1e-4))                 # lands in slot n - 1: tiny norm, best match of query 4
+    got = idx.search_exact(queries, 5, 0.0, use_tc=True)
+    assert _same(got, idx.search_exact(queries, 5, 0.0, use_tc=False))
+    assert int(got[0][4, 0]) == n - 1
+    assert idx.delete_row(idx.n - 1) is None and idx.n == n - 1   # removing the last row moves nothing
+
+
 def test_exact_tc_at_size_properties():
     """1M x 768 (BASELINE config 2/3 corpus), 64 queries, device-generated: bit-identical to the
     CUDA-core scan, and every query finds the row it was derived from first."""
