@@ -288,7 +288,9 @@ int rr_merge_hamming(const int32_t* in_dist, const int64_t* in_idx, int32_t q, i
 /* One-collective form of the Hamming exchange: rr_pack_hamming turns a shard's (dist, global row)
  * lists into int64 keys (dist << 40 | row, -1 = padding) so that ONE all_gather moves them;
  * rr_merge_hamming_gathered merges the gathered buffer in its native layout
- * in_keys i64 [n_shards][q][k_in] (no transpose) by (dist asc, row asc) -> [q, k]. */
+ * in_keys i64 [n_shards][q][k_in] (no transpose) by (dist asc, row asc) -> [q, k].  Every shard's k_in
+ * keys must be in ASCENDING order with the padding last - the order rr_hamming_topk / rr_hamming_topk_tc
+ * return and rr_pack_hamming keeps (the merge is a tree of sorted-list merges). */
 int rr_pack_hamming(const int32_t* dist, const int64_t* idx, int64_t n, int64_t* out_keys,
                     void* stream);
 int rr_merge_hamming_gathered(const int64_t* in_keys, int32_t n_shards, int32_t q, int32_t k_in,

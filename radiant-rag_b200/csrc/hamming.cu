@@ -509,6 +509,62 @@ __global__ void __launch_bounds__(MERGE_THREADS)
   }
 }
 
+// The same merge for SORTED shard lists (what rr_hamming_topk* + rr_pack_hamming leave: ascending keys, padding
+// last): a tree of bitonic top-P merges instead of a radix select + full sort.  Lists are padded to P = 2^p
+// >= k_in entries (+inf keys) and to G2 = 2^g >= n_shards lists in shared memory; one level merges list pairs
+// in place: C[i] = min(A[i], B[P-1-i]) holds the P smallest of A u B as a bitonic sequence, log2(P) compare-
+// exchange stages sort it.  log2(G2) * (1 + log2(P)) barriers in all (30 for 8 x 512) against several radix
+// passes over every entry plus a 45-stage sort.
+__global__ void __launch_bounds__(MERGE_THREADS)
+    merge_hamming_tree_kernel(const long long* keys, int n_shards, int g2, int q_total, int k_in, int p_len, int k,
+                              int* out_dist, long long* out_idx) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  u64* s = reinterpret_cast<u64*>(merge_smem);  // [g2][p_len]
+  const int q = blockIdx.x;
+  const int p_mask = p_len - 1;
+  const int p_shift = 31 - __clz(p_len);
+  for (int i = threadIdx.x; i < g2 * p_len; i += MERGE_THREADS) {
+    const int g = i >> p_shift, j = i & p_mask;
+    u64 v = ~0ull;
+    if (g < n_shards && j < k_in) {
+      const long long key = keys[((size_t)g * q_total + q) * k_in + j];
+      if (key >= 0) v = (u64)key;
+    }
+    s[i] = v;
+  }
+  __syncthreads();
+  const int half = p_len >> 1;
+  const int h_shift = p_shift - 1;
+  for (int w = 1; w < g2; w <<= 1) {  // lists at distance w merge into the lower one
+    const int pairs = g2 / (2 * w);
+    for (int i = threadIdx.x; i < pairs * p_len; i += MERGE_THREADS) {
+      const int pr = i >> p_shift, j = i & p_mask;
+      u64* a_list = s + (size_t)(2 * w * pr) * p_len;
+      const u64 a = a_list[j], b = a_list[(size_t)w * p_len + (p_mask - j)];
+      a_list[j] = a < b ? a : b;
+    }
+    __syncthreads();
+    for (int st = half; st > 0; st >>= 1) {
+      for (int i = threadIdx.x; i < pairs * half; i += MERGE_THREADS) {
+        const int pr = i >> h_shift, t = i & (half - 1);
+        const int lo = ((t & ~(st - 1)) << 1) | (t & (st - 1));
+        u64* a_list = s + (size_t)(2 * w * pr) * p_len;
+        const u64 a = a_list[lo], b = a_list[lo + st];
+        if (a > b) {
+          a_list[lo] = b;
+          a_list[lo + st] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int j = threadIdx.x; j < k; j += MERGE_THREADS) {
+    const u64 v = j < p_len ? s[j] : ~0ull;
+    const bool have = v != ~0ull;
+    merge_write<MERGE_HAMMING_PACKED>(out_dist, out_idx, (size_t)q * k + j, have, have ? v : 0, 0u, 0);
+  }
+}
+
 // BM25 lists as the all_gather leaves them: words [n_shards][2][q][k_in], plane 0 = float64 score bits,
 // plane 1 = global row (-1 = padding); (score desc, row asc), score > 0 was applied by the shards
 __global__ void __launch_bounds__(MERGE_THREADS)
@@ -578,6 +634,18 @@ extern "C" int rr_merge_hamming_gathered(const int64_t* in_keys, int32_t n_shard
   if (q == 0) return RR_OK;
   RR_CHECK_ARG(in_keys && out_dist && out_idx, "null pointer");
   RR_CHECK_ARG(q > 0 && n_shards > 0 && k_in > 0 && k >= 1 && k <= RR_MAX_K, "bad size");
+  // sorted shard lists (the documented input): bitonic merge tree when it fits shared memory
+  int p_len = 2, g2 = 1;
+  while (p_len < k_in) p_len <<= 1;
+  while (g2 < n_shards) g2 <<= 1;
+  const size_t tree_smem = (size_t)g2 * p_len * 8;
+  if (k <= p_len && p_len <= 1024 && tree_smem <= 96 * 1024) {
+    RR_CUDA(cudaFuncSetAttribute(merge_hamming_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem));
+    merge_hamming_tree_kernel<<<q, MERGE_THREADS, tree_smem, (cudaStream_t)stream>>>(
+        (const long long*)in_keys, n_shards, g2, q, k_in, p_len, k, out_dist, (long long*)out_idx);
+    RR_LAUNCH_CHECK();
+    return RR_OK;
+  }
   const int cap = merge_cap(k);
   merge_hamming_gathered_kernel<<<q, MERGE_THREADS, (size_t)cap * 12, (cudaStream_t)stream>>>(
       (const long long*)in_keys, n_shards, q, k_in, k, cap, out_dist, (long long*)out_idx);

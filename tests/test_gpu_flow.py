@@ -193,6 +193,35 @@ def test_dense_agent_error_becomes_empty_list():
         DenseRetrievalAgent(None, Broken(), RetrievalConfig())
 
 
+@pytest.mark.parametrize("g,q,k_in,k", [(8, 64, 400, 400),    # config 3 on 8 GPUs: 8 x 512 tree
+                                        (2, 33, 400, 400), (3, 17, 40, 40), (4, 9, 1000, 1000),
+                                        (5, 7, 100, 60),       # fewer wanted than a shard holds
+                                        (1, 5, 50, 50),
+                                        (16, 4, 700, 700)])    # too large for the tree: the select-based kernel
+def test_merge_of_gathered_sorted_hamming_lists(g, q, k_in, k):
+    """rr_merge_hamming_gathered over sorted shard lists with ties, short lists and padding == sorting the union."""
+    require_gpu()
+    from tests.cpu_ops import CpuShardOps
+    rng = np.random.default_rng(g * 1000 + k_in)
+    keys = np.full((g, q, k_in), -1, np.int64)
+    for s_ in range(g):
+        for r in range(q):
+            m = int(rng.integers(0, k_in + 1)) if (s_ + r) % 3 == 0 else k_in   # some lists are short or empty
+            dist = np.sort(rng.integers(200, 230, size=m))                       # few distinct distances: many ties
+            rows = rng.choice(1 << 22, size=m, replace=False).astype(np.int64) + (s_ << 24)
+            kk = np.sort((dist.astype(np.int64) << 40) | rows)
+            keys[s_, r, :m] = kk
+    index = DenseIndexForOps()
+    got_d, got_i = GpuShardOps(index).merge_hamming_gathered(torch.from_numpy(keys).cuda(), k)
+    want_d, want_i = CpuShardOps.merge_hamming_gathered(None, torch.from_numpy(keys), k)
+    assert torch.equal(got_i.cpu(), want_i) and torch.equal(got_d.cpu(), want_d)
+
+
+def DenseIndexForOps():
+    from radiant_rag_b200.index import DenseIndex
+    return DenseIndex(128, device=0, store_int8=False, store_f32=False)
+
+
 def test_row_sharded_emulated_on_one_gpu():
     """SURVEY.md 8e on one device: G shards processed one after the other, their lists
     concatenated exactly as the all_gather lays them out, merged by the product kernels.
