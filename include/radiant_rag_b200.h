@@ -301,7 +301,8 @@ int rr_merge_scores_f64(const double* in_score, const int64_t* in_idx, int32_t q
                         int32_t* out_count, void* stream);
 /* One-collective form of the BM25 exchange: every shard writes its lists into ONE buffer of 8-byte
  * words [2][q][k_in] (plane 0 = float64 scores, plane 1 = global rows, -1 = padding), ONE all_gather
- * moves it and this merges the gathered [n_shards][2][q][k_in] buffer where it lies. */
+ * moves it and this merges the gathered [n_shards][2][q][k_in] buffer where it lies.  Every shard's list must
+ * be in (score desc, row asc) order with the padding last, as rr_bm25_topk / rr_bm25_topk_fast return it. */
 int rr_merge_scores_f64_gathered(const int64_t* in_words, int32_t n_shards, int32_t q, int32_t k_in,
                                  int32_t k, double* out_score, int64_t* out_idx, int32_t* out_count,
                                  void* stream);

@@ -596,6 +596,74 @@ __global__ void __launch_bounds__(MERGE_THREADS)
   if (out_count && threadIdx.x == 0) out_count[q] = m;
 }
 
+// The BM25 merge as the same tree of bitonic top-P merges (sorted shard lists: score desc, row asc, padding last),
+// on (key1 = ~orderable(score), key2 = row) pairs
+__global__ void __launch_bounds__(MERGE_THREADS)
+    merge_f64_tree_kernel(const long long* words, int n_shards, int g2, int q_total, int k_in, int p_len, int k,
+                          double* out_score, long long* out_idx, int* out_count) {
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  u64* s1 = reinterpret_cast<u64*>(merge_smem);          // [g2][p_len]
+  u32* s2 = reinterpret_cast<u32*>(s1 + (size_t)g2 * p_len);  // [g2][p_len]
+  const int q = blockIdx.x;
+  const int p_mask = p_len - 1;
+  const int p_shift = 31 - __clz(p_len);
+  for (int i = threadIdx.x; i < g2 * p_len; i += MERGE_THREADS) {
+    const int g = i >> p_shift, j = i & p_mask;
+    u64 x = K1_INVALID;
+    u32 y = K2_INVALID;
+    if (g < n_shards && j < k_in) {
+      const size_t base = (size_t)g * 2 * q_total * k_in + (size_t)q * k_in + j;
+      const long long row = words[base + (size_t)q_total * k_in];
+      if (row >= 0) {
+        x = ~f64_orderable(__longlong_as_double(words[base]));
+        y = (u32)row;
+      }
+    }
+    s1[i] = x;
+    s2[i] = y;
+  }
+  __syncthreads();
+  const int half = p_len >> 1;
+  const int h_shift = p_shift - 1;
+  for (int w = 1; w < g2; w <<= 1) {
+    const int pairs = g2 / (2 * w);
+    for (int i = threadIdx.x; i < pairs * p_len; i += MERGE_THREADS) {
+      const int pr = i >> p_shift, j = i & p_mask;
+      const size_t ia = (size_t)(2 * w * pr) * p_len + j;
+      const size_t ib = (size_t)(2 * w * pr + w) * p_len + (p_mask - j);
+      if (pair_less(s1[ib], s2[ib], s1[ia], s2[ia])) {
+        s1[ia] = s1[ib];
+        s2[ia] = s2[ib];
+      }
+    }
+    __syncthreads();
+    for (int st = half; st > 0; st >>= 1) {
+      for (int i = threadIdx.x; i < pairs * half; i += MERGE_THREADS) {
+        const int pr = i >> h_shift, t = i & (half - 1);
+        const size_t lo = (size_t)(2 * w * pr) * p_len + (((t & ~(st - 1)) << 1) | (t & (st - 1)));
+        const size_t hi = lo + st;
+        const u64 a1 = s1[lo], b1 = s1[hi];
+        const u32 a2 = s2[lo], b2 = s2[hi];
+        if (pair_less(b1, b2, a1, a2)) {
+          s1[lo] = b1;
+          s2[lo] = b2;
+          s1[hi] = a1;
+          s2[hi] = a2;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  int m = 0;
+  for (int j0 = 0; j0 < k; j0 += MERGE_THREADS) {
+    const int j = j0 + threadIdx.x;
+    const bool have = j < k && j < p_len && s1[j] != K1_INVALID;
+    if (j < k) merge_write<MERGE_F64_DESC>(out_score, out_idx, (size_t)q * k + j, have, have ? s1[j] : 0, have ? s2[j] : 0, 0);
+    m += __syncthreads_count(have);
+  }
+  if (out_count && threadIdx.x == 0) out_count[q] = m;
+}
+
 __global__ void __launch_bounds__(256)
     pack_hamming_kernel(const int* dist, const long long* idx, long long n, long long* out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -659,6 +727,17 @@ extern "C" int rr_merge_scores_f64_gathered(const int64_t* in_words, int32_t n_s
   if (q == 0) return RR_OK;
   RR_CHECK_ARG(in_words && out_score && out_idx, "null pointer");
   RR_CHECK_ARG(q > 0 && n_shards > 0 && k_in > 0 && k >= 1 && k <= RR_MAX_K, "bad size");
+  int p_len = 2, g2 = 1;
+  while (p_len < k_in) p_len <<= 1;
+  while (g2 < n_shards) g2 <<= 1;
+  const size_t tree_smem = (size_t)g2 * p_len * 12;
+  if (k <= p_len && p_len <= 1024 && tree_smem <= 96 * 1024) {  // sorted shard lists: bitonic merge tree
+    RR_CUDA(cudaFuncSetAttribute(merge_f64_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tree_smem));
+    merge_f64_tree_kernel<<<q, MERGE_THREADS, tree_smem, (cudaStream_t)stream>>>(
+        (const long long*)in_words, n_shards, g2, q, k_in, p_len, k, out_score, (long long*)out_idx, out_count);
+    RR_LAUNCH_CHECK();
+    return RR_OK;
+  }
   const int cap = merge_cap(k);
   merge_f64_gathered_kernel<<<q, MERGE_THREADS, (size_t)cap * 12, (cudaStream_t)stream>>>(
       (const long long*)in_words, n_shards, q, k_in, k, cap, out_score, (long long*)out_idx, out_count);

@@ -321,6 +321,43 @@ def test_bm25_row_sharded_one_collective_merge_emulated():
         assert score[qi, :m].cpu().tolist() == sc.tolist(), qi
 
 
+@pytest.mark.parametrize("g,q,k_in,k", [(8, 48, 100, 100), (2, 9, 100, 100), (4, 5, 1000, 1000), (3, 7, 40, 25),
+                                        (16, 3, 900, 900)])   # too large for the merge tree: the select-based kernel
+def test_merge_of_gathered_sorted_bm25_lists(g, q, k_in, k):
+    """rr_merge_scores_f64_gathered over sorted shard lists (exact score ties across shards, short lists,
+    padding) == sorting the union by (score desc, row asc)."""
+    require_gpu()
+    from radiant_rag_b200.index import DenseIndex
+    from radiant_rag_b200.sharded import GpuShardOps
+
+    rng = np.random.default_rng(g * 100 + k_in)
+    words = np.zeros((g, 2, q, k_in), np.int64)
+    words[:, 1] = -1
+    pool = rng.random(64) * 20.0 + 0.5           # few distinct scores: ties within and across shards
+    for s_ in range(g):
+        for r in range(q):
+            m = int(rng.integers(0, k_in + 1)) if (s_ + r) % 3 == 0 else k_in
+            sc = rng.choice(pool, size=m)
+            rows = rng.choice(1 << 20, size=m, replace=False).astype(np.int64) + (s_ << 22)
+            order = np.lexsort((rows, -sc))
+            words[s_, 0, r, :m] = sc[order].view(np.int64)
+            words[s_, 1, r, :m] = rows[order]
+    ops = GpuShardOps(DenseIndex(32, device=0, store_int8=False, store_f32=False))
+    idx, score, count = ops.merge_scores_f64_gathered(torch.from_numpy(words).cuda(), k)
+    torch.cuda.synchronize()
+    for r in range(q):
+        rows = words[:, 1, r, :].reshape(-1)
+        sc = words[:, 0, r, :].reshape(-1).view(np.float64)
+        keep = rows >= 0
+        rows, sc = rows[keep], sc[keep]
+        order = np.lexsort((rows, -sc))[:k]
+        m = int(count[r])
+        assert m == order.size, r
+        assert idx[r, :m].cpu().tolist() == rows[order].tolist(), r
+        assert score[r, :m].cpu().numpy().tolist() == sc[order].tolist(), r
+        assert (idx[r, m:].cpu().numpy() == -1).all()
+
+
 def test_bm25_incremental_adds_refresh_the_device_index_instead_of_rebuilding():
     """``add_document`` is O(document) in the reference; here the device index of the
     documents already indexed keeps its sorted postings - its impacts are re-evaluated in place from
